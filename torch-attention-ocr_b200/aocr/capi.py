@@ -1,0 +1,267 @@
+"""ctypes binding of include/aocr.h (the Python twin of lua/aocr_ffi.lua)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+GROUPS = ["cnn", "enc_fw", "enc_bw", "decoder", "proj"]   # src/model/model.lua:150
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.environ.get("AOCR_LIB", os.path.join(os.path.dirname(_HERE), "lib", "libaocr.so"))
+
+
+class AocrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libaocr error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class AocrConfig(C.Structure):
+    _fields_ = [("batch_size", C.c_int32), ("max_encoder_l", C.c_int32), ("max_decoder_l", C.c_int32),
+                ("encoder_num_hidden", C.c_int32), ("encoder_num_layers", C.c_int32),
+                ("decoder_num_layers", C.c_int32), ("target_vocab_size", C.c_int32),
+                ("target_embedding_size", C.c_int32), ("input_feed", C.c_int32), ("dropout", C.c_float),
+                ("learning_rate", C.c_float), ("dp_rank", C.c_int32), ("dp_world", C.c_int32),
+                ("global_batch", C.c_int32), ("gemm_mode", C.c_int32)]
+
+
+_SYMBOLS = {
+    "aocr_create": (C.c_int, [C.POINTER(AocrConfig), C.c_int, C.POINTER(C.c_void_p)]),
+    "aocr_destroy": (None, [C.c_void_p]),
+    "aocr_last_error": (C.c_char_p, [C.c_void_p]),
+    "aocr_param_groups": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "aocr_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "aocr_get_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "aocr_get_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "aocr_set_bn_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "aocr_get_bn_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "aocr_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.POINTER(C.c_double)]),
+    "aocr_group_norms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "aocr_sgd_update": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "aocr_grad_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "aocr_param_axpy": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "aocr_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_double, C.POINTER(C.c_double)]),
+    "aocr_decode_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_int32)]),
+    "aocr_get_logprobs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "aocr_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "aocr_stage_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "aocr_train_step_staged": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double)]),
+    "aocr_decode_greedy_staged": (C.c_int, [C.c_void_p, C.c_int]),
+    "aocr_grad_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "aocr_group_extent": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "aocr_forward_backward_staged": (C.c_int, [C.c_void_p]),
+    "aocr_sgd_update_async": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "aocr_read_loss": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "aocr_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "aocr_synchronize": (C.c_int, [C.c_void_p]),
+    "aocr_launch_count": (C.c_int64, [C.c_void_p]),
+    "aocr_prof_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "aocr_prof_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_double)]),
+}
+
+
+def exported_symbols():
+    return sorted(_SYMBOLS)
+
+
+class Lib:
+    """Loaded libaocr.so with typed prototypes.  Raises if the library is missing (no fallback)."""
+    _inst = None
+
+    def __init__(self, path=None):
+        path = path or lib_path()
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build it with `python __graft_entry__.py` / `make -C torch-attention-ocr_b200` "
+                "(the hot path has no CPU or PyTorch fallback)")
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in _SYMBOLS.items():
+            fn = getattr(self.dll, name)
+            fn.restype = res
+            fn.argtypes = args
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = Lib()
+        return cls._inst
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Handle:
+    """RAII wrapper of one aocr_handle; methods map 1:1 onto the C ABI."""
+
+    def __init__(self, cfg: AocrConfig, device=0):
+        self.lib = Lib.get()
+        self.h = C.c_void_p()
+        rc = self.lib.dll.aocr_create(C.byref(cfg), device, C.byref(self.h))
+        if rc != 0:
+            raise AocrError(rc, self.lib.dll.aocr_last_error(None).decode())
+        self.cfg = cfg
+        n = C.c_int32()
+        sizes = (C.c_int64 * 5)()
+        self._ck(self.lib.dll.aocr_param_groups(self.h, C.byref(n), sizes))
+        self.group_sizes = [int(s) for s in sizes]
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise AocrError(rc, self.lib.dll.aocr_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.dll.aocr_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters
+    def set_params(self, group, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        self._ck(self.lib.dll.aocr_set_params(self.h, group, _ptr(a), a.size))
+
+    def get_params(self, group):
+        a = np.empty(self.group_sizes[group], np.float32)
+        self._ck(self.lib.dll.aocr_get_params(self.h, group, _ptr(a), a.size))
+        return a
+
+    def get_grads(self, group):
+        a = np.empty(self.group_sizes[group], np.float32)
+        self._ck(self.lib.dll.aocr_get_grads(self.h, group, _ptr(a), a.size))
+        return a
+
+    def set_bn_stats(self, layer, mean, var):
+        m = np.ascontiguousarray(mean, dtype=np.float32)
+        v = np.ascontiguousarray(var, dtype=np.float32)
+        self._ck(self.lib.dll.aocr_set_bn_stats(self.h, layer, _ptr(m), _ptr(v), m.size))
+
+    def get_bn_stats(self, layer):
+        n = 256 if layer == 0 else 512
+        m, v = np.empty(n, np.float32), np.empty(n, np.float32)
+        self._ck(self.lib.dll.aocr_get_bn_stats(self.h, layer, _ptr(m), _ptr(v), n))
+        return m, v
+
+    # ---- steps
+    @staticmethod
+    def _batch(images, targets, targets_eval):
+        img = np.ascontiguousarray(images, dtype=np.float32)
+        tg = np.ascontiguousarray(targets, dtype=np.int32)
+        te = np.ascontiguousarray(targets_eval, dtype=np.int32)
+        assert img.ndim == 4 and img.shape[1] == 1 and img.shape[2] == 32, "images must be (b,1,32,W)"
+        assert tg.shape == te.shape and tg.shape[0] == img.shape[0]
+        return img, tg, te, img.shape[0], img.shape[3], tg.shape[1]
+
+    def forward_backward(self, images, targets, targets_eval):
+        img, tg, te, b, W, T = self._batch(images, targets, targets_eval)
+        loss = C.c_double()
+        self._ck(self.lib.dll.aocr_forward_backward(self.h, _ptr(img), b, W, _ptr(tg), _ptr(te), T, C.byref(loss)))
+        return loss.value
+
+    def train_step(self, images, targets, targets_eval, lr):
+        img, tg, te, b, W, T = self._batch(images, targets, targets_eval)
+        loss = C.c_double()
+        self._ck(self.lib.dll.aocr_train_step(self.h, _ptr(img), b, W, _ptr(tg), _ptr(te), T, lr, C.byref(loss)))
+        return loss.value
+
+    def group_norms(self):
+        pn, gn = (C.c_double * 5)(), (C.c_double * 5)()
+        self._ck(self.lib.dll.aocr_group_norms(self.h, pn, gn))
+        return list(pn), list(gn)
+
+    def sgd_update(self, lr, clip=5.0):
+        self._ck(self.lib.dll.aocr_sgd_update(self.h, lr, clip))
+
+    def grad_scale(self, group, s):
+        self._ck(self.lib.dll.aocr_grad_scale(self.h, group, s))
+
+    def param_axpy(self, group, a):
+        self._ck(self.lib.dll.aocr_param_axpy(self.h, group, a))
+
+    def decode_greedy(self, images, targets, targets_eval):
+        img, tg, te, b, W, T = self._batch(images, targets, targets_eval)
+        Ld = self.cfg.max_decoder_l
+        labels = np.empty((b, Ld), np.int32)
+        pred, gold = np.empty(b, np.float64), np.empty(b, np.float64)
+        loss, nc = C.c_double(), C.c_int32()
+        self._ck(self.lib.dll.aocr_decode_greedy(self.h, _ptr(img), b, W, _ptr(tg), _ptr(te), T, _ptr(labels),
+                                                 _ptr(pred), _ptr(gold), C.byref(loss), C.byref(nc)))
+        return {"labels": labels, "pred_scores": pred, "gold_scores": gold, "loss_sum": loss.value,
+                "num_correct": nc.value}
+
+    def get_logprobs(self, which, rows):
+        a = np.empty((rows, self.cfg.target_vocab_size), np.float32)
+        self._ck(self.lib.dll.aocr_get_logprobs(self.h, which, _ptr(a), a.size))
+        return a
+
+    def debug_read(self, name, shape):
+        a = np.empty(shape, np.float32)
+        self._ck(self.lib.dll.aocr_debug_read(self.h, name.encode(), _ptr(a), a.size))
+        return a
+
+    # ---- device-resident path
+    def stage_batch(self, images, targets, targets_eval):
+        img, tg, te, b, W, T = self._batch(images, targets, targets_eval)
+        self._ck(self.lib.dll.aocr_stage_batch(self.h, _ptr(img), b, W, _ptr(tg), _ptr(te), T))
+
+    def train_step_staged(self, lr, sync=True):
+        loss = C.c_double()
+        self._ck(self.lib.dll.aocr_train_step_staged(self.h, lr, 1 if sync else 0, C.byref(loss)))
+        return loss.value if sync else None
+
+    def decode_greedy_staged(self, sync=True):
+        self._ck(self.lib.dll.aocr_decode_greedy_staged(self.h, 1 if sync else 0))
+
+    def forward_backward_staged(self):
+        self._ck(self.lib.dll.aocr_forward_backward_staged(self.h))
+
+    def sgd_update_async(self, lr, clip=5.0):
+        self._ck(self.lib.dll.aocr_sgd_update_async(self.h, lr, clip))
+
+    def read_loss(self):
+        loss = C.c_double()
+        self._ck(self.lib.dll.aocr_read_loss(self.h, C.byref(loss)))
+        return loss.value
+
+    def grad_buffer(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.dll.aocr_grad_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def group_extent(self, group):
+        o, n = C.c_int64(), C.c_int64()
+        self._ck(self.lib.dll.aocr_group_extent(self.h, group, C.byref(o), C.byref(n)))
+        return o.value, n.value
+
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(self.lib.dll.aocr_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def synchronize(self):
+        self._ck(self.lib.dll.aocr_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.dll.aocr_launch_count(self.h))
+
+    def prof_enable(self, on=True):
+        self._ck(self.lib.dll.aocr_prof_enable(self.h, 1 if on else 0))
+
+    def prof_read(self, cls):
+        ms, n, w = C.c_double(), C.c_int64(), C.c_double()
+        self._ck(self.lib.dll.aocr_prof_read(self.h, cls, C.byref(ms), C.byref(n), C.byref(w)))
+        return ms.value, n.value, w.value

@@ -1,0 +1,485 @@
+// engine.cu — step scheduler: the reference's feval (src/model/model.lua:284-695) as a fixed launch
+// sequence on one CUDA stream.  No host synchronisation inside a step; the loss scalar, greedy labels
+// and scores are read back once at the end (the reference syncs every decoder step, model.lua:403,612).
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace aocr {
+
+const ConvSpec kConv[7] = {
+    // cin cout k pad bn pool_kw          (src/model/cnn.lua:12-42)
+    {1, 64, 3, 1, -1, 2},   {64, 128, 3, 1, -1, 2}, {128, 256, 3, 1, 0, 0}, {256, 256, 3, 1, -1, 1},
+    {256, 512, 3, 1, 1, 0}, {512, 512, 3, 1, -1, 1}, {512, 512, 2, 0, 2, 0},
+};
+
+namespace {
+// Wt[ci][k*k-1-tap][co] = W[co][tap][ci]  (flipped taps, in/out swapped): the data-gradient weight.
+__global__ void conv_wt_kernel(const float* __restrict__ W, float* __restrict__ Wt, int cout, int kk, int cin) {
+  const int64_t total = (int64_t)cout * kk * cin;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(e % cout);
+    int64_t r = e / cout;
+    int tp = (int)(r % kk);
+    int ci = (int)(r / kk);
+    Wt[e] = W[((int64_t)co * kk + (kk - 1 - tp)) * cin + ci];
+  }
+}
+}  // namespace
+
+template <typename T>
+T* Engine::alloc(int64_t n) {
+  void* p = nullptr;
+  size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(T);
+  bytes = (bytes + 255) & ~(size_t)255;
+  AOCR_CUDA(cudaMalloc(&p, bytes));
+  AOCR_CUDA(cudaMemsetAsync(p, 0, bytes, ctx_.st));
+  allocs_.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+
+void Engine::layout_params() {
+  int64_t off = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += n; return o; };
+  const int in1 = E + (cfg.input_feed ? Hd : 0);
+  // physical order: proj | decoder | enc_fw | enc_bw | cnn
+  L.goff[G_PROJ] = off;
+  L.wo = take((int64_t)V * Hd); L.bo = take(V);
+  L.gsize[G_PROJ] = off - L.goff[G_PROJ];
+  L.goff[G_DEC] = off;
+  L.emb = take((int64_t)V * E);
+  L.l1_wi = take((int64_t)4 * Hd * in1); L.l1_bi = take(4 * Hd);
+  L.l1_wh = take((int64_t)4 * Hd * Hd);  L.l1_bh = take(4 * Hd);
+  L.l2_wi = take((int64_t)4 * Hd * Hd);  L.l2_bi = take(4 * Hd);
+  L.l2_wh = take((int64_t)4 * Hd * Hd);  L.l2_bh = take(4 * Hd);
+  L.wa = take((int64_t)Hd * Hd); L.wc = take((int64_t)Hd * 2 * Hd);
+  L.gsize[G_DEC] = off - L.goff[G_DEC];
+  for (int d = 0; d < 2; d++) {
+    int g = d == 0 ? G_ENC_FW : G_ENC_BW;
+    L.goff[g] = off;
+    L.enc_wi[d] = take((int64_t)4 * He * 512); L.enc_bi[d] = take(4 * He);
+    L.enc_wh[d] = take((int64_t)4 * He * He);  L.enc_bh[d] = take(4 * He);
+    L.gsize[g] = off - L.goff[g];
+  }
+  L.goff[G_CNN] = off;
+  for (int l = 0; l < 7; l++) {
+    const ConvSpec& c = kConv[l];
+    L.conv_w[l] = take((int64_t)c.cout * c.cin * c.k * c.k);
+    L.conv_b[l] = take(c.cout);
+    if (c.bn >= 0) { L.bn_g[c.bn] = take(c.cout); L.bn_b[c.bn] = take(c.cout); }
+  }
+  L.gsize[G_CNN] = off - L.goff[G_CNN];
+  L.total = off;
+}
+
+Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
+  AOCR_CHECK(c.batch_size >= 1 && c.max_encoder_l >= 1 && c.max_decoder_l >= 1, "batch_size/max_*_l must be >= 1");
+  AOCR_CHECK(c.encoder_num_layers == 1 && c.decoder_num_layers == 2,
+             "only encoder_num_layers=1, decoder_num_layers=2 (the reference defaults) are supported");
+  AOCR_CHECK(c.encoder_num_hidden >= 64 && c.encoder_num_hidden % 64 == 0 && c.encoder_num_hidden <= 512,
+             "encoder_num_hidden must be a multiple of 64 in [64,512]");
+  AOCR_CHECK(c.target_vocab_size >= 4 && c.target_vocab_size <= 64, "target_vocab_size must be in [4,64]");
+  AOCR_CHECK(c.target_embedding_size >= 1 && c.target_embedding_size % 4 == 0, "target_embedding_size must be a multiple of 4");
+  AOCR_CHECK(c.dropout == 0.0f, "dropout must be 0 (reference default)");
+  AOCR_CHECK(c.dp_world >= 0 && c.dp_rank >= 0, "bad dp_rank/dp_world");
+  AOCR_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AOCR_CUDA(cudaGetDeviceProperties(&prop, device));
+  AOCR_CHECK(prop.major == 10, "libaocr is built for sm_100a (B200) only");
+  ctx_.num_sms = prop.multiProcessorCount;
+  AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
+  AOCR_CUDA(cudaEventCreate(&ev0_));
+  AOCR_CUDA(cudaEventCreate(&ev1_));
+  He = c.encoder_num_hidden; Hd = 2 * He; E = c.target_embedding_size; V = c.target_vocab_size;
+  K1 = cfg.input_feed ? 2 * Hd : Hd; h1off = cfg.input_feed ? Hd : 0;
+  Bmax = c.batch_size; Smax = c.max_encoder_l; Tmax = c.max_decoder_l;
+  Wmax = 4 * (Smax + 1) + 3;
+  layout_params();
+  d_params = alloc<float>(L.total);
+  d_grads = alloc<float>(L.total);
+
+  const int64_t B = Bmax, W1 = Wmax / 2, W2 = W1 / 2, S = Smax, T = Tmax;
+  x0 = alloc<float>(B * 32 * Wmax);
+  tgt_bt = alloc<int32_t>(B * T); tev_bt = alloc<int32_t>(B * T);
+  tgt_tb = alloc<int32_t>(B * T); tev_tb = alloc<int32_t>(B * T);
+  act[1] = alloc<float>(B * 16 * W1 * 64);   pidx[1] = alloc<uint8_t>(B * 16 * W1 * 64);
+  zb[2] = alloc<float>(B * 16 * W1 * 128);   act[2] = alloc<float>(B * 8 * W2 * 128); pidx[2] = alloc<uint8_t>(B * 8 * W2 * 128);
+  zb[3] = alloc<float>(B * 8 * W2 * 256);    act[3] = alloc<float>(B * 8 * W2 * 256);
+  zb[4] = alloc<float>(B * 8 * W2 * 256);    act[4] = alloc<float>(B * 4 * W2 * 256); pidx[4] = alloc<uint8_t>(B * 4 * W2 * 256);
+  zb[5] = alloc<float>(B * 4 * W2 * 512);    act[5] = alloc<float>(B * 4 * W2 * 512);
+  zb[6] = alloc<float>(B * 4 * W2 * 512);    act[6] = alloc<float>(B * 2 * W2 * 512); pidx[6] = alloc<uint8_t>(B * 2 * W2 * 512);
+  zb[7] = alloc<float>(B * S * 512);
+  src = alloc<float>(S * B * 512);
+  act[7] = src;
+  const int bnc[3] = {256, 512, 512};
+  for (int i = 0; i < 3; i++) {
+    bn_mean[i] = alloc<float>(bnc[i]); bn_var[i] = alloc<float>(bnc[i]);
+    bn_rmean[i] = alloc<float>(bnc[i]); bn_rvar[i] = alloc<float>(bnc[i]);
+    std::vector<float> ones(bnc[i], 1.0f);
+    AOCR_CUDA(cudaMemcpyAsync(bn_rvar[i], ones.data(), bnc[i] * sizeof(float), cudaMemcpyHostToDevice, ctx_.st));
+    AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  }
+  col = alloc<float>(B * W1 * 18432);
+  gA = alloc<float>(B * 16 * W1 * 128);
+  gB = alloc<float>(B * 16 * W1 * 128);
+  partial = alloc<float>((int64_t)256 * 8192);
+  tmpvec = alloc<float>(8192);
+  for (int l = 1; l < 7; l++) wt[l] = alloc<float>((int64_t)kConv[l].cout * kConv[l].cin * kConv[l].k * kConv[l].k);
+
+  xg = alloc<float>(S * B * 8 * He);
+  Henc = alloc<float>(2 * (S + 1) * B * He); Cenc = alloc<float>(2 * (S + 1) * B * He);
+  acts_enc = alloc<float>(2 * S * B * 4 * He);
+  ctx = alloc<float>(B * S * 2 * He);
+  encb = alloc<float>(8 * He);
+  Dctx = alloc<float>(B * S * 2 * He); dGe = alloc<float>(S * B * 8 * He);
+  enc_dh = alloc<float>(2 * B * He); enc_dc = alloc<float>(2 * B * He);
+  dsrc = alloc<float>(S * B * 512);
+
+  X1 = alloc<float>(T * B * K1);  C1 = alloc<float>((T + 1) * B * Hd); ACT1 = alloc<float>(T * B * 4 * Hd);
+  X2 = alloc<float>(T * B * 2 * Hd); C2 = alloc<float>((T + 1) * B * Hd); ACT2 = alloc<float>(T * B * 4 * Hd);
+  CAT = alloc<float>(T * B * 2 * Hd); Q = alloc<float>(T * B * Hd); ALPHA = alloc<float>(T * B * S);
+  A_all = alloc<float>(T * B * Hd);
+  Ptab = alloc<float>((int64_t)V * 4 * Hd); bsum1 = alloc<float>(4 * Hd); bsum2 = alloc<float>(4 * Hd);
+  Gs = alloc<float>(B * 4 * Hd);
+  for (int i = 0; i < 3; i++) logp[i] = alloc<float>(T * B * V);
+  dZ = alloc<float>(T * B * V); rowloss = alloc<float>(T * B); dAgen = alloc<float>(T * B * Hd);
+  dU = alloc<float>(T * B * Hd); dCAT = alloc<float>(T * B * 2 * Hd); DE = alloc<float>(T * B * S);
+  dQ = alloc<float>(T * B * Hd); dH2q = alloc<float>(B * Hd);
+  dG2 = alloc<float>(T * B * 4 * Hd); dG1 = alloc<float>(T * B * 4 * Hd);
+  dX2 = alloc<float>(B * 2 * Hd); dX1 = alloc<float>(B * K1);
+  dc1 = alloc<float>(B * Hd); dc2 = alloc<float>(B * Hd); dP = alloc<float>((int64_t)V * 4 * Hd);
+  tok = alloc<int32_t>(B); labels = alloc<int32_t>(B * T);
+  score = alloc<double>(B); d_loss = alloc<double>(1); d_sumsq = alloc<double>(16); d_sq_partial = alloc<double>(5 * 1024);
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (ctx_.st) cudaStreamSynchronize(ctx_.st);
+  for (void* p : allocs_) cudaFree(p);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (ctx_.st) cudaStreamDestroy(ctx_.st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameter I/O.  External layout = Torch layout (conv weights (Cout,Cin,kH,kW)); native layout stores conv
+// weights as (Cout,kH,kW,Cin) so the K dimension of the implicit GEMM is channel-contiguous.
+static void permute_conv(const float* in, float* out, int cout, int cin, int kk, bool to_native) {
+  for (int co = 0; co < cout; co++)
+    for (int ci = 0; ci < cin; ci++)
+      for (int t = 0; t < kk; t++) {
+        int64_t ext = ((int64_t)co * cin + ci) * kk + t, nat = ((int64_t)co * kk + t) * cin + ci;
+        if (to_native) out[nat] = in[ext]; else out[ext] = in[nat];
+      }
+}
+
+void Engine::set_params(int group, const float* host, int64_t n) {
+  AOCR_CHECK(group >= 0 && group < 5, "group must be in [0,5)");
+  AOCR_CHECK(n == L.gsize[group], "parameter vector length does not match the group size");
+  AOCR_CUDA(cudaSetDevice(device_));
+  std::vector<float> tmp(host, host + n);
+  if (group == G_CNN) {
+    for (int l = 0; l < 7; l++) {
+      const ConvSpec& c = kConv[l];
+      int64_t o = L.conv_w[l] - L.goff[G_CNN];
+      permute_conv(host + o, tmp.data() + o, c.cout, c.cin, c.k * c.k, true);
+    }
+  }
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  AOCR_CUDA(cudaMemcpy(d_params + L.goff[group], tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  weights_dirty_ = true;
+}
+
+void Engine::get_flat(bool grads, int group, float* host, int64_t n) {
+  AOCR_CHECK(group >= 0 && group < 5, "group must be in [0,5)");
+  AOCR_CHECK(n == L.gsize[group], "vector length does not match the group size");
+  if (grads) AOCR_CHECK(have_grads_, "no gradients yet: call aocr_forward_backward first");
+  AOCR_CUDA(cudaSetDevice(device_));
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  const float* base = grads ? d_grads : d_params;
+  std::vector<float> tmp(n);
+  AOCR_CUDA(cudaMemcpy(tmp.data(), base + L.goff[group], n * sizeof(float), cudaMemcpyDeviceToHost));
+  memcpy(host, tmp.data(), n * sizeof(float));
+  if (group == G_CNN) {
+    for (int l = 0; l < 7; l++) {
+      const ConvSpec& c = kConv[l];
+      int64_t o = L.conv_w[l] - L.goff[G_CNN];
+      permute_conv(tmp.data() + o, host + o, c.cout, c.cin, c.k * c.k, false);
+    }
+  }
+}
+
+void Engine::set_bn(int layer, const float* mean, const float* var, int64_t n) {
+  AOCR_CHECK(layer >= 0 && layer < 3, "bn layer must be in [0,3)");
+  AOCR_CHECK(n == (layer == 0 ? 256 : 512), "bn stat length mismatch");
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  AOCR_CUDA(cudaMemcpy(bn_rmean[layer], mean, n * sizeof(float), cudaMemcpyHostToDevice));
+  AOCR_CUDA(cudaMemcpy(bn_rvar[layer], var, n * sizeof(float), cudaMemcpyHostToDevice));
+}
+void Engine::get_bn(int layer, float* mean, float* var, int64_t n) {
+  AOCR_CHECK(layer >= 0 && layer < 3, "bn layer must be in [0,3)");
+  AOCR_CHECK(n == (layer == 0 ? 256 : 512), "bn stat length mismatch");
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  AOCR_CUDA(cudaMemcpy(mean, bn_rmean[layer], n * sizeof(float), cudaMemcpyDeviceToHost));
+  AOCR_CUDA(cudaMemcpy(var, bn_rvar[layer], n * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+// ---------------------------------------------------------------------------------------------
+void Engine::stage_batch(const float* images, int b, int W, const int32_t* tgt, const int32_t* tev, int T) {
+  AOCR_CHECK(b >= 1 && b <= Bmax, "batch larger than config.batch_size");
+  AOCR_CHECK(W >= 8 && W <= Wmax, "image width out of range for max_encoder_l");
+  char msg[128];
+  if (T > Tmax) {   // model.lua:264
+    snprintf(msg, sizeof(msg), "max_decoder_l (%d) < target_l (%d)!", Tmax, T);
+    throw InvalidError(msg);
+  }
+  AOCR_CHECK(T >= 1, "target_l must be >= 1");
+  int S = (W / 2) / 2 - 1;
+  if (S > Smax) {   // model.lua:287
+    snprintf(msg, sizeof(msg), "max_encoder_l (%d) < source_l (%d)!", Smax, S);
+    throw InvalidError(msg);
+  }
+  AOCR_CHECK(S >= 1, "image too narrow: source_l < 1");
+  for (int64_t i = 0; i < (int64_t)b * T; i++)
+    AOCR_CHECK(tgt[i] >= 1 && tgt[i] <= V && tev[i] >= 1 && tev[i] <= V, "token id outside [1, target_vocab_size]");
+  AOCR_CUDA(cudaSetDevice(device_));
+  b_ = b; W_ = W; T_ = T; W1_ = W / 2; W2_ = W1_ / 2; S_ = S;
+  AOCR_CUDA(cudaMemcpyAsync(x0, images, (size_t)b * 32 * W * sizeof(float), cudaMemcpyHostToDevice, ctx_.st));
+  AOCR_CUDA(cudaMemcpyAsync(tgt_bt, tgt, (size_t)b * T * sizeof(int32_t), cudaMemcpyHostToDevice, ctx_.st));
+  AOCR_CUDA(cudaMemcpyAsync(tev_bt, tev, (size_t)b * T * sizeof(int32_t), cudaMemcpyHostToDevice, ctx_.st));
+  h_tev_.assign(tev, tev + (size_t)b * T);
+  have_batch_ = true;
+}
+
+void Engine::prof_begin(int cls) {
+  if (prof_on) AOCR_CUDA(cudaEventRecord(ev0_, ctx_.st));
+}
+void Engine::prof_end(int cls, double work) {
+  if (!prof_on) return;
+  AOCR_CUDA(cudaEventRecord(ev1_, ctx_.st));
+  AOCR_CUDA(cudaEventSynchronize(ev1_));
+  float ms = 0.f;
+  AOCR_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  prof_ms[cls] += ms; prof_launches[cls] += 1; prof_work[cls] += work;
+}
+
+void Engine::gemm(const Gemm& g, int cls) {
+  prof_begin(cls);
+  gemm_simt(ctx_, g);
+  prof_end(cls, 2.0 * g.M * g.N * (double)g.K * g.batch);
+}
+
+void Engine::conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const {
+  // l = 1..6 (0-based index into kConv): input of conv_{l+1}
+  static const int hin[7] = {32, 16, 8, 8, 4, 4, 2};
+  Hin = hin[l];
+  Win = l == 0 ? W_ : (l == 1 ? W1_ : W2_);
+  Hout = Hin + 2 * kConv[l].pad - kConv[l].k + 1;
+  Wout = Win + 2 * kConv[l].pad - kConv[l].k + 1;
+}
+
+void Engine::prep_weights() {
+  if (!weights_dirty_) return;
+  for (int l = 1; l < 7; l++) {
+    const ConvSpec& c = kConv[l];
+    int64_t total = (int64_t)c.cout * c.k * c.k * c.cin;
+    conv_wt_kernel<<<cdiv(total, 256) < 1184 ? cdiv(total, 256) : 1184, 256, 0, ctx_.st>>>(d_params + L.conv_w[l], wt[l],
+                                                                                       c.cout, c.k * c.k, c.cin);
+    AOCR_LAUNCH_CHECK(ctx_);
+  }
+  for (int d = 0; d < 2; d++)
+    add_vec(ctx_, encb + d * 4 * He, d_params + L.enc_bi[d], d_params + L.enc_bh[d], 4 * He);
+  add_vec(ctx_, bsum1, d_params + L.l1_bi, d_params + L.l1_bh, 4 * Hd);
+  add_vec(ctx_, bsum2, d_params + L.l2_bi, d_params + L.l2_bh, 4 * Hd);
+  // P[v] = E[v] W_i1[:, :E]^T + b_i1 + b_h1 : the embedding half of the layer-1 input projection (K12)
+  const int in1 = E + (cfg.input_feed ? Hd : 0);
+  Gemm g;
+  g.M = V; g.N = 4 * Hd; g.K = E;
+  g.A = d_params + L.emb; g.sam = E; g.sak = 1;
+  g.B = d_params + L.l1_wi; g.sbk = 1; g.sbn = in1;
+  g.C = Ptab; g.ldc = 4 * Hd; g.bias_n = bsum1;
+  gemm_simt(ctx_, g);
+  weights_dirty_ = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CNN forward (src/model/cnn.lua:9-45; called model.lua:285)
+void Engine::cnn_forward(bool train) {
+  cnn_train_ = train;
+  const int B = b_;
+  conv1_fwd(ctx_, x0, d_params + L.conv_w[0], d_params + L.conv_b[0], act[1], pidx[1], B, W_);
+  for (int l = 1; l < 7; l++) {
+    const ConvSpec& c = kConv[l];
+    int Hin, Win, Hout, Wout;
+    conv_dims(l, Hin, Win, Hout, Wout);
+    const int64_t rows = (int64_t)B * Hout * Wout;
+    const int Kc = c.k * c.k * c.cin;
+    im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
+    Gemm g;
+    g.M = (int)rows; g.N = c.cout; g.K = Kc;
+    g.A = col; g.sam = Kc; g.sak = 1;
+    g.B = d_params + L.conv_w[l]; g.sbk = 1; g.sbn = Kc;
+    g.C = zb[l + 1]; g.ldc = c.cout; g.bias_n = d_params + L.conv_b[l];
+    gemm(g);
+    if (c.bn >= 0) {
+      const float *mean, *var;
+      if (train) {
+        bn_stats(ctx_, zb[l + 1], rows, c.cout, bn_mean[c.bn], bn_var[c.bn], partial);
+        bn_update_running(ctx_, bn_mean[c.bn], bn_var[c.bn], bn_rmean[c.bn], bn_rvar[c.bn], c.cout, rows);
+        mean = bn_mean[c.bn]; var = bn_var[c.bn];
+      } else {
+        mean = bn_rmean[c.bn]; var = bn_rvar[c.bn];
+      }
+      const bool last = (l == 6);
+      bn_relu_fwd(ctx_, zb[l + 1], mean, var, d_params + L.bn_g[c.bn], d_params + L.bn_b[c.bn], act[l + 1], rows, c.cout,
+                  last ? S_ : 0, last ? B : 0);
+    } else {
+      relu_pool_fwd(ctx_, zb[l + 1], act[l + 1], pidx[l + 1], B, Hout, Wout, c.cout, c.pool_kw);
+    }
+  }
+  taps_["cnn_out"] = {src, (int64_t)S_ * B * 512};
+}
+
+// CNN backward (model.lua:692)
+void Engine::cnn_backward() {
+  const int B = b_;
+  const float* dcur = dsrc;   // gradient wrt act[l+1]
+  for (int l = 6; l >= 1; l--) {
+    const ConvSpec& c = kConv[l];
+    int Hin, Win, Hout, Wout;
+    conv_dims(l, Hin, Win, Hout, Wout);
+    const int64_t rows = (int64_t)B * Hout * Wout;
+    const int Kc = c.k * c.k * c.cin;
+    float* dz = gA;
+    if (c.bn >= 0) {
+      const bool last = (l == 6);
+      const float* mean = cnn_train_ ? bn_mean[c.bn] : bn_rmean[c.bn];
+      const float* var = cnn_train_ ? bn_var[c.bn] : bn_rvar[c.bn];
+      bn_relu_bwd(ctx_, dcur, act[l + 1], zb[l + 1], mean, var, d_params + L.bn_g[c.bn], dz, d_grads + L.bn_g[c.bn],
+                  d_grads + L.bn_b[c.bn], partial, rows, c.cout, last ? S_ : 0, last ? B : 0, cnn_train_ ? 1 : 0);
+    } else {
+      relu_pool_bwd(ctx_, dcur, act[l + 1], pidx[l + 1], dz, B, Hout, Wout, c.cout, c.pool_kw);
+    }
+    // bias grad
+    col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);
+    // weight grad: dW[co][tap,ci] = sum_rows dz[row][co] * col[row][tap,ci]
+    im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
+    Gemm gw;
+    gw.M = c.cout; gw.N = Kc; gw.K = (int)rows;
+    gw.A = dz; gw.sam = 1; gw.sak = c.cout;
+    gw.B = col; gw.sbk = Kc; gw.sbn = 1;
+    gw.C = d_grads + L.conv_w[l]; gw.ldc = Kc;
+    gemm(gw);
+    // data grad: correlation of dz with flipped, in/out-swapped weights, padding k-1-pad
+    const int padd = c.k - 1 - c.pad;
+    im2col(ctx_, dz, col, B, Hout, Wout, c.cout, c.k, padd);
+    const int Kd = c.k * c.k * c.cout;
+    const int64_t rows_in = (int64_t)B * Hin * Win;
+    Gemm gd;
+    gd.M = (int)rows_in; gd.N = c.cin; gd.K = Kd;
+    gd.A = col; gd.sam = Kd; gd.sak = 1;
+    gd.B = wt[l]; gd.sbk = 1; gd.sbn = Kd;
+    gd.C = gB; gd.ldc = c.cin;
+    gemm(gd);
+    dcur = gB;
+    // next iteration writes dz into gA again and reads dcur=gB: fine (distinct buffers)
+  }
+  const int nblk = 256;
+  conv1_bwd(ctx_, x0, act[1], pidx[1], dcur, d_grads + L.conv_w[0], d_grads + L.conv_b[0], partial, nblk, B, W_);
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoder (model.lua:293-316).  Slot convention: fw slot t+1 = state after column t (slot 0 = zeros);
+// bw slot t = state after column t (slot S = zeros).
+void Engine::encoder_forward() {
+  const int B = b_, S = S_;
+  for (int d = 0; d < 2; d++) {   // time-batched input projection for all columns (K10)
+    Gemm g;
+    g.M = S * B; g.N = 4 * He; g.K = 512;
+    g.A = src; g.sam = 512; g.sak = 1;
+    g.B = d_params + L.enc_wi[d]; g.sbk = 1; g.sbn = 512;
+    g.C = xg + d * 4 * He; g.ldc = 8 * He; g.bias_n = encb + d * 4 * He;
+    gemm(g);
+  }
+  const int64_t slot = (int64_t)B * He;
+  fill_zero(ctx_, Henc, slot * sizeof(float));                                   // fw slot 0
+  fill_zero(ctx_, Cenc, slot * sizeof(float));
+  fill_zero(ctx_, Henc + ((int64_t)(S + 1) + S) * slot, slot * sizeof(float));   // bw slot S
+  fill_zero(ctx_, Cenc + ((int64_t)(S + 1) + S) * slot, slot * sizeof(float));
+  EncStep p;
+  p.xg = xg; p.Wh[0] = d_params + L.enc_wh[0]; p.Wh[1] = d_params + L.enc_wh[1];
+  p.H = Henc; p.Cst = Cenc; p.acts = acts_enc; p.ctx = ctx; p.B = B; p.S = S; p.He = He;
+  prof_begin(2);
+  for (int i = 0; i < S; i++) {
+    p.step = i;
+    enc_step_fwd(ctx_, p);
+  }
+  prof_end(2, 2.0 * 2 * S * (double)B * He * 4 * He);
+  taps_["context"] = {ctx, (int64_t)B * S * 2 * He};
+}
+
+void Engine::encoder_backward() {
+  const int B = b_, S = S_;
+  const int64_t slot = (int64_t)B * He;
+  // seeds: halves of d c1(0), d h1(0) (model.lua:666-667,680-681).  dc1 / dX1[:, h1off:] hold them.
+  for (int d = 0; d < 2; d++) {
+    copy_strided(ctx_, enc_dc + d * slot, He, dc1 + d * He, Hd, B, He);
+    copy_strided(ctx_, enc_dh + d * slot, He, dX1 + h1off + d * He, K1, B, He);
+  }
+  EncStepBwd p;
+  p.Wh[0] = d_params + L.enc_wh[0]; p.Wh[1] = d_params + L.enc_wh[1];
+  p.Cst = Cenc; p.acts = acts_enc; p.Dctx = Dctx; p.dh = enc_dh; p.dc = enc_dc; p.dG = dGe;
+  p.B = B; p.S = S; p.He = He;
+  for (int i = 0; i < S; i++) {
+    p.step = i;
+    enc_cell_bwd(ctx_, p);
+    // dh_prev[d] = dG_t[d] W_h[d]   (B x 4He) x (4He x He), both directions in one batched launch
+    for (int d = 0; d < 2; d++) {
+      int t = d == 0 ? S - 1 - i : i;
+      Gemm g;
+      g.M = B; g.N = He; g.K = 4 * He;
+      g.A = dGe + (int64_t)t * B * 8 * He + d * 4 * He; g.sam = 8 * He; g.sak = 1;
+      g.B = d_params + L.enc_wh[d]; g.sbk = He; g.sbn = 1;
+      g.C = enc_dh + d * slot; g.ldc = He;
+      gemm(g, 2);
+    }
+  }
+  // time-batched parameter and input gradients
+  for (int d = 0; d < 2; d++) {
+    const float* dG = dGe + d * 4 * He;
+    Gemm gi;   // dW_i = dG^T src
+    gi.M = 4 * He; gi.N = 512; gi.K = S * B;
+    gi.A = dG; gi.sam = 1; gi.sak = 8 * He;
+    gi.B = src; gi.sbk = 512; gi.sbn = 1;
+    gi.C = d_grads + L.enc_wi[d]; gi.ldc = 512;
+    gemm(gi);
+    // dW_h = sum_t dG_t^T h_prev(t).  fw: h_prev(t) = slot t -> rows [0, S*B) of Henc[0]; bw: h_prev(t) = slot t+1.
+    Gemm gh;
+    gh.M = 4 * He; gh.N = He; gh.K = S * B;
+    gh.A = dG; gh.sam = 1; gh.sak = 8 * He;
+    gh.B = Henc + (int64_t)d * (S + 1) * slot + (d == 0 ? 0 : slot); gh.sbk = He; gh.sbn = 1;
+    gh.C = d_grads + L.enc_wh[d]; gh.ldc = He;
+    gemm(gh);
+  }
+  // bias grads: b_i and b_h both receive the column sums of dG (two biases per cell, LSTM.lua:79-87)
+  col_sum(ctx_, dGe, (int64_t)S * B, 8 * He, tmpvec, partial, 0);
+  for (int d = 0; d < 2; d++) {
+    AOCR_CUDA(cudaMemcpyAsync(d_grads + L.enc_bi[d], tmpvec + d * 4 * He, (size_t)4 * He * sizeof(float),
+                              cudaMemcpyDeviceToDevice, ctx_.st));
+    AOCR_CUDA(cudaMemcpyAsync(d_grads + L.enc_bh[d], tmpvec + d * 4 * He, (size_t)4 * He * sizeof(float),
+                              cudaMemcpyDeviceToDevice, ctx_.st));
+  }
+  // d src = dG_fw W_i_fw + dG_bw W_i_bw  (model.lua:675,689)
+  for (int d = 0; d < 2; d++) {
+    Gemm g;
+    g.M = S * B; g.N = 512; g.K = 4 * He;
+    g.A = dGe + d * 4 * He; g.sam = 8 * He; g.sak = 1;
+    g.B = d_params + L.enc_wi[d]; g.sbk = 512; g.sbn = 1;
+    g.C = dsrc; g.ldc = 512; g.accumulate = d;
+    gemm(g);
+  }
+}
+
+}  // namespace aocr

@@ -1,0 +1,115 @@
+// engine.h — host-side step scheduler of libaocr: owns device memory, the parameter/gradient flat
+// buffers and runs the reference's `feval` schedule (src/model/model.lua:284-695) as kernel launches.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/aocr.h"
+#include "kernels.h"
+
+namespace aocr {
+
+// API group ids follow src/model/model.lua:150; the physical order in the flat buffers is the order in
+// which backward finishes them ([proj | decoder | enc_fw | enc_bw | cnn]) so a bucketed allreduce can
+// start on the head of the buffer while the tail is still being produced.
+enum Group { G_CNN = 0, G_ENC_FW = 1, G_ENC_BW = 2, G_DEC = 3, G_PROJ = 4 };
+
+struct ConvSpec { int cin, cout, k, pad, bn /* -1 or bn index */, pool_kw /* 0 none, 1: 2x1, 2: 2x2 */; };
+extern const ConvSpec kConv[7];
+
+struct ParamLayout {
+  int64_t goff[5], gsize[5], total;
+  int64_t conv_w[7], conv_b[7], bn_g[3], bn_b[3];
+  int64_t enc_wi[2], enc_bi[2], enc_wh[2], enc_bh[2];
+  int64_t emb, l1_wi, l1_bi, l1_wh, l1_bh, l2_wi, l2_bi, l2_wh, l2_bh, wa, wc;
+  int64_t wo, bo;
+};
+
+struct Tap { const float* ptr; int64_t n; };
+
+class Engine {
+ public:
+  Engine(const aocr_config& cfg, int device);
+  ~Engine();
+
+  void set_params(int group, const float* host, int64_t n);
+  void get_flat(bool grads, int group, float* host, int64_t n);
+  void set_bn(int layer, const float* mean, const float* var, int64_t n);
+  void get_bn(int layer, float* mean, float* var, int64_t n);
+
+  void stage_batch(const float* images, int b, int W, const int32_t* tgt, const int32_t* tev, int T);
+  void forward_backward_enqueue();
+  double read_loss();
+  void group_norms(double* pn, double* gn);
+  void sgd_enqueue(double lr, double clip);
+  void decode_enqueue();
+  void decode_collect(int32_t* labels, double* pred, double* gold, double* loss_sum, int32_t* num_correct);
+  void get_logprobs(int which, float* out, int64_t n);
+  void debug_read(const char* name, float* out, int64_t n);
+  void sync() { AOCR_CUDA(cudaStreamSynchronize(ctx_.st)); }
+  void mark_weights_dirty() { weights_dirty_ = true; }
+
+  aocr_config cfg;
+  ParamLayout L;
+  Ctx ctx_;
+  float* d_params = nullptr;
+  float* d_grads = nullptr;
+  std::string last_error;
+  // profiling of kernel classes (bench roofline): 0 tensor GEMM/conv, 1 attention, 2 recurrence
+  bool prof_on = false;
+  double prof_ms[3] = {0, 0, 0};
+  int64_t prof_launches[3] = {0, 0, 0};
+  double prof_work[3] = {0, 0, 0};
+
+ private:
+  template <typename T> T* alloc(int64_t n);
+  void layout_params();
+  void gemm(const Gemm& g, int cls = 0);
+  void prep_weights();
+  void cnn_forward(bool train);
+  void cnn_backward();
+  void encoder_forward();
+  void encoder_backward();
+  void decoder_init();
+  void decoder_step(int t, const int32_t* tok);
+  void decoder_backward();
+  void conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const;
+  void prof_begin(int cls);
+  void prof_end(int cls, double work);
+
+  int device_;
+  int He, Hd, E, V, K1, h1off, Bmax, Smax, Tmax, Wmax;
+  std::vector<void*> allocs_;
+  std::map<std::string, Tap> taps_;
+
+  // current batch
+  int b_ = 0, W_ = 0, T_ = 0, W1_ = 0, W2_ = 0, S_ = 0;
+  bool have_batch_ = false, have_grads_ = false, weights_dirty_ = true;
+  int dec_steps_ = 0;
+  std::vector<int32_t> h_tev_;
+  int last_logp_rows_[3] = {0, 0, 0};
+  float* x0 = nullptr;
+  int32_t *tgt_bt = nullptr, *tev_bt = nullptr, *tgt_tb = nullptr, *tev_tb = nullptr;
+  // CNN
+  float *act[8] = {}, *zb[8] = {};
+  uint8_t* pidx[8] = {};
+  float *bn_mean[3], *bn_var[3], *bn_rmean[3], *bn_rvar[3];
+  float *col = nullptr, *gA = nullptr, *gB = nullptr, *partial = nullptr, *tmpvec = nullptr, *wt[8] = {};
+  bool cnn_train_ = true;
+  // encoder
+  float *src = nullptr, *xg = nullptr, *Henc = nullptr, *Cenc = nullptr, *acts_enc = nullptr, *ctx = nullptr;
+  float *encb = nullptr, *Dctx = nullptr, *dGe = nullptr, *enc_dh = nullptr, *enc_dc = nullptr, *dsrc = nullptr;
+  // decoder
+  float *X1 = nullptr, *C1 = nullptr, *ACT1 = nullptr, *X2 = nullptr, *C2 = nullptr, *ACT2 = nullptr, *CAT = nullptr,
+        *Q = nullptr, *ALPHA = nullptr, *A_all = nullptr, *Ptab = nullptr, *bsum1 = nullptr, *bsum2 = nullptr,
+        *Gs = nullptr;
+  float *logp[3] = {}, *dZ = nullptr, *rowloss = nullptr, *dAgen = nullptr, *dU = nullptr, *dCAT = nullptr,
+        *DE = nullptr, *dQ = nullptr, *dH2q = nullptr, *dG2 = nullptr, *dG1 = nullptr, *dX2 = nullptr, *dX1 = nullptr,
+        *dc1 = nullptr, *dc2 = nullptr, *dP = nullptr;
+  int32_t *tok = nullptr, *labels = nullptr;
+  double *score = nullptr, *d_loss = nullptr, *d_sumsq = nullptr, *d_sq_partial = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+};
+
+}  // namespace aocr

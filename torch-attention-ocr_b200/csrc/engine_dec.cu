@@ -1,0 +1,384 @@
+// engine_dec.cu — decoder schedule, criterion, optimiser and the greedy path of the step scheduler.
+// Reference: src/model/model.lua:360-404,446-459,516-536 (greedy), :539-568 (train forward),
+// :589-627 (gold pass), :643-661 (decoder backward), src/optim/optim_sgd.lua:40-95.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace aocr {
+
+// model.lua:539-552 / 360-372 / 589-602.  Quirk Q14: with -input_feed the reference's
+// "zero layers >= 2" loop indexes the state list without the input-feed offset and so zeroes h1(0); the
+// decoder starts from c1(0) = [c_fw(S); c_bw(1)], h1(0) = 0.  Without input feed h1(0) = [h_fw(S); h_bw(1)].
+void Engine::decoder_init() {
+  const int B = b_, S = S_;
+  const int64_t slot = (int64_t)B * He;
+  const float* cfw = Cenc + ((int64_t)0 * (S + 1) + S) * slot;
+  const float* cbw = Cenc + ((int64_t)1 * (S + 1) + 0) * slot;
+  concat_enc_finals(ctx_, cfw, cbw, C1, Hd, B, He);
+  fill_zero(ctx_, X1, (size_t)B * K1 * sizeof(float));
+  if (!cfg.input_feed) {
+    const float* hfw = Henc + ((int64_t)0 * (S + 1) + S) * slot;
+    const float* hbw = Henc + ((int64_t)1 * (S + 1) + 0) * slot;
+    concat_enc_finals(ctx_, hfw, hbw, X1, K1, B, He);
+  }
+  fill_zero(ctx_, C2, (size_t)B * Hd * sizeof(float));
+  fill_zero(ctx_, X2, (size_t)B * 2 * Hd * sizeof(float));
+}
+
+// One decoder step (src/model/LSTM.lua:18-162).  Saved-state layout, per step t:
+//   X1[t] = [a_{t-1} | h1_{t-1}]   X2[t] = [h1_t | h2_{t-1}]   CAT[t] = [cv_t | h2_t]   A_all[t] = a_t
+void Engine::decoder_step(int t, const int32_t* tokens) {
+  const int B = b_, S = S_;
+  const int in1 = E + (cfg.input_feed ? Hd : 0);
+  const int nsteps = dec_steps_;
+  float* x1 = X1 + (int64_t)t * B * K1;
+  float* x2 = X2 + (int64_t)t * B * 2 * Hd;
+  float* cat = CAT + (int64_t)t * B * 2 * Hd;
+  const bool has_next = (t + 1 < nsteps);
+  Gemm g;
+  // ---- layer 1 gates: a_{t-1} W_i1[:,E:]^T + h1_{t-1} W_h1^T   (embedding part + biases come from Ptab)
+  if (cfg.input_feed) {
+    g = Gemm();
+    g.M = B; g.N = 4 * Hd; g.K = Hd;
+    g.A = x1; g.sam = K1; g.sak = 1;
+    g.B = d_params + L.l1_wi + E; g.sbk = 1; g.sbn = in1;
+    g.C = Gs; g.ldc = 4 * Hd;
+    gemm(g);
+  }
+  g = Gemm();
+  g.M = B; g.N = 4 * Hd; g.K = Hd;
+  g.A = x1 + h1off; g.sam = K1; g.sak = 1;
+  g.B = d_params + L.l1_wh; g.sbk = 1; g.sbn = Hd;
+  g.C = Gs; g.ldc = 4 * Hd; g.accumulate = cfg.input_feed ? 1 : 0;
+  gemm(g);
+  DecCell c1;
+  c1.G = Gs; c1.addrows = Ptab; c1.rowsel = tokens; c1.addld = 4 * Hd;
+  c1.c_prev = C1 + (int64_t)t * B * Hd; c1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
+  c1.acts = ACT1 + (int64_t)t * B * 4 * Hd;
+  c1.h_out0 = x2; c1.ld0 = 2 * Hd;
+  c1.h_out1 = has_next ? x1 + (int64_t)B * K1 + h1off : nullptr; c1.ld1 = K1;
+  c1.B = B; c1.H = Hd;
+  dec_cell_fwd(ctx_, c1);
+  // ---- layer 2 gates: h1_t W_i2^T + h2_{t-1} W_h2^T + (b_i2 + b_h2)
+  g = Gemm();
+  g.M = B; g.N = 4 * Hd; g.K = Hd;
+  g.A = x2; g.sam = 2 * Hd; g.sak = 1;
+  g.B = d_params + L.l2_wi; g.sbk = 1; g.sbn = Hd;
+  g.C = Gs; g.ldc = 4 * Hd;
+  gemm(g);
+  g.A = x2 + Hd; g.B = d_params + L.l2_wh; g.accumulate = 1;
+  gemm(g);
+  DecCell c2;
+  c2.G = Gs; c2.addrows = bsum2; c2.rowsel = nullptr; c2.addld = 0;
+  c2.c_prev = C2 + (int64_t)t * B * Hd; c2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
+  c2.acts = ACT2 + (int64_t)t * B * 4 * Hd;
+  c2.h_out0 = cat + Hd; c2.ld0 = 2 * Hd;
+  c2.h_out1 = has_next ? x2 + (int64_t)B * 2 * Hd + Hd : nullptr; c2.ld1 = 2 * Hd;
+  c2.B = B; c2.H = Hd;
+  dec_cell_fwd(ctx_, c2);
+  // ---- attention: q = W_a h2 ; scores, softmax, context vector (fused kernel)
+  float* q = Q + (int64_t)t * B * Hd;
+  g = Gemm();
+  g.M = B; g.N = Hd; g.K = Hd;
+  g.A = cat + Hd; g.sam = 2 * Hd; g.sak = 1;
+  g.B = d_params + L.wa; g.sbk = 1; g.sbn = Hd;
+  g.C = q; g.ldc = Hd;
+  gemm(g);
+  prof_begin(1);
+  attn_fwd(ctx_, ctx, q, ALPHA + (int64_t)t * B * S, cat, 2 * Hd, B, S, Hd);
+  prof_end(1, (double)B * S * Hd * 4 + (double)B * (2.0 * Hd + S) * 4);
+  // ---- a_t = tanh(W_c [cv ; h2])
+  float* a = A_all + (int64_t)t * B * Hd;
+  g = Gemm();
+  g.M = B; g.N = Hd; g.K = 2 * Hd;
+  g.A = cat; g.sam = 2 * Hd; g.sak = 1;
+  g.B = d_params + L.wc; g.sbk = 1; g.sbn = 2 * Hd;
+  g.C = a; g.ldc = Hd; g.act = ACT_TANH;
+  gemm(g);
+  if (cfg.input_feed && has_next) copy_strided(ctx_, x1 + (int64_t)B * K1, K1, a, Hd, B, Hd);
+}
+
+// decoder backward through time (model.lua:643-661) with every parameter gradient time-batched afterwards
+void Engine::decoder_backward() {
+  const int B = b_, S = S_, T = T_;
+  const int in1 = E + (cfg.input_feed ? Hd : 0);
+  const int64_t R = (int64_t)T * B;
+  const float inv_bn = 1.0f / (float)(cfg.global_batch > 0 ? cfg.global_batch : B);
+  // generator + criterion for all steps at once (a_t are all known): model.lua:644-648
+  generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[0], dZ, rowloss, R, Hd, V, inv_bn);
+  reduce_sum_double(ctx_, rowloss, R, d_loss);
+  Gemm g;
+  g.M = (int)R; g.N = Hd; g.K = V;                       // dA_gen = dZ W_o
+  g.A = dZ; g.sam = V; g.sak = 1;
+  g.B = d_params + L.wo; g.sbk = Hd; g.sbn = 1;
+  g.C = dAgen; g.ldc = Hd;
+  gemm(g);
+  g = Gemm();
+  g.M = V; g.N = Hd; g.K = (int)R;                       // dW_o = dZ^T A
+  g.A = dZ; g.sam = 1; g.sak = V;
+  g.B = A_all; g.sbk = Hd; g.sbn = 1;
+  g.C = d_grads + L.wo; g.ldc = Hd;
+  gemm(g);
+  col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
+
+  fill_zero(ctx_, dc1, (size_t)B * Hd * sizeof(float));
+  fill_zero(ctx_, dc2, (size_t)B * Hd * sizeof(float));
+  for (int t = T - 1; t >= 0; t--) {
+    const bool last = (t == T - 1);
+    float* du = dU + (int64_t)t * B * Hd;
+    float* dcat = dCAT + (int64_t)t * B * 2 * Hd;
+    float* dq = dQ + (int64_t)t * B * Hd;
+    float* dg2 = dG2 + (int64_t)t * B * 4 * Hd;
+    float* dg1 = dG1 + (int64_t)t * B * 4 * Hd;
+    du_from_da(ctx_, (!last && cfg.input_feed) ? dX1 : nullptr, K1, dAgen + (int64_t)t * B * Hd,
+               A_all + (int64_t)t * B * Hd, du, (int64_t)B * Hd, Hd);
+    g = Gemm();                                           // d[cv;h2] = du W_c
+    g.M = B; g.N = 2 * Hd; g.K = Hd;
+    g.A = du; g.sam = Hd; g.sak = 1;
+    g.B = d_params + L.wc; g.sbk = 2 * Hd; g.sbn = 1;
+    g.C = dcat; g.ldc = 2 * Hd;
+    gemm(g);
+    prof_begin(1);
+    attn_bwd(ctx_, ctx, ALPHA + (int64_t)t * B * S, dcat, 2 * Hd, DE + (int64_t)t * B * S, dq, B, S, Hd);
+    prof_end(1, 2.0 * B * S * Hd * 4);
+    g = Gemm();                                           // dh2 += dq W_a
+    g.M = B; g.N = Hd; g.K = Hd;
+    g.A = dq; g.sam = Hd; g.sak = 1;
+    g.B = d_params + L.wa; g.sbk = Hd; g.sbn = 1;
+    g.C = dH2q; g.ldc = Hd;
+    gemm(g);
+    DecCellBwd b2;
+    b2.dh_a = dcat + Hd; b2.lda = 2 * Hd;
+    b2.dh_b = dH2q; b2.ldb = Hd;
+    b2.dh_c = last ? nullptr : dX2 + Hd; b2.ldc = 2 * Hd;
+    b2.dc = dc2; b2.c_prev = C2 + (int64_t)t * B * Hd; b2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
+    b2.acts = ACT2 + (int64_t)t * B * 4 * Hd; b2.dG = dg2; b2.B = B; b2.H = Hd;
+    dec_cell_bwd(ctx_, b2);
+    g = Gemm();                                           // [dh1 | dh2_prev] = dg2 [W_i2 | W_h2]
+    g.M = B; g.N = Hd; g.K = 4 * Hd;
+    g.A = dg2; g.sam = 4 * Hd; g.sak = 1;
+    g.B = d_params + L.l2_wi; g.sbk = Hd; g.sbn = 1;
+    g.C = dX2; g.ldc = 2 * Hd;
+    gemm(g);
+    g.B = d_params + L.l2_wh; g.C = dX2 + Hd;
+    gemm(g);
+    DecCellBwd b1;
+    b1.dh_a = dX2; b1.lda = 2 * Hd;
+    b1.dh_b = last ? nullptr : dX1 + h1off; b1.ldb = K1;
+    b1.dh_c = nullptr; b1.ldc = 0;
+    b1.dc = dc1; b1.c_prev = C1 + (int64_t)t * B * Hd; b1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
+    b1.acts = ACT1 + (int64_t)t * B * 4 * Hd; b1.dG = dg1; b1.B = B; b1.H = Hd;
+    dec_cell_bwd(ctx_, b1);
+    if (cfg.input_feed) {                                 // da_prev = dg1 W_i1[:, E:]
+      g = Gemm();
+      g.M = B; g.N = Hd; g.K = 4 * Hd;
+      g.A = dg1; g.sam = 4 * Hd; g.sak = 1;
+      g.B = d_params + L.l1_wi + E; g.sbk = in1; g.sbn = 1;
+      g.C = dX1; g.ldc = K1;
+      gemm(g);
+    }
+    g = Gemm();                                           // dh1_prev = dg1 W_h1
+    g.M = B; g.N = Hd; g.K = 4 * Hd;
+    g.A = dg1; g.sam = 4 * Hd; g.sak = 1;
+    g.B = d_params + L.l1_wh; g.sbk = Hd; g.sbn = 1;
+    g.C = dX1 + h1off; g.ldc = K1;
+    gemm(g);
+  }
+  // ---- time-batched parameter gradients (weights are tied across t: clone_many_times, model_utils.lua:3-50)
+  auto wgrad = [&](const float* dY, int M, const float* X, int64_t ldx, int N, float* dW, int64_t ldw) {
+    Gemm w;
+    w.M = M; w.N = N; w.K = (int)R;
+    w.A = dY; w.sam = 1; w.sak = M;
+    w.B = X; w.sbk = ldx; w.sbn = 1;
+    w.C = dW; w.ldc = ldw;
+    gemm(w);
+  };
+  wgrad(dU, Hd, CAT, 2 * Hd, 2 * Hd, d_grads + L.wc, 2 * Hd);
+  wgrad(dQ, Hd, CAT + Hd, 2 * Hd, Hd, d_grads + L.wa, Hd);
+  wgrad(dG2, 4 * Hd, X2, 2 * Hd, Hd, d_grads + L.l2_wi, Hd);
+  wgrad(dG2, 4 * Hd, X2 + Hd, 2 * Hd, Hd, d_grads + L.l2_wh, Hd);
+  col_sum(ctx_, dG2, R, 4 * Hd, d_grads + L.l2_bi, partial, 0);
+  AOCR_CUDA(cudaMemcpyAsync(d_grads + L.l2_bh, d_grads + L.l2_bi, (size_t)4 * Hd * sizeof(float), cudaMemcpyDeviceToDevice,
+                            ctx_.st));
+  if (cfg.input_feed) wgrad(dG1, 4 * Hd, X1, K1, Hd, d_grads + L.l1_wi + E, in1);
+  wgrad(dG1, 4 * Hd, X1 + h1off, K1, Hd, d_grads + L.l1_wh, Hd);
+  col_sum(ctx_, dG1, R, 4 * Hd, d_grads + L.l1_bi, partial, 0);
+  AOCR_CUDA(cudaMemcpyAsync(d_grads + L.l1_bh, d_grads + L.l1_bi, (size_t)4 * Hd * sizeof(float), cudaMemcpyDeviceToDevice,
+                            ctx_.st));
+  // embedding path: dP[v] = sum of dg1 rows whose input token is v (LookupTable has no paddingValue: PAD rows count)
+  token_segment_sum(ctx_, dG1, tgt_tb, dP, R, 4 * Hd, V);
+  g = Gemm();                                             // dEmb = dP W_i1[:, :E]
+  g.M = V; g.N = E; g.K = 4 * Hd;
+  g.A = dP; g.sam = 4 * Hd; g.sak = 1;
+  g.B = d_params + L.l1_wi; g.sbk = in1; g.sbn = 1;
+  g.C = d_grads + L.emb; g.ldc = E;
+  gemm(g);
+  g = Gemm();                                             // dW_i1[:, :E] = dP^T Emb
+  g.M = 4 * Hd; g.N = E; g.K = V;
+  g.A = dP; g.sam = 1; g.sak = 4 * Hd;
+  g.B = d_params + L.emb; g.sbk = E; g.sbn = 1;
+  g.C = d_grads + L.l1_wi; g.ldc = in1;
+  gemm(g);
+  // D_ctx[b] = sum_t alpha_t[b]^T dcv_t[b] + de_t[b]^T q_t[b]   (replaces the per-step RMW of model.lua:652-653)
+  g = Gemm();
+  g.M = S; g.N = Hd; g.K = T; g.batch = B;
+  g.A = ALPHA; g.sam = 1; g.sak = (int64_t)B * S; g.bsa = S;
+  g.B = dCAT; g.sbk = (int64_t)B * 2 * Hd; g.sbn = 1; g.bsb = 2 * Hd;
+  g.C = Dctx; g.ldc = Hd; g.bsc = (int64_t)S * Hd;
+  gemm(g);
+  g.A = DE;
+  g.B = Q; g.sbk = (int64_t)B * Hd; g.bsb = Hd;
+  g.accumulate = 1;
+  gemm(g);
+  taps_["dctx"] = {Dctx, (int64_t)B * S * Hd};
+}
+
+// feval, train branch (model.lua:284-316,537-569,634-695)
+void Engine::forward_backward_enqueue() {
+  AOCR_CHECK(have_batch_, "no batch staged");
+  AOCR_CUDA(cudaSetDevice(device_));
+  const int B = b_, T = T_;
+  prep_weights();
+  gather_tokens(ctx_, tgt_bt, tgt_tb, B, T, T, 1);
+  gather_tokens(ctx_, tev_bt, tev_tb, B, T, T, 1);
+  fill_zero(ctx_, d_grads, (size_t)L.total * sizeof(float));   // model.lua:637-639
+  cnn_forward(true);
+  encoder_forward();
+  decoder_init();
+  dec_steps_ = T;
+  for (int t = 0; t < T; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
+  taps_["a_all"] = {A_all, (int64_t)T * B * Hd};
+  taps_["alpha"] = {ALPHA, (int64_t)T * B * S_};
+  decoder_backward();
+  encoder_backward();
+  taps_["dsrc"] = {dsrc, (int64_t)S_ * B * 512};
+  cnn_backward();
+  have_grads_ = true;
+  last_logp_rows_[0] = T * B;
+}
+
+double Engine::read_loss() {
+  double v = 0.0;
+  AOCR_CUDA(cudaMemcpyAsync(&v, d_loss, sizeof(double), cudaMemcpyDeviceToHost, ctx_.st));
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  return v;
+}
+
+static int sq_blocks(int64_t n) { return (int)(n / 4096 + 1 < 1024 ? n / 4096 + 1 : 1024); }
+
+void Engine::group_norms(double* pn, double* gn) {
+  AOCR_CHECK(have_grads_, "no gradients yet: call aocr_forward_backward first");
+  for (int g = 0; g < 5; g++) {
+    int nb = sq_blocks(L.gsize[g]);
+    sumsq_partial(ctx_, d_grads + L.goff[g], L.gsize[g], d_sq_partial + g * 1024, nb);
+    sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + g);
+  }
+  for (int g = 0; g < 5; g++) {
+    int nb = sq_blocks(L.gsize[g]);
+    sumsq_partial(ctx_, d_params + L.goff[g], L.gsize[g], d_sq_partial + g * 1024, nb);
+    sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + 5 + g);
+  }
+  double h[10];
+  AOCR_CUDA(cudaMemcpyAsync(h, d_sumsq, sizeof(h), cudaMemcpyDeviceToHost, ctx_.st));
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  for (int g = 0; g < 5; g++) { gn[g] = sqrt(h[g]); pn[g] = sqrt(h[5 + g]); }
+}
+
+// optim.sgd_list, default branch (optim_sgd.lua:49-52,90): per group clip to `clip`, p -= lr*g.  No host sync.
+void Engine::sgd_enqueue(double lr, double clip) {
+  AOCR_CHECK(have_grads_, "no gradients yet: call aocr_forward_backward first");
+  for (int g = 0; g < 5; g++) {
+    int nb = sq_blocks(L.gsize[g]);
+    sumsq_partial(ctx_, d_grads + L.goff[g], L.gsize[g], d_sq_partial + g * 1024, nb);
+    sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + g);
+    sgd_apply(ctx_, d_params + L.goff[g], d_grads + L.goff[g], L.gsize[g], d_sumsq + g, lr, clip);
+  }
+  weights_dirty_ = true;
+}
+
+// forward_only branch, beam 1, no trie (model.lua:360-404,446-459,516-536,570-627)
+void Engine::decode_enqueue() {
+  AOCR_CHECK(have_batch_, "no batch staged");
+  AOCR_CUDA(cudaSetDevice(device_));
+  const int B = b_, T = T_, Ld = Tmax;
+  prep_weights();
+  gather_tokens(ctx_, tgt_bt, tgt_tb, B, T, Ld, 1);   // model.lua:266-274: pad to max_decoder_l with PAD
+  gather_tokens(ctx_, tev_bt, tev_tb, B, T, Ld, 1);
+  cnn_forward(false);
+  encoder_forward();
+  dec_steps_ = Ld;
+  // greedy pass
+  AOCR_CUDA(cudaMemcpyAsync(tok, tgt_tb, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx_.st));  // GO row
+  decoder_init();
+  for (int t = 0; t < Ld; t++) {
+    decoder_step(t, tok);
+    float* lp = logp[1] + (int64_t)t * B * V;
+    generator_fwd(ctx_, A_all + (int64_t)t * B * Hd, d_params + L.wo, d_params + L.bo, nullptr, lp, nullptr, nullptr, B,
+                  Hd, V, 1.0f);
+    greedy_select(ctx_, lp, tok, score, labels, Ld, t, B, V);
+  }
+  // gold pass: teacher forced with the padded targets (model.lua:589-627)
+  decoder_init();
+  for (int t = 0; t < Ld; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
+  generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[2], nullptr, rowloss, (int64_t)Ld * B, Hd, V,
+                1.0f);
+  reduce_sum_double(ctx_, rowloss, (int64_t)Ld * B, d_loss);
+  last_logp_rows_[1] = last_logp_rows_[2] = Ld * B;
+}
+
+void Engine::decode_collect(int32_t* out_labels, double* pred, double* gold, double* loss_sum, int32_t* num_correct) {
+  const int B = b_, Ld = Tmax, T = T_;
+  std::vector<int32_t> hl((size_t)B * Ld);
+  std::vector<double> hs(B);
+  std::vector<float> hr((size_t)Ld * B);
+  double hloss = 0.0;
+  AOCR_CUDA(cudaMemcpyAsync(hl.data(), labels, hl.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx_.st));
+  AOCR_CUDA(cudaMemcpyAsync(hs.data(), score, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx_.st));
+  AOCR_CUDA(cudaMemcpyAsync(hr.data(), rowloss, hr.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx_.st));
+  AOCR_CUDA(cudaMemcpyAsync(&hloss, d_loss, sizeof(double), cudaMemcpyDeviceToHost, ctx_.st));
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  if (out_labels) memcpy(out_labels, hl.data(), hl.size() * sizeof(int32_t));
+  if (pred) memcpy(pred, hs.data(), hs.size() * sizeof(double));
+  if (gold) {
+    for (int b = 0; b < B; b++) {
+      double s = 0.0;
+      for (int t = 0; t < Ld; t++) s -= (double)hr[(size_t)t * B + b];
+      gold[b] = s;
+    }
+  }
+  if (loss_sum) *loss_sum = hloss;
+  if (num_correct) {
+    // evalWordErrRate (utils.lua:136-175): compare id lists up to (not including) the first EOS (3)
+    int nc = 0;
+    for (int b = 0; b < B; b++) {
+      int lp = 0, lt = 0;
+      while (lp < Ld && hl[(size_t)b * Ld + lp] != 3) lp++;
+      auto tv = [&](int t) { return t < T ? h_tev_[(size_t)b * T + t] : 1; };
+      while (lt < Ld && tv(lt) != 3) lt++;
+      bool same = (lp == lt);
+      for (int t = 0; same && t < lp; t++) same = (hl[(size_t)b * Ld + t] == tv(t));
+      nc += same ? 1 : 0;
+    }
+    *num_correct = nc;
+  }
+}
+
+void Engine::get_logprobs(int which, float* out, int64_t n) {
+  AOCR_CHECK(which >= 0 && which < 3, "which must be 0 (train), 1 (greedy) or 2 (gold)");
+  AOCR_CHECK(last_logp_rows_[which] > 0, "no log-probs of that kind have been produced yet");
+  AOCR_CHECK(n == (int64_t)last_logp_rows_[which] * V, "log-prob buffer length mismatch");
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  AOCR_CUDA(cudaMemcpy(out, logp[which], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+void Engine::debug_read(const char* name, float* out, int64_t n) {
+  auto it = taps_.find(name);
+  AOCR_CHECK(it != taps_.end(), std::string("unknown debug tap: ") + name);
+  AOCR_CHECK(n == it->second.n, "debug tap length mismatch");
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  AOCR_CUDA(cudaMemcpy(out, it->second.ptr, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+}  // namespace aocr

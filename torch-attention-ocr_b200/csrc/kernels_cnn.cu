@@ -1,0 +1,416 @@
+// kernels_cnn.cu — memory-bound pieces of the CNN (reference: src/model/cnn.lua:9-45):
+// conv1 (K=9, too thin for tensor cores), ReLU+max-pool, batch-norm, im2col, column reductions.
+// All activations are NHWC fp32 (channel fastest) so every warp access is a contiguous run of channels.
+#include "kernels.h"
+
+namespace aocr {
+
+namespace {
+
+constexpr float BN_EPS = 1e-5f;
+
+// ------------------------------------------------------------------ conv1
+// thread = one pooled output element (n, ph, pw, c); the 4x4 input patch is shared by the 64 channel
+// threads (L1 broadcast), weights live in smem.
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ a1,
+                                                        uint8_t* __restrict__ idx, int B, int W) {
+  __shared__ float ws[64 * 9];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int W1 = W / 2;
+  const int64_t total = (int64_t)B * 16 * W1 * 64;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % 64);
+    int64_t r = e / 64;
+    int pw = (int)(r % W1); r /= W1;
+    int ph = (int)(r % 16);
+    int n = (int)(r / 16);
+    const float* xi = x + (int64_t)n * 32 * W;
+    float p[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int h = 2 * ph - 1 + i;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int ww = 2 * pw - 1 + j;
+        float v = 0.f;
+        if (h >= 0 && h < 32 && ww >= 0 && ww < W) v = (xi[h * W + ww] - 128.0f) * (1.0f / 128.0f);
+        p[i][j] = v;
+      }
+    }
+    float best = -1.f;
+    int bi = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 2; dx++) {
+        float s = bs[c];
+#pragma unroll
+        for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+          for (int kw = 0; kw < 3; kw++) s = fmaf(ws[c * 9 + kh * 3 + kw], p[dy + kh][dx + kw], s);
+        s = fmaxf(s, 0.f);
+        if (s > best) { best = s; bi = dy * 2 + dx; }
+      }
+    a1[e] = best;
+    idx[e] = (uint8_t)bi;
+  }
+}
+
+// dW1[c][tap] = sum over pooled elements with a1>0 of da1 * xnorm(argmax position + tap); db1[c] = sum da1*(a1>0).
+// block = 64 channel lanes x 4 pixel lanes; each block reduces a contiguous slab of pooled pixels, writes a
+// (10 x 64) partial; a second kernel folds the partials in fixed order (deterministic).
+__global__ void __launch_bounds__(256) conv1_bwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ a1,
+                                                                const uint8_t* __restrict__ idx,
+                                                                const float* __restrict__ da1, float* __restrict__ partial,
+                                                                int B, int W, int64_t pix_per_blk) {
+  const int c = threadIdx.x % 64, lane = threadIdx.x / 64;   // 4 pixel lanes
+  const int W1 = W / 2;
+  const int64_t npix = (int64_t)B * 16 * W1;
+  int64_t p0 = (int64_t)blockIdx.x * pix_per_blk;
+  int64_t p1 = p0 + pix_per_blk < npix ? p0 + pix_per_blk : npix;
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) acc[i] = 0.f;
+  for (int64_t p = p0 + lane; p < p1; p += 4) {
+    float g = da1[p * 64 + c];
+    float a = a1[p * 64 + c];
+    if (!(a > 0.f) || g == 0.f) continue;
+    int bi = idx[p * 64 + c];
+    int64_t r = p;
+    int pw = (int)(r % W1); r /= W1;
+    int ph = (int)(r % 16);
+    int n = (int)(r / 16);
+    int h0 = 2 * ph + (bi >> 1) - 1, w0 = 2 * pw + (bi & 1) - 1;
+    const float* xi = x + (int64_t)n * 32 * W;
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+      for (int kw = 0; kw < 3; kw++) {
+        int h = h0 + kh, ww = w0 + kw;
+        float v = 0.f;
+        if (h >= 0 && h < 32 && ww >= 0 && ww < W) v = (xi[h * W + ww] - 128.0f) * (1.0f / 128.0f);
+        acc[kh * 3 + kw] = fmaf(g, v, acc[kh * 3 + kw]);
+      }
+    acc[9] += g;
+  }
+  __shared__ float red[4][10][64];
+#pragma unroll
+  for (int i = 0; i < 10; i++) red[lane][i][c] = acc[i];
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; i++)
+      partial[((int64_t)blockIdx.x * 10 + i) * 64 + c] = red[0][i][c] + red[1][i][c] + red[2][i][c] + red[3][i][c];
+  }
+}
+__global__ void conv1_bwd_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw,
+                                       float* __restrict__ db) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;   // 640 outputs
+  if (e >= 640) return;
+  int i = e / 64, c = e % 64;
+  float s = 0.f;
+  for (int b = 0; b < nblk; b++) s += partial[((int64_t)b * 10 + i) * 64 + c];
+  if (i < 9) dw[c * 9 + i] += s; else db[c] += s;
+}
+
+// ------------------------------------------------------------------ ReLU + max-pool
+template <int KW>
+__global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restrict__ z, float* __restrict__ a,
+                                                            uint8_t* __restrict__ idx, int B, int H, int Wi, int C) {
+  const int Ho = H / 2, Wo = Wi / KW;
+  const int64_t total = (int64_t)B * Ho * Wo * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    int64_t r = e / C;
+    int pw = (int)(r % Wo); r /= Wo;
+    int ph = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    float best = -1.f;
+    int bi = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (int dx = 0; dx < KW; dx++) {
+        float v = z[(((int64_t)n * H + 2 * ph + dy) * Wi + KW * pw + dx) * C + c];
+        v = fmaxf(v, 0.f);
+        if (v > best) { best = v; bi = dy * 2 + dx; }
+      }
+    a[e] = best;
+    idx[e] = (uint8_t)bi;
+  }
+}
+
+// one thread per *input* (pre-pool) element so dz is written exactly once, coalesced, incl. zeros and
+// the floor-mode leftover column.
+template <int KW>
+__global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a,
+                                                            const uint8_t* __restrict__ idx, float* __restrict__ dz,
+                                                            int B, int H, int Wi, int C) {
+  const int Ho = H / 2, Wo = Wi / KW;
+  const int64_t total = (int64_t)B * H * Wi * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    int64_t r = e / C;
+    int w = (int)(r % Wi); r /= Wi;
+    int h = (int)(r % H);
+    int n = (int)(r / H);
+    int ph = h / 2, pw = w / KW;
+    float v = 0.f;
+    if (ph < Ho && pw < Wo) {
+      int64_t o = (((int64_t)n * Ho + ph) * Wo + pw) * C + c;
+      int bi = (h & 1) * 2 + (KW == 2 ? (w & 1) : 0);
+      if (idx[o] == bi && a[o] > 0.f) v = da[o];
+    }
+    dz[e] = v;
+  }
+}
+
+// ------------------------------------------------------------------ im2col
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ a, float* __restrict__ col, int B, int H,
+                                                     int Wi, int C, int k, int pad, int Ho, int Wo) {
+  const int C4 = C / 4;
+  const int64_t total = (int64_t)B * Ho * Wo * k * k * C4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(e % C4);
+    int64_t r = e / C4;
+    int tap = (int)(r % (k * k)); r /= (k * k);
+    int wo = (int)(r % Wo); r /= Wo;
+    int ho = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    int kh = tap / k, kw = tap % k;
+    int h = ho + kh - pad, w = wo + kw - pad;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h >= 0 && h < H && w >= 0 && w < Wi)
+      v = *reinterpret_cast<const float4*>(a + (((int64_t)n * H + h) * Wi + w) * C + c4 * 4);
+    *reinterpret_cast<float4*>(col + e * 4) = v;
+  }
+}
+
+// ------------------------------------------------------------------ column reductions over (R, C)
+// mode 0: sum z ; mode 1: sum (z-mean)^2 ; mode 2: sum z*xhat where xhat=(z2-mean)*inv  (z = dy)
+// grid (C/32, nslab); block 32 x 8: each thread walks rows r = slab*rows_per + ty, += 8
+__global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict__ z, const float* __restrict__ z2,
+                                                         const float* __restrict__ mean, const float* __restrict__ var,
+                                                         int64_t R, int C, int64_t rows_per, int mode,
+                                                         float* __restrict__ partial) {
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + tx;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per;
+  int64_t r1 = r0 + rows_per < R ? r0 + rows_per : R;
+  float acc = 0.f;
+  if (c < C) {
+    float mu = (mode >= 1) ? mean[c] : 0.f;
+    float inv = (mode == 2) ? rsqrtf(var[c] + BN_EPS) : 0.f;
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float v = z[r * C + c];
+      if (mode == 0) acc += v;
+      else if (mode == 1) { float d = v - mu; acc = fmaf(d, d, acc); }
+      else acc = fmaf(v, (z2[r * C + c] - mu) * inv, acc);
+    }
+  }
+  __shared__ float red[8][33];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += red[i][tx];
+    partial[(int64_t)blockIdx.y * C + c] = s;
+  }
+}
+// out[c] (op)= scale * sum_slab partial ; op: 0 set, 1 add
+__global__ void col_reduce_final_kernel(const float* __restrict__ partial, int nslab, int C, float scale, int accumulate,
+                                        float* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int i = 0; i < nslab; i++) s += partial[(int64_t)i * C + c];
+  s *= scale;
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+__global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var,
+                                         float* __restrict__ rmean, float* __restrict__ rvar, int C, float unbias) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  rmean[c] = 0.9f * rmean[c] + 0.1f * mean[c];
+  rvar[c] = 0.9f * rvar[c] + 0.1f * var[c] * unbias;
+}
+
+__global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                                          const float* __restrict__ var, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ a, int64_t R,
+                                                          int C, int tm_S, int tm_B) {
+  const int C4 = C / 4;
+  const int64_t total = R * C4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C4) * 4;
+    int64_t r = e / C4;
+    float4 v = *reinterpret_cast<const float4*>(z + r * C + c);
+    float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    float4 va = *reinterpret_cast<const float4*>(var + c);
+    float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = fmaxf(fmaf((v.x - mu.x) * rsqrtf(va.x + BN_EPS), ga.x, be.x), 0.f);
+    o.y = fmaxf(fmaf((v.y - mu.y) * rsqrtf(va.y + BN_EPS), ga.y, be.y), 0.f);
+    o.z = fmaxf(fmaf((v.z - mu.z) * rsqrtf(va.z + BN_EPS), ga.z, be.z), 0.f);
+    o.w = fmaxf(fmaf((v.w - mu.w) * rsqrtf(va.w + BN_EPS), ga.w, be.w), 0.f);
+    int64_t ro = r;
+    if (tm_S > 0) ro = (r % tm_S) * tm_B + r / tm_S;
+    *reinterpret_cast<float4*>(a + ro * C + c) = o;
+  }
+}
+
+// dy = da * (a > 0), rows optionally read time-major
+__global__ void __launch_bounds__(256) relu_mask_kernel(const float* __restrict__ da, const float* __restrict__ a,
+                                                        float* __restrict__ dy, int64_t R, int C, int tm_S, int tm_B) {
+  const int C4 = C / 4;
+  const int64_t total = R * C4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C4) * 4;
+    int64_t r = e / C4;
+    int64_t ri = r;
+    if (tm_S > 0) ri = (r % tm_S) * tm_B + r / tm_S;
+    float4 g = *reinterpret_cast<const float4*>(da + ri * C + c);
+    float4 v = *reinterpret_cast<const float4*>(a + ri * C + c);
+    float4 o;
+    o.x = v.x > 0.f ? g.x : 0.f;
+    o.y = v.y > 0.f ? g.y : 0.f;
+    o.z = v.z > 0.f ? g.z : 0.f;
+    o.w = v.w > 0.f ? g.w : 0.f;
+    *reinterpret_cast<float4*>(dy + r * C + c) = o;
+  }
+}
+
+// dz = gamma*inv*(dy - s1/R - xhat*s2/R) in place on dz (=dy)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restrict__ z,
+                                                           const float* __restrict__ mean, const float* __restrict__ var,
+                                                           const float* __restrict__ gamma, const float* __restrict__ s1,
+                                                           const float* __restrict__ s2, int64_t R, int C, int train) {
+  const int64_t total = R * C;
+  const float invR = 1.0f / (float)R;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    float inv = rsqrtf(var[c] + BN_EPS);
+    float dy = dz[e];
+    float o;
+    if (train) {
+      float xh = (z[e] - mean[c]) * inv;
+      o = gamma[c] * inv * (dy - s1[c] * invR - xh * s2[c] * invR);
+    } else {
+      o = gamma[c] * inv * dy;
+    }
+    dz[e] = o;
+  }
+}
+
+inline int grid_for(int64_t total, int threads, int num_sms) {
+  int64_t g = (total + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms * 8;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+inline int nslabs_for(int64_t R, int num_sms, int C) {
+  int cb = (C + 31) / 32;
+  int want = (2 * num_sms + cb - 1) / cb;
+  int64_t maxs = (R + 63) / 64;
+  if (want > maxs) want = (int)maxs;
+  if (want < 1) want = 1;
+  if (want > 256) want = 256;
+  return want;
+}
+
+void col_reduce(Ctx& ctx, const float* z, const float* z2, const float* mean, const float* var, int64_t R, int C,
+                int mode, float scale, int accumulate, float* out, float* partial) {
+  int ns = nslabs_for(R, ctx.num_sms, C);
+  int64_t rows_per = (R + ns - 1) / ns;
+  dim3 grid(cdiv(C, 32), ns);
+  col_reduce_kernel<<<grid, 256, 0, ctx.st>>>(z, z2, mean, var, R, C, rows_per, mode, partial);
+  AOCR_LAUNCH_CHECK(ctx);
+  col_reduce_final_kernel<<<cdiv(C, 128), 128, 0, ctx.st>>>(partial, ns, C, scale, accumulate, out);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace
+
+void conv1_fwd(Ctx& ctx, const float* x, const float* w, const float* bias, float* a1, uint8_t* idx, int B, int W) {
+  int64_t total = (int64_t)B * 16 * (W / 2) * 64;
+  conv1_fwd_kernel<<<grid_for(total, 256, ctx.num_sms), 256, 0, ctx.st>>>(x, w, bias, a1, idx, B, W);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void conv1_bwd(Ctx& ctx, const float* x, const float* a1, const uint8_t* idx, const float* da1, float* dw, float* db,
+               float* partial, int nblk, int B, int W) {
+  int64_t npix = (int64_t)B * 16 * (W / 2);
+  int64_t per = (npix + nblk - 1) / nblk;
+  conv1_bwd_partial_kernel<<<nblk, 256, 0, ctx.st>>>(x, a1, idx, da1, partial, B, W, per);
+  AOCR_LAUNCH_CHECK(ctx);
+  conv1_bwd_final_kernel<<<cdiv(640, 128), 128, 0, ctx.st>>>(partial, nblk, dw, db);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void relu_pool_fwd(Ctx& ctx, const float* z, float* a, uint8_t* idx, int B, int H, int Wi, int C, int kw) {
+  int64_t total = (int64_t)B * (H / 2) * (Wi / kw) * C;
+  int g = grid_for(total, 256, ctx.num_sms);
+  if (kw == 2) relu_pool_fwd_kernel<2><<<g, 256, 0, ctx.st>>>(z, a, idx, B, H, Wi, C);
+  else relu_pool_fwd_kernel<1><<<g, 256, 0, ctx.st>>>(z, a, idx, B, H, Wi, C);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void relu_pool_bwd(Ctx& ctx, const float* da, const float* a, const uint8_t* idx, float* dz, int B, int H, int Wi, int C,
+                   int kw) {
+  int64_t total = (int64_t)B * H * Wi * C;
+  int g = grid_for(total, 256, ctx.num_sms);
+  if (kw == 2) relu_pool_bwd_kernel<2><<<g, 256, 0, ctx.st>>>(da, a, idx, dz, B, H, Wi, C);
+  else relu_pool_bwd_kernel<1><<<g, 256, 0, ctx.st>>>(da, a, idx, dz, B, H, Wi, C);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void im2col(Ctx& ctx, const float* a, float* col, int B, int H, int Wi, int C, int k, int pad) {
+  int Ho = H + 2 * pad - k + 1, Wo = Wi + 2 * pad - k + 1;
+  int64_t total = (int64_t)B * Ho * Wo * k * k * (C / 4);
+  im2col_kernel<<<grid_for(total, 256, ctx.num_sms), 256, 0, ctx.st>>>(a, col, B, H, Wi, C, k, pad, Ho, Wo);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void col_sum(Ctx& ctx, const float* z, int64_t R, int C, float* out, float* partial, int accumulate) {
+  col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, 1.0f, accumulate, out, partial);
+}
+
+void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* var, float* partial) {
+  col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, 1.0f / (float)R, 0, mean, partial);
+  col_reduce(ctx, z, nullptr, mean, nullptr, R, C, 1, 1.0f / (float)R, 0, var, partial);
+}
+
+void bn_update_running(Ctx& ctx, const float* mean, const float* var, float* rmean, float* rvar, int C, int64_t R) {
+  float unbias = R > 1 ? (float)((double)R / (double)(R - 1)) : 1.f;
+  bn_update_running_kernel<<<cdiv(C, 128), 128, 0, ctx.st>>>(mean, var, rmean, rvar, C, unbias);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void bn_relu_fwd(Ctx& ctx, const float* z, const float* mean, const float* var, const float* gamma, const float* beta,
+                 float* a, int64_t R, int C, int tm_S, int tm_B) {
+  bn_relu_fwd_kernel<<<grid_for(R * (C / 4), 256, ctx.num_sms), 256, 0, ctx.st>>>(z, mean, var, gamma, beta, a, R, C,
+                                                                                 tm_S, tm_B);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, const float* mean, const float* var,
+                 const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial, int64_t R, int C, int tm_S,
+                 int tm_B, int train) {
+  relu_mask_kernel<<<grid_for(R * (C / 4), 256, ctx.num_sms), 256, 0, ctx.st>>>(da, a, dz, R, C, tm_S, tm_B);
+  AOCR_LAUNCH_CHECK(ctx);
+  // dbeta = s1 ; dgamma = s2 (each BN parameter receives gradient exactly once per step)
+  col_reduce(ctx, dz, nullptr, nullptr, nullptr, R, C, 0, 1.0f, 0, dbeta, partial);
+  col_reduce(ctx, dz, z, mean, var, R, C, 2, 1.0f, 0, dgamma, partial);
+  bn_bwd_apply_kernel<<<grid_for(R * C, 256, ctx.num_sms), 256, 0, ctx.st>>>(dz, z, mean, var, gamma, dbeta, dgamma, R,
+                                                                           C, train);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace aocr
