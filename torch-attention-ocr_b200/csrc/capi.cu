@@ -158,7 +158,7 @@ int aocr_group_extent(aocr_handle* h, int group, int64_t* offset_floats, int64_t
   AOCR_API_BEGIN(h)
   AOCR_CHECK(group >= 0 && group < 5, "group must be in [0,5)");
   if (offset_floats) *offset_floats = h->eng->L.goff[group];
-  if (n_floats) *n_floats = h->eng->L.gsize[group];
+  if (n_floats) *n_floats = h->eng->L.gphys[group];
   AOCR_API_END(h)
 }
 int aocr_forward_backward_staged(aocr_handle* h) {
@@ -203,14 +203,14 @@ extern "C" {
 int aocr_grad_scale(aocr_handle* h, int group, double s) {
   AOCR_API_BEGIN(h)
   AOCR_CHECK(group >= 0 && group < 5, "group must be in [0,5)");
-  aocr::scale_vec(h->eng->ctx_, h->eng->d_grads + h->eng->L.goff[group], h->eng->L.gsize[group], (float)s);
+  aocr::scale_vec(h->eng->ctx_, h->eng->d_grads + h->eng->L.goff[group], h->eng->L.gphys[group], (float)s);
   AOCR_API_END(h)
 }
 int aocr_param_axpy(aocr_handle* h, int group, double a) {
   AOCR_API_BEGIN(h)
   AOCR_CHECK(group >= 0 && group < 5, "group must be in [0,5)");
   aocr::axpy_vec(h->eng->ctx_, h->eng->d_params + h->eng->L.goff[group], h->eng->d_grads + h->eng->L.goff[group],
-                 h->eng->L.gsize[group], (float)a);
+                 h->eng->L.gphys[group], (float)a);
   h->eng->mark_weights_dirty();
   AOCR_API_END(h)
 }

@@ -41,35 +41,46 @@ T* Engine::alloc(int64_t n) {
 
 void Engine::layout_params() {
   int64_t off = 0;
-  auto take = [&](int64_t n) { int64_t o = off; off += n; return o; };
+  int cur_group = 0;
+  int64_t ext = 0;
+  auto take = [&](int64_t n, int cout = 0, int cin = 0, int kk = 0) {
+    off = (off + 63) & ~(int64_t)63;
+    TensorEntry e{cur_group, ext, off, n, cout, cin, kk};
+    L.tensors.push_back(e);
+    int64_t o = off;
+    off += n; ext += n;
+    return o;
+  };
+  auto begin_group = [&](int g) { off = (off + 63) & ~(int64_t)63; cur_group = g; ext = 0; L.goff[g] = off; };
+  auto end_group = [&](int g) { off = (off + 63) & ~(int64_t)63; L.gsize[g] = ext; L.gphys[g] = off - L.goff[g]; };
   const int in1 = E + (cfg.input_feed ? Hd : 0);
-  // physical order: proj | decoder | enc_fw | enc_bw | cnn
-  L.goff[G_PROJ] = off;
+  // physical order: proj | decoder | enc_fw | enc_bw | cnn ; within a group the caller-visible tensor order
+  begin_group(G_PROJ);
   L.wo = take((int64_t)V * Hd); L.bo = take(V);
-  L.gsize[G_PROJ] = off - L.goff[G_PROJ];
-  L.goff[G_DEC] = off;
+  end_group(G_PROJ);
+  begin_group(G_DEC);
   L.emb = take((int64_t)V * E);
   L.l1_wi = take((int64_t)4 * Hd * in1); L.l1_bi = take(4 * Hd);
   L.l1_wh = take((int64_t)4 * Hd * Hd);  L.l1_bh = take(4 * Hd);
   L.l2_wi = take((int64_t)4 * Hd * Hd);  L.l2_bi = take(4 * Hd);
   L.l2_wh = take((int64_t)4 * Hd * Hd);  L.l2_bh = take(4 * Hd);
   L.wa = take((int64_t)Hd * Hd); L.wc = take((int64_t)Hd * 2 * Hd);
-  L.gsize[G_DEC] = off - L.goff[G_DEC];
+  end_group(G_DEC);
   for (int d = 0; d < 2; d++) {
     int g = d == 0 ? G_ENC_FW : G_ENC_BW;
-    L.goff[g] = off;
+    begin_group(g);
     L.enc_wi[d] = take((int64_t)4 * He * 512); L.enc_bi[d] = take(4 * He);
     L.enc_wh[d] = take((int64_t)4 * He * He);  L.enc_bh[d] = take(4 * He);
-    L.gsize[g] = off - L.goff[g];
+    end_group(g);
   }
-  L.goff[G_CNN] = off;
+  begin_group(G_CNN);
   for (int l = 0; l < 7; l++) {
     const ConvSpec& c = kConv[l];
-    L.conv_w[l] = take((int64_t)c.cout * c.cin * c.k * c.k);
+    L.conv_w[l] = take((int64_t)c.cout * c.cin * c.k * c.k, c.cout, c.cin, c.k * c.k);
     L.conv_b[l] = take(c.cout);
     if (c.bn >= 0) { L.bn_g[c.bn] = take(c.cout); L.bn_b[c.bn] = take(c.cout); }
   }
-  L.gsize[G_CNN] = off - L.goff[G_CNN];
+  end_group(G_CNN);
   L.total = off;
 }
 
@@ -179,16 +190,15 @@ void Engine::set_params(int group, const float* host, int64_t n) {
   AOCR_CHECK(group >= 0 && group < 5, "group must be in [0,5)");
   AOCR_CHECK(n == L.gsize[group], "parameter vector length does not match the group size");
   AOCR_CUDA(cudaSetDevice(device_));
-  std::vector<float> tmp(host, host + n);
-  if (group == G_CNN) {
-    for (int l = 0; l < 7; l++) {
-      const ConvSpec& c = kConv[l];
-      int64_t o = L.conv_w[l] - L.goff[G_CNN];
-      permute_conv(host + o, tmp.data() + o, c.cout, c.cin, c.k * c.k, true);
-    }
+  std::vector<float> tmp(L.gphys[group], 0.0f);
+  for (const TensorEntry& e : L.tensors) {
+    if (e.group != group) continue;
+    float* dst = tmp.data() + (e.phys_off - L.goff[group]);
+    if (e.conv_kk) permute_conv(host + e.ext_off, dst, e.conv_cout, e.conv_cin, e.conv_kk, true);
+    else memcpy(dst, host + e.ext_off, e.n * sizeof(float));
   }
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
-  AOCR_CUDA(cudaMemcpy(d_params + L.goff[group], tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  AOCR_CUDA(cudaMemcpy(d_params + L.goff[group], tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
   weights_dirty_ = true;
 }
 
@@ -199,15 +209,13 @@ void Engine::get_flat(bool grads, int group, float* host, int64_t n) {
   AOCR_CUDA(cudaSetDevice(device_));
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
   const float* base = grads ? d_grads : d_params;
-  std::vector<float> tmp(n);
-  AOCR_CUDA(cudaMemcpy(tmp.data(), base + L.goff[group], n * sizeof(float), cudaMemcpyDeviceToHost));
-  memcpy(host, tmp.data(), n * sizeof(float));
-  if (group == G_CNN) {
-    for (int l = 0; l < 7; l++) {
-      const ConvSpec& c = kConv[l];
-      int64_t o = L.conv_w[l] - L.goff[G_CNN];
-      permute_conv(tmp.data() + o, host + o, c.cout, c.cin, c.k * c.k, false);
-    }
+  std::vector<float> tmp(L.gphys[group]);
+  AOCR_CUDA(cudaMemcpy(tmp.data(), base + L.goff[group], tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (const TensorEntry& e : L.tensors) {
+    if (e.group != group) continue;
+    const float* srcp = tmp.data() + (e.phys_off - L.goff[group]);
+    if (e.conv_kk) permute_conv(srcp, host + e.ext_off, e.conv_cout, e.conv_cin, e.conv_kk, false);
+    else memcpy(host + e.ext_off, srcp, e.n * sizeof(float));
   }
 }
 

@@ -18,8 +18,14 @@ enum Group { G_CNN = 0, G_ENC_FW = 1, G_ENC_BW = 2, G_DEC = 3, G_PROJ = 4 };
 struct ConvSpec { int cin, cout, k, pad, bn /* -1 or bn index */, pool_kw /* 0 none, 1: 2x1, 2: 2x2 */; };
 extern const ConvSpec kConv[7];
 
+// one parameter tensor: where it sits in the caller-visible ("Torch") group vector and in the device buffer.
+// Device offsets are padded to 64 floats so every tensor is 256-byte aligned (float4 / TMA requirements);
+// the padding holds zeros in both params and grads, so group norms and axpys are unaffected.
+struct TensorEntry { int group; int64_t ext_off, phys_off, n; int conv_cout, conv_cin, conv_kk; };
+
 struct ParamLayout {
-  int64_t goff[5], gsize[5], total;
+  int64_t goff[5], gsize[5] /* caller-visible sizes */, gphys[5] /* device extent incl. padding */, total;
+  std::vector<TensorEntry> tensors;
   int64_t conv_w[7], conv_b[7], bn_g[3], bn_b[3];
   int64_t enc_wi[2], enc_bi[2], enc_wh[2], enc_bh[2];
   int64_t emb, l1_wi, l1_bi, l1_wh, l1_bh, l2_wi, l2_bi, l2_wh, l2_bh, wa, wc;

@@ -271,13 +271,13 @@ static int sq_blocks(int64_t n) { return (int)(n / 4096 + 1 < 1024 ? n / 4096 + 
 void Engine::group_norms(double* pn, double* gn) {
   AOCR_CHECK(have_grads_, "no gradients yet: call aocr_forward_backward first");
   for (int g = 0; g < 5; g++) {
-    int nb = sq_blocks(L.gsize[g]);
-    sumsq_partial(ctx_, d_grads + L.goff[g], L.gsize[g], d_sq_partial + g * 1024, nb);
+    int nb = sq_blocks(L.gphys[g]);
+    sumsq_partial(ctx_, d_grads + L.goff[g], L.gphys[g], d_sq_partial + g * 1024, nb);
     sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + g);
   }
   for (int g = 0; g < 5; g++) {
-    int nb = sq_blocks(L.gsize[g]);
-    sumsq_partial(ctx_, d_params + L.goff[g], L.gsize[g], d_sq_partial + g * 1024, nb);
+    int nb = sq_blocks(L.gphys[g]);
+    sumsq_partial(ctx_, d_params + L.goff[g], L.gphys[g], d_sq_partial + g * 1024, nb);
     sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + 5 + g);
   }
   double h[10];
@@ -290,10 +290,10 @@ void Engine::group_norms(double* pn, double* gn) {
 void Engine::sgd_enqueue(double lr, double clip) {
   AOCR_CHECK(have_grads_, "no gradients yet: call aocr_forward_backward first");
   for (int g = 0; g < 5; g++) {
-    int nb = sq_blocks(L.gsize[g]);
-    sumsq_partial(ctx_, d_grads + L.goff[g], L.gsize[g], d_sq_partial + g * 1024, nb);
+    int nb = sq_blocks(L.gphys[g]);
+    sumsq_partial(ctx_, d_grads + L.goff[g], L.gphys[g], d_sq_partial + g * 1024, nb);
     sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + g);
-    sgd_apply(ctx_, d_params + L.goff[g], d_grads + L.goff[g], L.gsize[g], d_sumsq + g, lr, clip);
+    sgd_apply(ctx_, d_params + L.goff[g], d_grads + L.goff[g], L.gphys[g], d_sumsq + g, lr, clip);
   }
   weights_dirty_ = true;
 }
