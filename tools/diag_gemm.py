@@ -1,0 +1,18 @@
+"""GPU diagnostic: error of each GEMM back end on a few shapes (prints, never asserts)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "torch-attention-ocr_b200")]
+import numpy as np
+from aocr.capi import selftest_gemm
+rng = np.random.default_rng(0)
+for (M, N, K) in [(128, 128, 64), (128, 128, 128), (256, 256, 256), (200, 96, 200), (512, 4, 2048), (130, 17, 70)]:
+    A = rng.standard_normal((M, K)).astype(np.float32); B = rng.standard_normal((K, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    for mode in (2, 1, 0):
+        for swap in ((False, True) if mode != 2 else (False,)):
+            try:
+                C = selftest_gemm(A, B, ta=False, tb=True, mode=mode, swap=swap)
+                err = np.abs(C - ref).max() / np.abs(ref).max()
+                print(f"M{M} N{N} K{K} mode{mode} swap{int(swap)} err {err:.3e}", flush=True)
+            except Exception as e:
+                print(f"M{M} N{N} K{K} mode{mode} swap{int(swap)} EXC {e}", flush=True)

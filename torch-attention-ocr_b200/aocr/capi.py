@@ -68,6 +68,28 @@ _SYMBOLS = {
 }
 
 
+_SELFTEST = ("aocr_selftest_gemm", (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]))
+
+
+def selftest_gemm(A, B, ta=False, tb=False, mode=0, swap=False):
+    """C = A @ B through the library's GEMM back ends (test hook; not part of include/aocr.h)."""
+    lib = Lib.get()
+    fn = getattr(lib.dll, _SELFTEST[0])
+    fn.restype, fn.argtypes = _SELFTEST[1]
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2
+    a = np.ascontiguousarray(A.T if ta else A, dtype=np.float32)
+    b = np.ascontiguousarray(B.T if tb else B, dtype=np.float32)
+    c = np.empty((M, N), np.float32)
+    err = C.create_string_buffer(512)
+    rc = fn(M, N, K, int(ta), int(tb), mode, int(swap), _ptr(a), _ptr(b), _ptr(c), err, 512)
+    if rc != 0:
+        raise AocrError(rc, err.value.decode())
+    return c
+
+
 def exported_symbols():
     return sorted(_SYMBOLS)
 

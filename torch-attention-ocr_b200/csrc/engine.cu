@@ -39,6 +39,14 @@ T* Engine::alloc(int64_t n) {
   return reinterpret_cast<T*>(p);
 }
 
+Pack Engine::alloc_pack(int64_t rows, int64_t kp) {
+  Pack p;
+  p.rows = rows; p.kp = kp;
+  p.hi = alloc<__nv_bfloat16>(rows * kp);
+  p.lo = alloc<__nv_bfloat16>(rows * kp);
+  return p;
+}
+
 void Engine::layout_params() {
   int64_t off = 0;
   int cur_group = 0;
@@ -136,6 +144,10 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   gB = alloc<float>(B * 16 * W1 * 128);
   partial = alloc<float>((int64_t)256 * 8192);
   tmpvec = alloc<float>(8192);
+  if (cfg.gemm_mode != 2) {
+    scratch_elems_ = B * W1 * 18432 + (int64_t)4608 * 64 * 8;
+    for (int i = 0; i < 2; i++) scratch_[i] = alloc_pack(1, scratch_elems_);
+  }
   for (int l = 1; l < 7; l++) wt[l] = alloc<float>((int64_t)kConv[l].cout * kConv[l].cin * kConv[l].k * kConv[l].k);
 
   xg = alloc<float>(S * B * 8 * He);
@@ -199,7 +211,7 @@ void Engine::set_params(int group, const float* host, int64_t n) {
   }
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
   AOCR_CUDA(cudaMemcpy(d_params + L.goff[group], tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
-  weights_dirty_ = true;
+  mark_weights_dirty();
 }
 
 void Engine::get_flat(bool grads, int group, float* host, int64_t n) {
@@ -237,18 +249,19 @@ void Engine::get_bn(int layer, float* mean, float* var, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 void Engine::stage_batch(const float* images, int b, int W, const int32_t* tgt, const int32_t* tev, int T) {
   AOCR_CHECK(b >= 1 && b <= Bmax, "batch larger than config.batch_size");
-  AOCR_CHECK(W >= 8 && W <= Wmax, "image width out of range for max_encoder_l");
   char msg[128];
   if (T > Tmax) {   // model.lua:264
     snprintf(msg, sizeof(msg), "max_decoder_l (%d) < target_l (%d)!", Tmax, T);
     throw InvalidError(msg);
   }
   AOCR_CHECK(T >= 1, "target_l must be >= 1");
+  AOCR_CHECK(W >= 8, "image too narrow");
   int S = (W / 2) / 2 - 1;
   if (S > Smax) {   // model.lua:287
     snprintf(msg, sizeof(msg), "max_encoder_l (%d) < source_l (%d)!", Smax, S);
     throw InvalidError(msg);
   }
+  AOCR_CHECK(W <= Wmax, "image width out of range for max_encoder_l");
   AOCR_CHECK(S >= 1, "image too narrow: source_l < 1");
   for (int64_t i = 0; i < (int64_t)b * T; i++)
     AOCR_CHECK(tgt[i] >= 1 && tgt[i] <= V && tev[i] >= 1 && tev[i] <= V, "token id outside [1, target_vocab_size]");
@@ -273,11 +286,6 @@ void Engine::prof_end(int cls, double work) {
   prof_ms[cls] += ms; prof_launches[cls] += 1; prof_work[cls] += work;
 }
 
-void Engine::gemm(const Gemm& g, int cls) {
-  prof_begin(cls);
-  gemm_simt(ctx_, g);
-  prof_end(cls, 2.0 * g.M * g.N * (double)g.K * g.batch);
-}
 
 void Engine::conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const {
   // l = 1..6 (0-based index into kConv): input of conv_{l+1}

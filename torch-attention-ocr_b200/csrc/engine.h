@@ -7,6 +7,9 @@
 
 #include "../../include/aocr.h"
 #include "kernels.h"
+#include "gemm_tc.cuh"
+#include <tuple>
+#include <string.h>
 
 namespace aocr {
 
@@ -54,7 +57,7 @@ class Engine {
   void get_logprobs(int which, float* out, int64_t n);
   void debug_read(const char* name, float* out, int64_t n);
   void sync() { AOCR_CUDA(cudaStreamSynchronize(ctx_.st)); }
-  void mark_weights_dirty() { weights_dirty_ = true; }
+  void mark_weights_dirty() { weights_dirty_ = true; weights_version_++; }
 
   aocr_config cfg;
   ParamLayout L;
@@ -81,10 +84,18 @@ class Engine {
   void decoder_step(int t, const int32_t* tok);
   void decoder_backward();
   void conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const;
+  Pack alloc_pack(int64_t rows, int64_t kp);
+  bool is_param(const float* p) const;
+  Pack operand_pack(const float* ptr, int64_t rows, int64_t K, int64_t srs, int64_t sks, int slot);
   void prof_begin(int cls);
   void prof_end(int cls, double work);
 
   int device_;
+  struct WeightPack { Pack pack; int64_t version; };
+  std::map<std::tuple<const float*, int64_t, int64_t, int64_t, int64_t>, WeightPack> wcache_;
+  int64_t weights_version_ = 0;
+  Pack scratch_[2];
+  int64_t scratch_elems_ = 0;
   int He, Hd, E, V, K1, h1off, Bmax, Smax, Tmax, Wmax;
   std::vector<void*> allocs_;
   std::map<std::string, Tap> taps_;

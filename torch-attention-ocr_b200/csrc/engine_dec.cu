@@ -295,7 +295,7 @@ void Engine::sgd_enqueue(double lr, double clip) {
     sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + g);
     sgd_apply(ctx_, d_params + L.goff[g], d_grads + L.goff[g], L.gphys[g], d_sumsq + g, lr, clip);
   }
-  weights_dirty_ = true;
+  mark_weights_dirty();
 }
 
 // forward_only branch, beam 1, no trie (model.lua:360-404,446-459,516-536,570-627)

@@ -1,0 +1,123 @@
+// engine_gemm.cu — routes every contraction of the step to the tcgen05 GEMM core (gemm_tc.cu) or, for the
+// thin shapes tensor cores cannot help (K < 64: generator K=39, embedding K=20, attention-gradient K=T),
+// to the fp32 FFMA kernel.  Operands are converted fp32 -> (hi, lo) bf16 planes on the way in; parameter
+// operands are converted once per weight update and cached.
+#include "engine.h"
+
+namespace aocr {
+
+// parameters, and the flipped/transposed conv weights derived from them in prep_weights()
+bool Engine::is_param(const float* p) const {
+  if (p >= d_params && p < d_params + L.total) return true;
+  for (int l = 1; l < 7; l++) {
+    const int64_t n = (int64_t)kConv[l].cout * kConv[l].cin * kConv[l].k * kConv[l].k;
+    if (wt[l] && p >= wt[l] && p < wt[l] + n) return true;
+  }
+  return false;
+}
+
+// operand (rows x K, strides srs/sks) as a K-major pack: cached for parameters, scratch slot otherwise
+Pack Engine::operand_pack(const float* ptr, int64_t rows, int64_t K, int64_t srs, int64_t sks, int slot) {
+  const int64_t kp = pad64(K);
+  if (is_param(ptr)) {
+    auto key = std::make_tuple(ptr, rows, K, srs, sks);
+    auto it = wcache_.find(key);
+    if (it == wcache_.end()) {
+      WeightPack wp;
+      wp.pack = alloc_pack(rows, kp);
+      wp.version = -1;
+      it = wcache_.emplace(key, wp).first;
+    }
+    if (it->second.version != weights_version_) {
+      split_to_pack(ctx_, ptr, rows, K, srs, sks, it->second.pack);
+      it->second.version = weights_version_;
+    }
+    return it->second.pack;
+  }
+  AOCR_CHECK(rows * kp <= scratch_elems_, "operand larger than the scratch pack (internal sizing error)");
+  Pack p;
+  p.rows = rows; p.kp = kp; p.hi = scratch_[slot].hi; p.lo = scratch_[slot].lo;
+  split_to_pack(ctx_, ptr, rows, K, srs, sks, p);
+  return p;
+}
+
+void Engine::gemm(const Gemm& g, int cls) {
+  prof_begin(cls);
+  const bool tc = cfg.gemm_mode != 2 && g.batch == 1 && g.K >= 64 && (g.M >= 64 || g.N >= 64);
+  if (!tc) {
+    gemm_simt(ctx_, g);
+  } else {
+    TcGemm t;
+    const bool swap = g.M < g.N;   // the larger side becomes the 128-row M side of the UMMA tile
+    Pack pa = operand_pack(g.A, g.M, g.K, g.sam, g.sak, 0);                 // rows m
+    Pack pb = operand_pack(g.B, g.N, g.K, g.sbn, g.sbk, 1);                 // rows n
+    t.K = g.K; t.C = g.C; t.ldc = g.ldc; t.act = g.act; t.accumulate = g.accumulate;
+    t.terms = cfg.gemm_mode == 1 ? 1 : 3;
+    if (!swap) {
+      t.A = pa; t.B = pb; t.M = g.M; t.N = g.N; t.transpose_out = false;
+      t.bias_m = g.bias_m; t.bias_n = g.bias_n;
+    } else {
+      t.A = pb; t.B = pa; t.M = g.N; t.N = g.M; t.transpose_out = true;
+      t.bias_m = g.bias_n; t.bias_n = g.bias_m;
+    }
+    gemm_tc(ctx_, t);
+  }
+  prof_end(cls, 2.0 * g.M * g.N * (double)g.K * g.batch);
+}
+
+}  // namespace aocr
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone GEMM self test (no handle): C = A(MxK) * B(KxN), row-major fp32 host buffers.
+// mode 0: tcgen05 bf16x3, 1: tcgen05 bf16, 2: fp32 SIMT.  ta/tb: operand stored transposed.
+extern "C" int aocr_selftest_gemm(int M, int N, int K, int ta, int tb, int mode, int swap, const float* A,
+                                  const float* B, float* C, char* err, int errlen) {
+  using namespace aocr;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  __nv_bfloat16* planes[4] = {nullptr, nullptr, nullptr, nullptr};
+  Ctx ctx;
+  int rc = 0;
+  try {
+    AOCR_CUDA(cudaStreamCreate(&ctx.st));
+    AOCR_CUDA(cudaMalloc(&dA, (size_t)M * K * 4));
+    AOCR_CUDA(cudaMalloc(&dB, (size_t)K * N * 4));
+    AOCR_CUDA(cudaMalloc(&dC, (size_t)M * N * 4));
+    AOCR_CUDA(cudaMemcpy(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));
+    AOCR_CUDA(cudaMemcpy(dB, B, (size_t)K * N * 4, cudaMemcpyHostToDevice));
+    AOCR_CUDA(cudaMemset(dC, 0, (size_t)M * N * 4));
+    // element strides of the logical operands inside the stored buffers
+    int64_t sam = ta ? 1 : K, sak = ta ? M : 1;       // A(m,k)
+    int64_t sbk = tb ? 1 : N, sbn = tb ? K : 1;       // B(k,n)
+    if (mode == 2) {
+      Gemm g;
+      g.M = M; g.N = N; g.K = K; g.A = dA; g.sam = sam; g.sak = sak; g.B = dB; g.sbk = sbk; g.sbn = sbn;
+      g.C = dC; g.ldc = N;
+      gemm_simt(ctx, g);
+    } else {
+      int64_t kp = pad64(K);
+      AOCR_CUDA(cudaMalloc(&planes[0], (size_t)M * kp * 2));
+      AOCR_CUDA(cudaMalloc(&planes[1], (size_t)M * kp * 2));
+      AOCR_CUDA(cudaMalloc(&planes[2], (size_t)N * kp * 2));
+      AOCR_CUDA(cudaMalloc(&planes[3], (size_t)N * kp * 2));
+      Pack pa, pb;
+      pa.hi = planes[0]; pa.lo = planes[1]; pa.rows = M; pa.kp = kp;
+      pb.hi = planes[2]; pb.lo = planes[3]; pb.rows = N; pb.kp = kp;
+      split_to_pack(ctx, dA, M, K, sam, sak, pa);
+      split_to_pack(ctx, dB, N, K, sbn, sbk, pb);
+      TcGemm t;
+      t.K = K; t.C = dC; t.ldc = N; t.terms = mode == 1 ? 1 : 3;
+      if (!swap) { t.A = pa; t.B = pb; t.M = M; t.N = N; t.transpose_out = false; }
+      else { t.A = pb; t.B = pa; t.M = N; t.N = M; t.transpose_out = true; }
+      gemm_tc(ctx, t);
+    }
+    AOCR_CUDA(cudaStreamSynchronize(ctx.st));
+    AOCR_CUDA(cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  } catch (const std::exception& e) {
+    if (err && errlen > 0) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    rc = -2;
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  for (auto p : planes) cudaFree(p);
+  if (ctx.st) cudaStreamDestroy(ctx.st);
+  return rc;
+}

@@ -1,0 +1,470 @@
+// gemm_tc.cu — the tensor-core contraction of libaocr: tcgen05.mma (UMMA 128 x BN x 16, kind::f16, bf16
+// operands, fp32 accumulators in TMEM) fed by TMA (cp.async.bulk.tensor, 128B swizzle) through a 3-4 stage
+// mbarrier pipeline.  One CTA per 128 x BN output tile; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// alloc), warps 2-5 = epilogue (tcgen05.ld -> bias/activation -> global).
+//
+// fp32-grade mode ("bf16x3"): every operand is stored as two bf16 planes x ~= hi + lo; each k-step issues
+// hi*hi + hi*lo + lo*hi into the same TMEM accumulator, which keeps ~16 mantissa bits per operand (needed for
+// the 1e-3 logit bar and tie-exact greedy decode against the float64 oracle; plain bf16 cannot meet them).
+//
+// Convolution = implicit GEMM: the A operand is the NHWC activation itself, addressed by a 4-D tensor map
+// (C, W, H, N); for every filter tap the producer shifts the box origin by (kw-pad, kh-pad) and TMA's
+// out-of-bounds zero fill supplies the padding halo.  No im2col buffer exists.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "gemm_tc.cuh"
+
+namespace aocr {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_PLANE_BYTES = BM * BK * 2;   // 16 KB
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kBPlane = BN * BK * 2;
+  static constexpr int kStageBytes = 2 * A_PLANE_BYTES + 2 * kBPlane;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+  int M, N, K;
+  int num_kb;
+  int terms;
+  // conv mode
+  int conv;
+  int cin_blocks, ksz, pad;
+  int bw, bh, bn, tiles_w, tiles_h;
+  int Nimg, Ho, Wo;
+  // epilogue
+  float* C;
+  long long ldc;
+  int transpose_out;
+  const float* bias_m;
+  const float* bias_n;
+  int act;
+  int accumulate;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// SM100 shared-memory matrix descriptor, K-major, 128-byte swizzle: start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 |
+// version 1 << 46 | SWIZZLE_128B (2) << 61      (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const TcParams p) {
+  using C_ = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bars = base + C_::kStages * C_::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C_::kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * C_::kStages);
+  const uint32_t tmem_slot = bars + 8u * (2 * C_::kStages + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  // M-tile origin
+  int m0 = blockIdx.y * BM;
+  int cn0 = 0, ch0 = 0, cw0 = 0;
+  if (p.conv) {
+    int id = blockIdx.y;
+    int wb = id % p.tiles_w; id /= p.tiles_w;
+    int hb = id % p.tiles_h; id /= p.tiles_h;
+    cn0 = id * p.bn; ch0 = hb * p.bh; cw0 = wb * p.bw;
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_::kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+  }
+  if (warp == 1) {   // TMEM allocation (whole warp, .sync.aligned)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(C_::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(p.terms == 3 ? 2 : 1) * (A_PLANE_BYTES + C_::kBPlane);
+      for (int kb = 0; kb < p.num_kb; kb++) {
+        const int s = kb % C_::kStages;
+        const uint32_t ph = (uint32_t)(kb / C_::kStages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t sa = base + s * C_::kStageBytes;
+        const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+        mbar_expect_tx(full_bar(s), tx);
+        if (p.conv) {
+          const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+          const int kh = tap / p.ksz, kw = tap % p.ksz;
+          tma_load_4d(sa, &tmAh, full_bar(s), cb * BK, cw0 + kw - p.pad, ch0 + kh - p.pad, cn0);
+          if (p.terms == 3)
+            tma_load_4d(sa + A_PLANE_BYTES, &tmAl, full_bar(s), cb * BK, cw0 + kw - p.pad, ch0 + kh - p.pad, cn0);
+        } else {
+          tma_load_2d(sa, &tmAh, full_bar(s), kb * BK, m0);
+          if (p.terms == 3) tma_load_2d(sa + A_PLANE_BYTES, &tmAl, full_bar(s), kb * BK, m0);
+        }
+        tma_load_2d(sb, &tmBh, full_bar(s), kb * BK, n0);
+        if (p.terms == 3) tma_load_2d(sb + C_::kBPlane, &tmBl, full_bar(s), kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected lane) =====================
+    const uint32_t idesc = make_idesc(BN);
+    for (int kb = 0; kb < p.num_kb; kb++) {
+      const int s = kb % C_::kStages;
+      const uint32_t ph = (uint32_t)(kb / C_::kStages) & 1u;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = base + s * C_::kStageBytes;
+        const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+        const uint64_t dah = make_desc_kmajor_sw128(sa), dal = make_desc_kmajor_sw128(sa + A_PLANE_BYTES);
+        const uint64_t dbh = make_desc_kmajor_sw128(sb), dbl = make_desc_kmajor_sw128(sb + C_::kBPlane);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; k++) {
+          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 bytes per k-step inside the swizzle row
+          tc_mma(tmem_base, dah + adv, dbh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (p.terms == 3) {
+            tc_mma(tmem_base, dah + adv, dbl + adv, idesc, 1u);
+            tc_mma(tmem_base, dal + adv, dbh + adv, idesc, 1u);
+          }
+        }
+        tc_commit(empty_bar(s));                       // frees the smem slot when these MMAs retire
+        if (kb == p.num_kb - 1) tc_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;                            // TMEM lane quadrant this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int ml = q * 32 + lane;                      // row inside the tile
+    long long row = (long long)m0 + ml;
+    bool row_ok = row < p.M;
+    if (p.conv) {
+      const int wl = ml % p.bw, hl = (ml / p.bw) % p.bh, nl = ml / (p.bw * p.bh);
+      const int n = cn0 + nl, h = ch0 + hl, w = cw0 + wl;
+      row_ok = (n < p.Nimg) && (h < p.Ho) && (w < p.Wo);
+      row = ((long long)n * p.Ho + h) * p.Wo + w;
+    }
+    const float bm = (p.bias_m && row_ok) ? p.bias_m[row] : 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int n = n0 + c0 + j;
+          if (n < p.N) {
+            float v = __uint_as_float(r[j]) + bm;
+            if (p.bias_n) v += p.bias_n[n];
+            if (p.act == ACT_TANH) v = tanhf(v);
+            float* dst = p.transpose_out ? p.C + (long long)n * p.ldc + row : p.C + row * p.ldc + n;
+            if (p.accumulate) v += *dst;
+            *dst = v;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ fp32 -> (hi, lo) bf16 planes
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  l = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+// k contiguous in the source (sks == 1): one thread per 4 consecutive k
+__global__ void __launch_bounds__(256) split_kfast_kernel(const float* __restrict__ src, int64_t rows, int64_t K,
+                                                          int64_t srs, int64_t kp, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ lo) {
+  const int64_t kq = kp / 4;
+  const int64_t total = rows * kq;
+  const bool vec = ((srs & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / kq, k = (e % kq) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec && k + 3 < K) {
+      float4 t = *reinterpret_cast<const float4*>(src + r * srs + k);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (k + j < K) v[j] = src[r * srs + k + j];
+    }
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) split2(v[j], h[j], l[j]);
+    *reinterpret_cast<uint2*>(hi + r * kp + k) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + r * kp + k) = *reinterpret_cast<uint2*>(l);
+  }
+}
+// general strides (typically srs == 1: the transposing case): 32x32 tile through shared memory
+__global__ void __launch_bounds__(256) split_tile_kernel(const float* __restrict__ src, int64_t rows, int64_t K,
+                                                         int64_t srs, int64_t sks, int64_t kp,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+  // read with the source-contiguous index on tx
+  const bool rows_fast = (srs == 1);
+  for (int i = ty; i < 32; i += 8) {
+    int64_t r = rows_fast ? r0 + tx : r0 + i;
+    int64_t k = rows_fast ? k0 + i : k0 + tx;
+    float v = (r < rows && k < K) ? src[r * srs + k * sks] : 0.f;
+    if (rows_fast) tile[tx][i] = v; else tile[i][tx] = v;     // tile[row][k]
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int64_t r = r0 + i, k = k0 + tx;
+    if (r < rows && k < kp) {
+      __nv_bfloat16 h, l;
+      split2(tile[i][tx], h, l);
+      hi[r * kp + k] = h;
+      lo[r * kp + k] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ tensor map cache
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+void resolve_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+}
+
+typedef std::tuple<const void*, int64_t, int64_t, int64_t, int64_t, int, int, int, int> MapKey;
+std::map<MapKey, CUtensorMap> g_maps;
+std::mutex g_maps_mu;
+
+// 2-D K-major plane [rows][kp], box = 64 x box_rows
+const CUtensorMap& map_2d(const __nv_bfloat16* ptr, int64_t rows, int64_t kp, int box_rows) {
+  MapKey key(ptr, rows, kp, 0, 0, box_rows, 0, 0, 2);
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled(2d) failed: " + std::to_string((int)r));
+  return g_maps.emplace(key, tm).first->second;
+}
+// 4-D NHWC activation (C, W, H, N), box = 64 x bw x bh x bn
+const CUtensorMap& map_4d(const __nv_bfloat16* ptr, int N, int H, int W, int C, int bw, int bh, int bn) {
+  MapKey key(ptr, N, H, W, C, bw, bh, bn, 4);
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  CUtensorMap tm;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled(4d) failed: " + std::to_string((int)r));
+  return g_maps.emplace(key, tm).first->second;
+}
+
+template <int BN>
+void launch(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+            const TcParams& p, dim3 grid) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AOCR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  tc_gemm_kernel<BN><<<grid, 192, Cfg<BN>::kSmemBytes, ctx.st>>>(ah, al, bh, bl, p);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace
+
+bool gemm_tc_available() {
+  resolve_encode();
+  return g_encode != nullptr;
+}
+
+void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst) {
+  AOCR_CHECK(dst.kp == pad64(K) && dst.rows >= rows, "split_to_pack: destination pack too small");
+  if (sks == 1) {
+    int64_t total = rows * (dst.kp / 4);
+    int64_t g = (total + 255) / 256;
+    int64_t cap = (int64_t)ctx.num_sms * 8;
+    split_kfast_kernel<<<(unsigned)(g < cap ? (g > 0 ? g : 1) : cap), 256, 0, ctx.st>>>(src, rows, K, srs, dst.kp, dst.hi,
+                                                                                    dst.lo);
+  } else {
+    dim3 grid((unsigned)((dst.kp + 31) / 32), (unsigned)((rows + 31) / 32));
+    split_tile_kernel<<<grid, 256, 0, ctx.st>>>(src, rows, K, srs, sks, dst.kp, dst.hi, dst.lo);
+  }
+  AOCR_LAUNCH_CHECK(ctx);
+}
+
+void gemm_tc(Ctx& ctx, const TcGemm& g) {
+  resolve_encode();
+  if (!g_encode) throw CudaError("cuTensorMapEncodeTiled entry point not found (driver too old?)");
+  AOCR_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "gemm_tc: empty problem");
+  int BN = g.N > 64 ? 128 : (g.N > 32 ? 64 : (g.N > 16 ? 32 : 16));
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.terms = g.terms;
+  p.C = g.C; p.ldc = g.ldc; p.transpose_out = g.transpose_out ? 1 : 0;
+  p.bias_m = g.bias_m; p.bias_n = g.bias_n; p.act = g.act; p.accumulate = g.accumulate;
+  dim3 grid;
+  grid.x = (g.N + BN - 1) / BN;
+  const CUtensorMap *ah, *al;
+  if (g.conv) {
+    const ConvView& c = *g.conv;
+    AOCR_CHECK(c.C % BK == 0 && g.A.kp == c.C, "conv A pack must be NHWC with C a multiple of 64");
+    AOCR_CHECK(g.K == c.k * c.k * c.C && g.B.kp == pad64(g.K), "conv weight pack must be [Cout][k*k*C]");
+    int bw = 8;
+    while (bw < c.Wo && bw < 128) bw *= 2;
+    int bh = 1;
+    while (bh * 2 * bw <= 128 && bh < c.Ho) bh *= 2;
+    int bn = 128 / (bw * bh);
+    p.conv = 1; p.cin_blocks = c.C / BK; p.ksz = c.k; p.pad = c.pad;
+    p.bw = bw; p.bh = bh; p.bn = bn;
+    p.tiles_w = (c.Wo + bw - 1) / bw; p.tiles_h = (c.Ho + bh - 1) / bh;
+    p.Nimg = c.N; p.Ho = c.Ho; p.Wo = c.Wo;
+    p.num_kb = c.k * c.k * p.cin_blocks;
+    grid.y = p.tiles_w * p.tiles_h * ((c.N + bn - 1) / bn);
+    ah = &map_4d(g.A.hi, c.N, c.H, c.W, c.C, bw, bh, bn);
+    al = &map_4d(g.A.lo, c.N, c.H, c.W, c.C, bw, bh, bn);
+  } else {
+    AOCR_CHECK(g.A.kp == g.B.kp && g.A.kp >= g.K, "gemm_tc: operand packs disagree on padded K");
+    p.num_kb = (int)(pad64(g.K) / BK);
+    grid.y = (g.M + BM - 1) / BM;
+    ah = &map_2d(g.A.hi, g.A.rows, g.A.kp, BM);
+    al = &map_2d(g.A.lo, g.A.rows, g.A.kp, BM);
+  }
+  const CUtensorMap& bh_ = map_2d(g.B.hi, g.B.rows, g.B.kp, BN);
+  const CUtensorMap& bl_ = map_2d(g.B.lo, g.B.rows, g.B.kp, BN);
+  grid.z = 1;
+  switch (BN) {
+    case 128: launch<128>(ctx, *ah, *al, bh_, bl_, p, grid); break;
+    case 64: launch<64>(ctx, *ah, *al, bh_, bl_, p, grid); break;
+    case 32: launch<32>(ctx, *ah, *al, bh_, bl_, p, grid); break;
+    default: launch<16>(ctx, *ah, *al, bh_, bl_, p, grid); break;
+  }
+}
+
+}  // namespace aocr

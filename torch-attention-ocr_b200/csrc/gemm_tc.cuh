@@ -1,0 +1,43 @@
+// gemm_tc.cuh — host interface of the tcgen05/TMEM/TMA GEMM core (definitions in gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace aocr {
+
+// A GEMM operand as bf16 planes: x ~= hi + lo (hi = bf16(x), lo = bf16(x - hi)).  `rows` x `kp` row-major
+// ("K-major"), kp = K rounded up to 64 and zero-padded, so every row is a whole number of 128-byte TMA boxes.
+struct Pack {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int64_t rows = 0, kp = 0;
+};
+inline int64_t pad64(int64_t k) { return (k + 63) & ~(int64_t)63; }
+
+// fp32 (rows x K, element (r,k) at src[r*srs + k*sks]) -> Pack.  Handles either stride being 1 with
+// coalesced access (the transposing case goes through a shared-memory tile).
+void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst);
+
+// NHWC view of a Pack for the implicit-GEMM convolution: rows = n*H*W pixels, kp = C channels.
+struct ConvView {
+  int N = 0, H = 0, W = 0, C = 0;      // input activation
+  int k = 0, pad = 0;                  // kernel size, padding
+  int Ho = 0, Wo = 0;                  // output spatial dims
+};
+
+struct TcGemm {
+  // D[m][n] = sum_k A[m][k] * B[n][k]; A is the M side (128-row tiles), B the N side.
+  Pack A, B;
+  int M = 0, N = 0, K = 0;             // logical sizes (K <= A.kp == B.kp), or K = k*k*C in conv mode
+  const ConvView* conv = nullptr;      // if set: A is an NHWC activation pack, M = N*Ho*Wo output pixels
+  float* C = nullptr; int64_t ldc = 0;
+  bool transpose_out = false;          // false: C[m*ldc+n] ; true: C[n*ldc+m]
+  const float* bias_m = nullptr;       // indexed by m
+  const float* bias_n = nullptr;       // indexed by n
+  int act = ACT_NONE;
+  int accumulate = 0;
+  int terms = 3;                       // 3: hi*hi + hi*lo + lo*hi (fp32-grade) ; 1: hi*hi (plain bf16)
+};
+void gemm_tc(Ctx& ctx, const TcGemm& g);
+bool gemm_tc_available();   // driver entry point for cuTensorMapEncodeTiled resolved
+
+}  // namespace aocr
