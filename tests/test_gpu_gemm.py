@@ -36,3 +36,18 @@ def test_tcgen05_bf16x3_gemm(shape):
 @pytest.mark.parametrize("shape", SHAPES[:4])
 def test_tcgen05_bf16_gemm(shape):
     _check(*shape, False, True, 1, False, 2e-2)
+
+
+@pytest.mark.parametrize("shape,splits", [((256, 64, 1024), 4), ((128, 16, 4096), 16), ((200, 96, 640), 3),
+                                          ((1024, 64, 4096), 0), ((4096, 64, 2048), 0)])
+def test_tcgen05_split_k(shape, splits):
+    from aocr.capi import selftest_gemm
+    M, N, K = shape
+    rng = np.random.default_rng(K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    c1 = selftest_gemm(A, B, tb=True, mode=0, splits=splits)
+    c2 = selftest_gemm(A, B, tb=True, mode=0, splits=splits)
+    assert np.abs(c1 - ref).max() / np.abs(ref).max() < 3e-5
+    assert np.array_equal(c1, c2), "split-K reduction must be deterministic"

@@ -69,10 +69,10 @@ _SYMBOLS = {
 
 
 _SELFTEST = ("aocr_selftest_gemm", (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                              C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]))
+                                              C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int]))
 
 
-def selftest_gemm(A, B, ta=False, tb=False, mode=0, swap=False):
+def selftest_gemm(A, B, ta=False, tb=False, mode=0, swap=False, splits=0):
     """C = A @ B through the library's GEMM back ends (test hook; not part of include/aocr.h)."""
     lib = Lib.get()
     fn = getattr(lib.dll, _SELFTEST[0])
@@ -84,7 +84,7 @@ def selftest_gemm(A, B, ta=False, tb=False, mode=0, swap=False):
     b = np.ascontiguousarray(B.T if tb else B, dtype=np.float32)
     c = np.empty((M, N), np.float32)
     err = C.create_string_buffer(512)
-    rc = fn(M, N, K, int(ta), int(tb), mode, int(swap), _ptr(a), _ptr(b), _ptr(c), err, 512)
+    rc = fn(M, N, K, int(ta), int(tb), mode, int(swap), _ptr(a), _ptr(b), _ptr(c), err, 512, splits)
     if rc != 0:
         raise AocrError(rc, err.value.decode())
     return c

@@ -36,6 +36,11 @@ struct Ctx {
   cudaStream_t st = nullptr;
   int64_t launches = 0;
   int num_sms = 148;
+  // split-K workspace of the tcgen05 GEMM (partial tiles + per-tile arrival counters)
+  float* tc_ws = nullptr;
+  int64_t tc_ws_floats = 0;
+  int* tc_counters = nullptr;
+  int tc_counters_n = 0;
 };
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -145,6 +145,10 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   partial = alloc<float>((int64_t)256 * 8192);
   tmpvec = alloc<float>(8192);
   if (cfg.gemm_mode != 2) {
+    ctx_.tc_ws_floats = (int64_t)32 * 148 * 128 * 128;
+    ctx_.tc_ws = alloc<float>(ctx_.tc_ws_floats);
+    ctx_.tc_counters_n = 4096;
+    ctx_.tc_counters = alloc<int>(ctx_.tc_counters_n);
     scratch_elems_ = B * W1 * 18432 + (int64_t)4608 * 64 * 8;
     for (int i = 0; i < 2; i++) scratch_[i] = alloc_pack(1, scratch_elems_);
   }

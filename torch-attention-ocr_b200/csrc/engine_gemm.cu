@@ -71,7 +71,7 @@ void Engine::gemm(const Gemm& g, int cls) {
 // stand-alone GEMM self test (no handle): C = A(MxK) * B(KxN), row-major fp32 host buffers.
 // mode 0: tcgen05 bf16x3, 1: tcgen05 bf16, 2: fp32 SIMT.  ta/tb: operand stored transposed.
 extern "C" int aocr_selftest_gemm(int M, int N, int K, int ta, int tb, int mode, int swap, const float* A,
-                                  const float* B, float* C, char* err, int errlen) {
+                                  const float* B, float* C, char* err, int errlen, int splits) {
   using namespace aocr;
   float *dA = nullptr, *dB = nullptr, *dC = nullptr;
   __nv_bfloat16* planes[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -79,6 +79,11 @@ extern "C" int aocr_selftest_gemm(int M, int N, int K, int ta, int tb, int mode,
   int rc = 0;
   try {
     AOCR_CUDA(cudaStreamCreate(&ctx.st));
+    ctx.tc_ws_floats = (int64_t)32 * 148 * 128 * 128;
+    AOCR_CUDA(cudaMalloc(&ctx.tc_ws, ctx.tc_ws_floats * 4));
+    ctx.tc_counters_n = 4096;
+    AOCR_CUDA(cudaMalloc(&ctx.tc_counters, 4096 * 4));
+    AOCR_CUDA(cudaMemset(ctx.tc_counters, 0, 4096 * 4));
     AOCR_CUDA(cudaMalloc(&dA, (size_t)M * K * 4));
     AOCR_CUDA(cudaMalloc(&dB, (size_t)K * N * 4));
     AOCR_CUDA(cudaMalloc(&dC, (size_t)M * N * 4));
@@ -105,7 +110,7 @@ extern "C" int aocr_selftest_gemm(int M, int N, int K, int ta, int tb, int mode,
       split_to_pack(ctx, dA, M, K, sam, sak, pa);
       split_to_pack(ctx, dB, N, K, sbn, sbk, pb);
       TcGemm t;
-      t.K = K; t.C = dC; t.ldc = N; t.terms = mode == 1 ? 1 : 3;
+      t.K = K; t.C = dC; t.ldc = N; t.terms = mode == 1 ? 1 : 3; t.force_splits = splits;
       if (!swap) { t.A = pa; t.B = pb; t.M = M; t.N = N; t.transpose_out = false; }
       else { t.A = pb; t.B = pa; t.M = N; t.N = M; t.transpose_out = true; }
       gemm_tc(ctx, t);
@@ -116,7 +121,7 @@ extern "C" int aocr_selftest_gemm(int M, int N, int K, int ta, int tb, int mode,
     if (err && errlen > 0) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
     rc = -2;
   }
-  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(ctx.tc_ws); cudaFree(ctx.tc_counters);
   for (auto p : planes) cudaFree(p);
   if (ctx.st) cudaStreamDestroy(ctx.st);
   return rc;

@@ -52,6 +52,10 @@ struct TcParams {
   const float* bias_n;
   int act;
   int accumulate;
+  // split-K: blockIdx.z owns k-blocks [z*kb_per, (z+1)*kb_per) and writes its raw partial to ws + z*part_stride
+  int splits, kb_per;
+  float* ws;
+  long long part_stride;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -141,6 +145,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const uint32_t tmem_slot = bars + 8u * (2 * C_::kStages + 1);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int kb_begin = blockIdx.z * p.kb_per;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per);
+  const int nkb = kb_end - kb_begin;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -176,9 +183,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(p.terms == 3 ? 2 : 1) * (A_PLANE_BYTES + C_::kBPlane);
-      for (int kb = 0; kb < p.num_kb; kb++) {
-        const int s = kb % C_::kStages;
-        const uint32_t ph = (uint32_t)(kb / C_::kStages) & 1u;
+      for (int i = 0; i < nkb; i++) {
+        const int kb = kb_begin + i;
+        const int s = i % C_::kStages;
+        const uint32_t ph = (uint32_t)(i / C_::kStages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t sa = base + s * C_::kStageBytes;
         const uint32_t sb = sa + 2 * A_PLANE_BYTES;
@@ -200,9 +208,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
     const uint32_t idesc = make_idesc(BN);
-    for (int kb = 0; kb < p.num_kb; kb++) {
-      const int s = kb % C_::kStages;
-      const uint32_t ph = (uint32_t)(kb / C_::kStages) & 1u;
+    for (int i = 0; i < nkb; i++) {
+      const int s = i % C_::kStages;
+      const uint32_t ph = (uint32_t)(i / C_::kStages) & 1u;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       if (lane == 0) {
@@ -213,14 +221,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; k++) {
           const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 bytes per k-step inside the swizzle row
-          tc_mma(tmem_base, dah + adv, dbh + adv, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma(tmem_base, dah + adv, dbh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
           if (p.terms == 3) {
             tc_mma(tmem_base, dah + adv, dbl + adv, idesc, 1u);
             tc_mma(tmem_base, dal + adv, dbh + adv, idesc, 1u);
           }
         }
         tc_commit(empty_bar(s));                       // frees the smem slot when these MMAs retire
-        if (kb == p.num_kb - 1) tc_commit(tmem_full_bar);
+        if (i == nkb - 1) tc_commit(tmem_full_bar);
       }
       __syncwarp();
     }
@@ -239,6 +247,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       row = ((long long)n * p.Ho + h) * p.Wo + w;
     }
     const float bm = (p.bias_m && row_ok) ? p.bias_m[row] : 0.f;
+    // split-K: raw partial sums go to ws + z*part_stride with the indexing of C; a reduce kernel (or the consumer
+    // kernel) sums the `splits` partials in fixed order, so the result is deterministic
+    float* __restrict__ outp = p.splits > 1 ? p.ws + (long long)blockIdx.z * p.part_stride : p.C;
+    const bool plain = (p.splits > 1);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t r[16];
@@ -249,18 +261,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row_ok) {
+      if (!row_ok) continue;
+      const int nb = n0 + c0;
+      float bias[16], old[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          const int n = n0 + c0 + j;
-          if (n < p.N) {
-            float v = __uint_as_float(r[j]) + bm;
-            if (p.bias_n) v += p.bias_n[n];
+      for (int j = 0; j < 16; j++) { bias[j] = 0.f; old[j] = 0.f; }
+      if (!plain) {        // gather every read-modify-write / bias load of this chunk first (one latency, not 16)
+        if (p.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (nb + j < p.N)
+              old[j] = p.transpose_out ? p.C[(long long)(nb + j) * p.ldc + row] : p.C[row * p.ldc + nb + j];
+        }
+        if (p.bias_n) {
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (nb + j < p.N) bias[j] = p.bias_n[nb + j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int n = nb + j;
+        if (n < p.N) {
+          float v = __uint_as_float(r[j]);
+          if (!plain) {
+            v += bm + bias[j];
             if (p.act == ACT_TANH) v = tanhf(v);
-            float* dst = p.transpose_out ? p.C + (long long)n * p.ldc + row : p.C + row * p.ldc + n;
-            if (p.accumulate) v += *dst;
-            *dst = v;
+            v += old[j];
           }
+          float* dst = p.transpose_out ? outp + (long long)n * p.ldc + row : outp + row * p.ldc + n;
+          *dst = v;
         }
       }
     }
@@ -327,6 +357,25 @@ __global__ void __launch_bounds__(256) split_tile_kernel(const float* __restrict
       hi[r * kp + k] = h;
       lo[r * kp + k] = l;
     }
+  }
+}
+
+// ------------------------------------------------------------------ split-K reduction + epilogue
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int nz, long long part_stride,
+                                                            float* __restrict__ C, long long rows, long long cols,
+                                                            long long ldc, const float* __restrict__ bias_r,
+                                                            const float* __restrict__ bias_c, int act, int accumulate) {
+  const long long total = rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / cols, c = e % cols;
+    const long long off = r * ldc + c;
+    float v = 0.f;
+    for (int z = 0; z < nz; z++) v += ws[(long long)z * part_stride + off];
+    if (bias_r) v += bias_r[r];
+    if (bias_c) v += bias_c[c];
+    if (act == ACT_TANH) v = tanhf(v);
+    if (accumulate) v += C[off];
+    C[off] = v;
   }
 }
 
@@ -458,12 +507,38 @@ void gemm_tc(Ctx& ctx, const TcGemm& g) {
   }
   const CUtensorMap& bh_ = map_2d(g.B.hi, g.B.rows, g.B.kp, BN);
   const CUtensorMap& bl_ = map_2d(g.B.lo, g.B.rows, g.B.kp, BN);
-  grid.z = 1;
+  // split-K when the output tiles alone cannot fill the machine (per-timestep decoder GEMMs, weight gradients)
+  const long long tiles = (long long)grid.x * grid.y;
+  const long long crows = g.transpose_out ? g.N : g.M, ccols = g.transpose_out ? g.M : g.N;
+  const long long part_stride = ((crows - 1) * g.ldc + ccols + 63) & ~63LL;
+  int splits = 1;
+  if (ctx.tc_ws && tiles * 2 <= ctx.num_sms && p.num_kb >= 4) {
+    splits = (int)(ctx.num_sms / tiles);
+    if (splits > p.num_kb / 2) splits = p.num_kb / 2;
+    if (splits > 16) splits = 16;
+  }
+  if (g.force_splits > 0 && ctx.tc_ws) splits = g.force_splits < p.num_kb ? g.force_splits : p.num_kb;
+  while (splits > 1 && (long long)splits * part_stride > ctx.tc_ws_floats) splits--;
+  if (splits < 1) splits = 1;
+  p.kb_per = (p.num_kb + splits - 1) / splits;
+  p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;
+  p.ws = ctx.tc_ws; p.part_stride = part_stride;
+  grid.z = p.splits;
   switch (BN) {
     case 128: launch<128>(ctx, *ah, *al, bh_, bl_, p, grid); break;
     case 64: launch<64>(ctx, *ah, *al, bh_, bl_, p, grid); break;
     case 32: launch<32>(ctx, *ah, *al, bh_, bl_, p, grid); break;
     default: launch<16>(ctx, *ah, *al, bh_, bl_, p, grid); break;
+  }
+  if (p.splits > 1) {
+    const float* bias_r = g.transpose_out ? g.bias_n : g.bias_m;
+    const float* bias_c = g.transpose_out ? g.bias_m : g.bias_n;
+    const long long total = crows * ccols;
+    long long nb = (total + 255) / 256;
+    if (nb > (long long)ctx.num_sms * 8) nb = (long long)ctx.num_sms * 8;
+    splitk_reduce_kernel<<<(unsigned)nb, 256, 0, ctx.st>>>(ctx.tc_ws, p.splits, part_stride, g.C, crows, ccols, g.ldc,
+                                                           bias_r, bias_c, g.act, g.accumulate);
+    AOCR_LAUNCH_CHECK(ctx);
   }
 }
 

@@ -36,6 +36,7 @@ struct TcGemm {
   int act = ACT_NONE;
   int accumulate = 0;
   int terms = 3;                       // 3: hi*hi + hi*lo + lo*hi (fp32-grade) ; 1: hi*hi (plain bf16)
+  int force_splits = 0;                // test hook: force a split-K factor
 };
 void gemm_tc(Ctx& ctx, const TcGemm& g);
 bool gemm_tc_available();   // driver entry point for cuTensorMapEncodeTiled resolved
