@@ -151,6 +151,16 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     ctx_.tc_counters = alloc<int>(ctx_.tc_counters_n);
     scratch_elems_ = B * W1 * 18432 + (int64_t)4608 * 64 * 8;
     for (int i = 0; i < 2; i++) scratch_[i] = alloc_pack(1, scratch_elems_);
+    // tensor-core decoder path (engine_dec_tc.cu)
+    const int64_t Hd_ = 2 * c.encoder_num_hidden, K1_ = c.input_feed ? 2 * Hd_ : Hd_, Tm = c.max_decoder_l;
+    Wcat1p = alloc_pack(4 * Hd_, K1_); Wcat2p = alloc_pack(4 * Hd_, 2 * Hd_);
+    Wap = alloc_pack(Hd_, Hd_); Wcp = alloc_pack(Hd_, 2 * Hd_);
+    Wcat1Tp = alloc_pack(K1_, 4 * Hd_); Wcat2Tp = alloc_pack(2 * Hd_, 4 * Hd_);
+    WaTp = alloc_pack(Hd_, Hd_); WcTp = alloc_pack(2 * Hd_, Hd_);
+    X1p = alloc_pack(Tm * B, K1_); X2p = alloc_pack(Tm * B, 2 * Hd_); CATp = alloc_pack(Tm * B, 2 * Hd_);
+    dUp = alloc_pack(B, Hd_); dQp = alloc_pack(B, Hd_); dG2p = alloc_pack(B, 4 * Hd_); dG1p = alloc_pack(B, 4 * Hd_);
+    dec_ws_floats = (int64_t)16 * B * 4 * Hd_ + 1024;
+    for (int i = 0; i < 4; i++) dec_ws[i] = alloc<float>(dec_ws_floats);
   }
   for (int l = 1; l < 7; l++) wt[l] = alloc<float>((int64_t)kConv[l].cout * kConv[l].cin * kConv[l].k * kConv[l].k);
 
@@ -321,6 +331,7 @@ void Engine::prep_weights() {
   g.B = d_params + L.l1_wi; g.sbk = 1; g.sbn = in1;
   g.C = Ptab; g.ldc = 4 * Hd; g.bias_n = bsum1;
   gemm_simt(ctx_, g);
+  if (cfg.gemm_mode != 2) build_decoder_packs();
   weights_dirty_ = false;
 }
 

@@ -7,6 +7,7 @@
 
 #include "../../include/aocr.h"
 #include "kernels.h"
+#include "kernels_dec.h"
 #include "gemm_tc.cuh"
 #include <tuple>
 #include <string.h>
@@ -83,6 +84,11 @@ class Engine {
   void decoder_init();
   void decoder_step(int t, const int32_t* tok);
   void decoder_backward();
+  void decoder_step_simt(int t, const int32_t* tok);
+  void decoder_step_tc(int t, const int32_t* tok);
+  void decoder_backward_steps_simt();
+  void decoder_backward_steps_tc();
+  void build_decoder_packs();
   void conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const;
   Pack alloc_pack(int64_t rows, int64_t kp);
   bool is_param(const float* p) const;
@@ -95,6 +101,12 @@ class Engine {
   std::map<std::tuple<const float*, int64_t, int64_t, int64_t, int64_t>, WeightPack> wcache_;
   int64_t weights_version_ = 0;
   Pack scratch_[2];
+  // tensor-core decoder path: concatenated weight packs, per-step operand packs, split-K partial regions
+  Pack Wcat1p, Wcat2p, Wap, Wcp, Wcat1Tp, Wcat2Tp, WaTp, WcTp;
+  Pack X1p, X2p, CATp, dUp, dQp, dG2p, dG1p;
+  float* dec_ws[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t dec_ws_floats = 0;
+  int64_t dec_packs_version_ = -1;
   int64_t scratch_elems_ = 0;
   int He, Hd, E, V, K1, h1off, Bmax, Smax, Tmax, Wmax;
   std::vector<void*> allocs_;

@@ -25,11 +25,21 @@ void Engine::decoder_init() {
   }
   fill_zero(ctx_, C2, (size_t)B * Hd * sizeof(float));
   fill_zero(ctx_, X2, (size_t)B * 2 * Hd * sizeof(float));
+  if (cfg.gemm_mode != 2) {   // the same initial state as bf16 operand planes for the first step's GEMMs
+    Pack x1_0 = X1p; x1_0.rows = B;
+    split_to_pack(ctx_, X1, B, K1, K1, 1, x1_0);
+    fill_zero(ctx_, X2p.hi, (size_t)B * 2 * Hd * sizeof(__nv_bfloat16));
+    fill_zero(ctx_, X2p.lo, (size_t)B * 2 * Hd * sizeof(__nv_bfloat16));
+  }
 }
 
 // One decoder step (src/model/LSTM.lua:18-162).  Saved-state layout, per step t:
 //   X1[t] = [a_{t-1} | h1_{t-1}]   X2[t] = [h1_t | h2_{t-1}]   CAT[t] = [cv_t | h2_t]   A_all[t] = a_t
 void Engine::decoder_step(int t, const int32_t* tokens) {
+  if (cfg.gemm_mode != 2) decoder_step_tc(t, tokens); else decoder_step_simt(t, tokens);
+}
+
+void Engine::decoder_step_simt(int t, const int32_t* tokens) {
   const int B = b_, S = S_;
   const int in1 = E + (cfg.input_feed ? Hd : 0);
   const int nsteps = dec_steps_;
@@ -100,29 +110,11 @@ void Engine::decoder_step(int t, const int32_t* tokens) {
   if (cfg.input_feed && has_next) copy_strided(ctx_, x1 + (int64_t)B * K1, K1, a, Hd, B, Hd);
 }
 
-// decoder backward through time (model.lua:643-661) with every parameter gradient time-batched afterwards
-void Engine::decoder_backward() {
+// per-timestep part of the decoder backward, fp32 SIMT flavour (gemm_mode 2: on-device cross-check path)
+void Engine::decoder_backward_steps_simt() {
   const int B = b_, S = S_, T = T_;
   const int in1 = E + (cfg.input_feed ? Hd : 0);
-  const int64_t R = (int64_t)T * B;
-  const float inv_bn = 1.0f / (float)(cfg.global_batch > 0 ? cfg.global_batch : B);
-  // generator + criterion for all steps at once (a_t are all known): model.lua:644-648
-  generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[0], dZ, rowloss, R, Hd, V, inv_bn);
-  reduce_sum_double(ctx_, rowloss, R, d_loss);
   Gemm g;
-  g.M = (int)R; g.N = Hd; g.K = V;                       // dA_gen = dZ W_o
-  g.A = dZ; g.sam = V; g.sak = 1;
-  g.B = d_params + L.wo; g.sbk = Hd; g.sbn = 1;
-  g.C = dAgen; g.ldc = Hd;
-  gemm(g);
-  g = Gemm();
-  g.M = V; g.N = Hd; g.K = (int)R;                       // dW_o = dZ^T A
-  g.A = dZ; g.sam = 1; g.sak = V;
-  g.B = A_all; g.sbk = Hd; g.sbn = 1;
-  g.C = d_grads + L.wo; g.ldc = Hd;
-  gemm(g);
-  col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
-
   fill_zero(ctx_, dc1, (size_t)B * Hd * sizeof(float));
   fill_zero(ctx_, dc2, (size_t)B * Hd * sizeof(float));
   for (int t = T - 1; t >= 0; t--) {
@@ -186,6 +178,33 @@ void Engine::decoder_backward() {
     g.C = dX1 + h1off; g.ldc = K1;
     gemm(g);
   }
+  // the carries the encoder backward starts from are now in place: d c1(0) in dc1, d h1(0) in dX1[:, h1off:]
+}
+
+// decoder backward through time (model.lua:643-661) with every parameter gradient time-batched afterwards
+void Engine::decoder_backward() {
+  const int B = b_, S = S_, T = T_;
+  const int in1 = E + (cfg.input_feed ? Hd : 0);
+  const int64_t R = (int64_t)T * B;
+  const float inv_bn = 1.0f / (float)(cfg.global_batch > 0 ? cfg.global_batch : B);
+  // generator + criterion for all steps at once (a_t are all known): model.lua:644-648
+  generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[0], dZ, rowloss, R, Hd, V, inv_bn);
+  reduce_sum_double(ctx_, rowloss, R, d_loss);
+  Gemm g;
+  g.M = (int)R; g.N = Hd; g.K = V;                       // dA_gen = dZ W_o
+  g.A = dZ; g.sam = V; g.sak = 1;
+  g.B = d_params + L.wo; g.sbk = Hd; g.sbn = 1;
+  g.C = dAgen; g.ldc = Hd;
+  gemm(g);
+  g = Gemm();
+  g.M = V; g.N = Hd; g.K = (int)R;                       // dW_o = dZ^T A
+  g.A = dZ; g.sam = 1; g.sak = V;
+  g.B = A_all; g.sbk = Hd; g.sbn = 1;
+  g.C = d_grads + L.wo; g.ldc = Hd;
+  gemm(g);
+  col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
+
+  if (cfg.gemm_mode != 2) decoder_backward_steps_tc(); else decoder_backward_steps_simt();
   // ---- time-batched parameter gradients (weights are tied across t: clone_many_times, model_utils.lua:3-50)
   auto wgrad = [&](const float* dY, int M, const float* X, int64_t ldx, int N, float* dW, int64_t ldw) {
     Gemm w;

@@ -1,0 +1,177 @@
+// engine_dec_tc.cu — the decoder schedule on tensor cores (gemm_mode 0/1).  Per timestep: four tcgen05 GEMMs
+// (layer-1 gates, layer-2 gates, attention query, output projection), each followed by ONE memory-bound
+// kernel that sums the GEMM's split-K partials, applies the cell / attention / tanh math and writes the next
+// GEMM's operand as bf16 planes.  Weights are concatenated along K ([W_i | W_h]) so a cell needs one GEMM,
+// and the batch rides the UMMA N dimension (swap-AB) so the 128-row M tile is filled by weight rows.
+// Reference schedule: src/model/model.lua:553-568 (forward), :643-661 (backward).
+#include "engine.h"
+
+namespace aocr {
+
+namespace {
+Pack sub_rows(const Pack& p, int64_t row0, int64_t rows) {
+  Pack s;
+  s.hi = p.hi + row0 * p.kp; s.lo = p.lo + row0 * p.kp; s.rows = rows; s.kp = p.kp;
+  return s;
+}
+Pack sub_cols(const Pack& p, int64_t col0) {   // same pitch, shifted origin (for split_to_pack with kwrite)
+  Pack s = p;
+  s.hi = p.hi + col0; s.lo = p.lo + col0;
+  return s;
+}
+PackOut pack_out(const Pack& p, int64_t row0, int64_t col0) {
+  PackOut o;
+  o.hi = p.hi + row0 * p.kp + col0; o.lo = p.lo + row0 * p.kp + col0; o.ld = p.kp;
+  return o;
+}
+PartIn part_in(const TcOut& o, int64_t ld, int64_t col0 = 0) {
+  PartIn a;
+  a.p = o.base + col0; a.nz = o.nz; a.stride = o.stride; a.ld = ld;
+  return a;
+}
+}  // namespace
+
+// (re)build the decoder weight packs after a parameter change
+void Engine::build_decoder_packs() {
+  if (dec_packs_version_ == weights_version_) return;
+  const int in1 = E + (cfg.input_feed ? Hd : 0);
+  const float* P = d_params;
+  // forward packs: rows = output units (the UMMA M side), K = concatenated inputs
+  if (cfg.input_feed) split_to_pack(ctx_, P + L.l1_wi + E, 4 * Hd, Hd, in1, 1, sub_cols(Wcat1p, 0), Hd);
+  split_to_pack(ctx_, P + L.l1_wh, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat1p, h1off), Hd);
+  split_to_pack(ctx_, P + L.l2_wi, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat2p, 0), Hd);
+  split_to_pack(ctx_, P + L.l2_wh, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat2p, Hd), Hd);
+  split_to_pack(ctx_, P + L.wa, Hd, Hd, Hd, 1, Wap);
+  split_to_pack(ctx_, P + L.wc, Hd, 2 * Hd, 2 * Hd, 1, Wcp);
+  // backward packs: rows = input units, K = output units (transposes)
+  if (cfg.input_feed) split_to_pack(ctx_, P + L.l1_wi + E, Hd, 4 * Hd, 1, in1, sub_rows(Wcat1Tp, 0, Hd));
+  split_to_pack(ctx_, P + L.l1_wh, Hd, 4 * Hd, 1, Hd, sub_rows(Wcat1Tp, h1off, Hd));
+  split_to_pack(ctx_, P + L.l2_wi, Hd, 4 * Hd, 1, Hd, sub_rows(Wcat2Tp, 0, Hd));
+  split_to_pack(ctx_, P + L.l2_wh, Hd, 4 * Hd, 1, Hd, sub_rows(Wcat2Tp, Hd, Hd));
+  split_to_pack(ctx_, P + L.wa, Hd, Hd, 1, Hd, WaTp);
+  split_to_pack(ctx_, P + L.wc, 2 * Hd, Hd, 1, 2 * Hd, WcTp);
+  dec_packs_version_ = weights_version_;
+}
+
+// One decoder step.  Saved fp32 state (for backward) has the layout of the SIMT path:
+//   X1[t] = [a_{t-1} | h1_{t-1}]   X2[t] = [h1_t | h2_{t-1}]   CAT[t] = [cv_t | h2_t]   A_all[t] = a_t
+// and X1p / X2p / CATp mirror them as bf16 planes (written by the producing kernels, never by a conversion pass).
+void Engine::decoder_step_tc(int t, const int32_t* tokens) {
+  const int B = b_, S = S_;
+  const int nsteps = dec_steps_;
+  const bool has_next = (t + 1 < nsteps);
+  const int terms = cfg.gemm_mode == 1 ? 1 : 3;
+  float* x1 = X1 + (int64_t)t * B * K1;
+  float* x2 = X2 + (int64_t)t * B * 2 * Hd;
+  float* cat = CAT + (int64_t)t * B * 2 * Hd;
+  const int64_t r0 = (int64_t)t * B, r1 = (int64_t)(t + 1) * B;
+  auto run = [&](const Pack& W, int M, const Pack& X, int K, int slot) {
+    TcGemm g;
+    g.A = W; g.B = X; g.M = M; g.N = B; g.K = K; g.ldc = M; g.transpose_out = true;   // C[b][m]
+    g.terms = terms; g.defer_reduce = true; g.ws = dec_ws[slot]; g.ws_floats = dec_ws_floats;
+    prof_begin(0);
+    TcOut o = gemm_tc(ctx_, g);
+    prof_end(0, 2.0 * M * (double)B * K);
+    return o;
+  };
+  // ---- layer 1
+  TcOut g1 = run(Wcat1p, 4 * Hd, sub_rows(X1p, r0, B), K1, 0);
+  CellFwdTc c1;
+  c1.G = part_in(g1, 4 * Hd); c1.addrows = Ptab; c1.rowsel = tokens; c1.addld = 4 * Hd;
+  c1.c_prev = C1 + (int64_t)t * B * Hd; c1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
+  c1.acts = ACT1 + (int64_t)t * B * 4 * Hd;
+  c1.h_out0 = x2; c1.ld0 = 2 * Hd;
+  c1.h_out1 = has_next ? x1 + (int64_t)B * K1 + h1off : nullptr; c1.ld1 = K1;
+  c1.pk0 = pack_out(X2p, r0, 0);
+  c1.pk1 = has_next ? pack_out(X1p, r1, h1off) : PackOut();
+  c1.B = B; c1.H = Hd;
+  cell_fwd_tc(ctx_, c1);
+  // ---- layer 2
+  TcOut g2 = run(Wcat2p, 4 * Hd, sub_rows(X2p, r0, B), 2 * Hd, 1);
+  CellFwdTc c2;
+  c2.G = part_in(g2, 4 * Hd); c2.addrows = bsum2; c2.rowsel = nullptr; c2.addld = 0;
+  c2.c_prev = C2 + (int64_t)t * B * Hd; c2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
+  c2.acts = ACT2 + (int64_t)t * B * 4 * Hd;
+  c2.h_out0 = cat + Hd; c2.ld0 = 2 * Hd;
+  c2.h_out1 = has_next ? x2 + (int64_t)B * 2 * Hd + Hd : nullptr; c2.ld1 = 2 * Hd;
+  c2.pk0 = pack_out(CATp, r0, Hd);
+  c2.pk1 = has_next ? pack_out(X2p, r1, Hd) : PackOut();
+  c2.B = B; c2.H = Hd;
+  cell_fwd_tc(ctx_, c2);
+  // ---- attention: q = W_a h2 (operand = second half of CATp[t]), fused score/softmax/context kernel
+  Pack h2p = sub_rows(CATp, r0, B);
+  h2p.hi += Hd; h2p.lo += Hd;
+  TcOut qo = run(Wap, Hd, h2p, Hd, 2);
+  prof_begin(1);
+  attn_fwd_tc(ctx_, ctx, part_in(qo, Hd), ALPHA + (int64_t)t * B * S, cat, 2 * Hd, pack_out(CATp, r0, 0), B, S, Hd);
+  prof_end(1, (double)B * S * Hd * 4 + (double)B * (2.0 * Hd + S) * 4);
+  // q itself is needed by the backward (D_ctx product): materialise it once per step
+  part_to_dense(ctx_, part_in(qo, Hd), Q + (int64_t)t * B * Hd, Hd, B, Hd);
+  // ---- a_t = tanh(W_c [cv ; h2])
+  TcOut uo = run(Wcp, Hd, sub_rows(CATp, r0, B), 2 * Hd, 3);
+  DecOutTc d;
+  d.U = part_in(uo, Hd); d.a_out = A_all + (int64_t)t * B * Hd;
+  d.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; d.ld_next = K1;
+  d.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();
+  d.B = B; d.H = Hd;
+  dec_out_tc(ctx_, d);
+}
+
+// per-timestep part of the decoder backward (model.lua:643-661) on tensor cores
+void Engine::decoder_backward_steps_tc() {
+  const int B = b_, S = S_, T = T_;
+  const int terms = cfg.gemm_mode == 1 ? 1 : 3;
+  fill_zero(ctx_, dc1, (size_t)B * Hd * sizeof(float));
+  fill_zero(ctx_, dc2, (size_t)B * Hd * sizeof(float));
+  auto run = [&](const Pack& WT, int M, const Pack& X, int K, int slot) {
+    TcGemm g;
+    g.A = WT; g.B = X; g.M = M; g.N = B; g.K = K; g.ldc = M; g.transpose_out = true;
+    g.terms = terms; g.defer_reduce = true; g.ws = dec_ws[slot]; g.ws_floats = dec_ws_floats;
+    prof_begin(0);
+    TcOut o = gemm_tc(ctx_, g);
+    prof_end(0, 2.0 * M * (double)B * K);
+    return o;
+  };
+  TcOut dx1, dx2;   // carries of the previous (t+1) iteration; valid when !last
+  for (int t = T - 1; t >= 0; t--) {
+    const bool last = (t == T - 1);
+    // du = (da_prev + W_o^T dz) * (1 - a^2)
+    DuTc du;
+    du.da_carry = (!last && cfg.input_feed) ? part_in(dx1, K1, 0) : PartIn();
+    du.da_gen = dAgen + (int64_t)t * B * Hd; du.a = A_all + (int64_t)t * B * Hd;
+    du.du = dU + (int64_t)t * B * Hd; du.pk = pack_out(dUp, 0, 0); du.B = B; du.H = Hd;
+    du_tc(ctx_, du);
+    // d[cv ; h2] = du W_c
+    TcOut dcat = run(WcTp, 2 * Hd, dUp, Hd, 0);
+    prof_begin(1);
+    attn_bwd_tc(ctx_, ctx, ALPHA + (int64_t)t * B * S, part_in(dcat, 2 * Hd, 0), dCAT + (int64_t)t * B * 2 * Hd, 2 * Hd,
+                DE + (int64_t)t * B * S, dQ + (int64_t)t * B * Hd, pack_out(dQp, 0, 0), B, S, Hd);
+    prof_end(1, 2.0 * B * S * Hd * 4);
+    // dh2 += dq W_a
+    TcOut dh2q = run(WaTp, Hd, dQp, Hd, 1);
+    CellBwdTc b2;
+    b2.dh_a = part_in(dcat, 2 * Hd, Hd);
+    b2.dh_b = part_in(dh2q, Hd, 0);
+    b2.dh_c = last ? PartIn() : part_in(dx2, 2 * Hd, Hd);
+    b2.dc = dc2; b2.c_prev = C2 + (int64_t)t * B * Hd; b2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
+    b2.acts = ACT2 + (int64_t)t * B * 4 * Hd; b2.dG = dG2 + (int64_t)t * B * 4 * Hd; b2.pk = pack_out(dG2p, 0, 0);
+    b2.B = B; b2.H = Hd;
+    cell_bwd_tc(ctx_, b2);
+    // [dh1 | dh2_prev] = dg2 [W_i2 | W_h2]      (slot 2 must outlive this iteration: read again at t-1)
+    dx2 = run(Wcat2Tp, 2 * Hd, dG2p, 4 * Hd, 2);
+    CellBwdTc b1;
+    b1.dh_a = part_in(dx2, 2 * Hd, 0);
+    b1.dh_b = last ? PartIn() : part_in(dx1, K1, h1off);
+    b1.dh_c = PartIn();
+    b1.dc = dc1; b1.c_prev = C1 + (int64_t)t * B * Hd; b1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
+    b1.acts = ACT1 + (int64_t)t * B * 4 * Hd; b1.dG = dG1 + (int64_t)t * B * 4 * Hd; b1.pk = pack_out(dG1p, 0, 0);
+    b1.B = B; b1.H = Hd;
+    cell_bwd_tc(ctx_, b1);
+    // [da_prev | dh1_prev] = dg1 [W_i1[:,E:] | W_h1]
+    dx1 = run(Wcat1Tp, K1, dG1p, 4 * Hd, 3);
+  }
+  // hand d h1(0) to the encoder backward through the dense dX1 buffer (model.lua:666-667,680-681; quirk Q14)
+  part_to_dense(ctx_, part_in(dx1, K1, 0), dX1, K1, B, K1);
+}
+
+}  // namespace aocr

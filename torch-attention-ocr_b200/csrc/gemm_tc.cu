@@ -310,9 +310,10 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& h, __nv_bfloat16&
 }
 // k contiguous in the source (sks == 1): one thread per 4 consecutive k
 __global__ void __launch_bounds__(256) split_kfast_kernel(const float* __restrict__ src, int64_t rows, int64_t K,
-                                                          int64_t srs, int64_t kp, __nv_bfloat16* __restrict__ hi,
+                                                          int64_t srs, int64_t kp, int64_t kw,
+                                                          __nv_bfloat16* __restrict__ hi,
                                                           __nv_bfloat16* __restrict__ lo) {
-  const int64_t kq = kp / 4;
+  const int64_t kq = kw / 4;   // kw = columns written (zero padded past K), kp = row pitch of the planes
   const int64_t total = rows * kq;
   const bool vec = ((srs & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(256) split_kfast_kernel(const float* __restric
 }
 // general strides (typically srs == 1: the transposing case): 32x32 tile through shared memory
 __global__ void __launch_bounds__(256) split_tile_kernel(const float* __restrict__ src, int64_t rows, int64_t K,
-                                                         int64_t srs, int64_t sks, int64_t kp,
+                                                         int64_t srs, int64_t sks, int64_t kp, int64_t kw,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(256) split_tile_kernel(const float* __restrict
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     int64_t r = r0 + i, k = k0 + tx;
-    if (r < rows && k < kp) {
+    if (r < rows && k < kw) {
       __nv_bfloat16 h, l;
       split2(tile[i][tx], h, l);
       hi[r * kp + k] = h;
@@ -454,22 +455,28 @@ bool gemm_tc_available() {
   return g_encode != nullptr;
 }
 
-void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst) {
-  AOCR_CHECK(dst.kp == pad64(K) && dst.rows >= rows, "split_to_pack: destination pack too small");
+void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst,
+                   int64_t kwrite) {
+  int64_t kw = kwrite;
+  if (kw < 0) {
+    AOCR_CHECK(dst.kp == pad64(K), "split_to_pack: destination pitch must be K rounded up to 64");
+    kw = dst.kp;
+  }
+  AOCR_CHECK(dst.rows >= rows && kw >= K && kw % 4 == 0 && kw <= dst.kp, "split_to_pack: bad destination extent");
   if (sks == 1) {
-    int64_t total = rows * (dst.kp / 4);
+    int64_t total = rows * (kw / 4);
     int64_t g = (total + 255) / 256;
     int64_t cap = (int64_t)ctx.num_sms * 8;
-    split_kfast_kernel<<<(unsigned)(g < cap ? (g > 0 ? g : 1) : cap), 256, 0, ctx.st>>>(src, rows, K, srs, dst.kp, dst.hi,
-                                                                                    dst.lo);
+    split_kfast_kernel<<<(unsigned)(g < cap ? (g > 0 ? g : 1) : cap), 256, 0, ctx.st>>>(src, rows, K, srs, dst.kp, kw,
+                                                                                    dst.hi, dst.lo);
   } else {
-    dim3 grid((unsigned)((dst.kp + 31) / 32), (unsigned)((rows + 31) / 32));
-    split_tile_kernel<<<grid, 256, 0, ctx.st>>>(src, rows, K, srs, sks, dst.kp, dst.hi, dst.lo);
+    dim3 grid((unsigned)((kw + 31) / 32), (unsigned)((rows + 31) / 32));
+    split_tile_kernel<<<grid, 256, 0, ctx.st>>>(src, rows, K, srs, sks, dst.kp, kw, dst.hi, dst.lo);
   }
   AOCR_LAUNCH_CHECK(ctx);
 }
 
-void gemm_tc(Ctx& ctx, const TcGemm& g) {
+TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   resolve_encode();
   if (!g_encode) throw CudaError("cuTensorMapEncodeTiled entry point not found (driver too old?)");
   AOCR_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "gemm_tc: empty problem");
@@ -499,7 +506,7 @@ void gemm_tc(Ctx& ctx, const TcGemm& g) {
     ah = &map_4d(g.A.hi, c.N, c.H, c.W, c.C, bw, bh, bn);
     al = &map_4d(g.A.lo, c.N, c.H, c.W, c.C, bw, bh, bn);
   } else {
-    AOCR_CHECK(g.A.kp == g.B.kp && g.A.kp >= g.K, "gemm_tc: operand packs disagree on padded K");
+    AOCR_CHECK(g.A.kp >= pad64(g.K) && g.B.kp >= pad64(g.K), "gemm_tc: operand pack narrower than K");
     p.num_kb = (int)(pad64(g.K) / BK);
     grid.y = (g.M + BM - 1) / BM;
     ah = &map_2d(g.A.hi, g.A.rows, g.A.kp, BM);
@@ -518,11 +525,18 @@ void gemm_tc(Ctx& ctx, const TcGemm& g) {
     if (splits > 16) splits = 16;
   }
   if (g.force_splits > 0 && ctx.tc_ws) splits = g.force_splits < p.num_kb ? g.force_splits : p.num_kb;
-  while (splits > 1 && (long long)splits * part_stride > ctx.tc_ws_floats) splits--;
+  float* wsbase = g.ws ? g.ws : ctx.tc_ws;
+  const long long wscap = g.ws ? g.ws_floats : ctx.tc_ws_floats;
+  while (splits > 1 && (long long)splits * part_stride > wscap) splits--;
   if (splits < 1) splits = 1;
   p.kb_per = (p.num_kb + splits - 1) / splits;
   p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;
-  p.ws = ctx.tc_ws; p.part_stride = part_stride;
+  p.ws = wsbase; p.part_stride = part_stride;
+  if (g.defer_reduce) {   // raw sums only: the consumer kernel adds the partials (and any bias / activation)
+    AOCR_CHECK(!g.bias_m && !g.bias_n && g.act == ACT_NONE && !g.accumulate && g.ws, "deferred GEMM takes no epilogue");
+    AOCR_CHECK(part_stride <= wscap, "deferred GEMM workspace too small");
+    p.C = wsbase;        // splits == 1 writes the single partial straight into the workspace
+  }
   grid.z = p.splits;
   switch (BN) {
     case 128: launch<128>(ctx, *ah, *al, bh_, bl_, p, grid); break;
@@ -530,16 +544,20 @@ void gemm_tc(Ctx& ctx, const TcGemm& g) {
     case 32: launch<32>(ctx, *ah, *al, bh_, bl_, p, grid); break;
     default: launch<16>(ctx, *ah, *al, bh_, bl_, p, grid); break;
   }
-  if (p.splits > 1) {
+  TcOut out;
+  out.base = (p.splits > 1 || g.defer_reduce) ? wsbase : g.C;
+  out.nz = p.splits; out.stride = part_stride;
+  if (p.splits > 1 && !g.defer_reduce) {
     const float* bias_r = g.transpose_out ? g.bias_n : g.bias_m;
     const float* bias_c = g.transpose_out ? g.bias_m : g.bias_n;
     const long long total = crows * ccols;
     long long nb = (total + 255) / 256;
     if (nb > (long long)ctx.num_sms * 8) nb = (long long)ctx.num_sms * 8;
-    splitk_reduce_kernel<<<(unsigned)nb, 256, 0, ctx.st>>>(ctx.tc_ws, p.splits, part_stride, g.C, crows, ccols, g.ldc,
+    splitk_reduce_kernel<<<(unsigned)nb, 256, 0, ctx.st>>>(wsbase, p.splits, part_stride, g.C, crows, ccols, g.ldc,
                                                            bias_r, bias_c, g.act, g.accumulate);
     AOCR_LAUNCH_CHECK(ctx);
   }
+  return out;
 }
 
 }  // namespace aocr

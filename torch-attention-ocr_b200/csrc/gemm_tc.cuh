@@ -15,7 +15,10 @@ inline int64_t pad64(int64_t k) { return (k + 63) & ~(int64_t)63; }
 
 // fp32 (rows x K, element (r,k) at src[r*srs + k*sks]) -> Pack.  Handles either stride being 1 with
 // coalesced access (the transposing case goes through a shared-memory tile).
-void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst);
+// kwrite < 0: write the whole padded row (dst.kp == pad64(K)); otherwise write exactly `kwrite` (>= K, % 4 == 0)
+// columns of a wider pack (used to assemble concatenated weight packs).
+void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst,
+                   int64_t kwrite = -1);
 
 // NHWC view of a Pack for the implicit-GEMM convolution: rows = n*H*W pixels, kp = C channels.
 struct ConvView {
@@ -37,8 +40,14 @@ struct TcGemm {
   int accumulate = 0;
   int terms = 3;                       // 3: hi*hi + hi*lo + lo*hi (fp32-grade) ; 1: hi*hi (plain bf16)
   int force_splits = 0;                // test hook: force a split-K factor
+  // deferred reduction: leave the split-K partial sums in `ws` (ws_floats capacity) for the consumer kernel
+  bool defer_reduce = false;
+  float* ws = nullptr;
+  int64_t ws_floats = 0;
 };
-void gemm_tc(Ctx& ctx, const TcGemm& g);
+// where the result lives: value(i) = sum_{z < nz} base[z*stride + i], i indexed like C (ldc / transpose_out)
+struct TcOut { const float* base = nullptr; int nz = 1; int64_t stride = 0; };
+TcOut gemm_tc(Ctx& ctx, const TcGemm& g);
 bool gemm_tc_available();   // driver entry point for cuTensorMapEncodeTiled resolved
 
 }  // namespace aocr

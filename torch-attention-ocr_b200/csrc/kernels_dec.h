@@ -1,0 +1,48 @@
+// kernels_dec.h — kernels of the tensor-core decoder path (definitions in kernels_dec.cu).
+#pragma once
+#include "common.cuh"
+
+namespace aocr {
+
+// value(b, j) = sum_{z < nz} p[z*stride + b*ld + j] : a GEMM result still split along K (gemm_tc TcOut)
+struct PartIn { const float* p = nullptr; int nz = 1; int64_t stride = 0; int64_t ld = 0; };
+// destination of a bf16 (hi, lo) operand plane pair; element (b, j) at [b*ld + j]; hi == nullptr: skip
+struct PackOut { __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr; int64_t ld = 0; };
+
+struct CellFwdTc {
+  PartIn G;                                   // gate pre-activations (B, 4H), without bias
+  const float* addrows; const int32_t* rowsel; int64_t addld;   // + addrows[(rowsel[b]-1)*addld] (embedding table / bias)
+  const float* c_prev; float* c_new; float* acts;
+  float* h_out0; int64_t ld0; float* h_out1; int64_t ld1;       // fp32 sinks (h_out1 may be null)
+  PackOut pk0, pk1;                                             // bf16 sinks = operands of the next GEMMs
+  int B, H;
+};
+void cell_fwd_tc(Ctx&, const CellFwdTc&);
+
+struct DecOutTc {
+  PartIn U; float* a_out; float* x_next; int64_t ld_next; PackOut pk_next; int B, H;
+};
+void dec_out_tc(Ctx&, const DecOutTc&);
+
+struct DuTc {
+  PartIn da_carry; const float* da_gen; const float* a; float* du; PackOut pk; int B, H;
+};
+void du_tc(Ctx&, const DuTc&);
+
+struct CellBwdTc {
+  PartIn dh_a, dh_b, dh_c;                    // summed; p == nullptr: absent
+  float* dc; const float* c_prev; const float* c_new; const float* acts;
+  float* dG; PackOut pk;                      // (B, 4H)
+  int B, H;
+};
+void cell_bwd_tc(Ctx&, const CellBwdTc&);
+
+// dst[b*ld + j] = value(b, j): materialise a split result (used once per step for the encoder seeds)
+void part_to_dense(Ctx&, const PartIn& in, float* dst, int64_t ld, int B, int cols);
+
+void attn_fwd_tc(Ctx&, const float* ctx, const PartIn& q, float* alpha, float* cv, int64_t ldcv, const PackOut& cvp,
+                 int B, int S, int H);
+void attn_bwd_tc(Ctx&, const float* ctx, const float* alpha, const PartIn& dcv, float* dcv_out, int64_t ld_dcv_out,
+                 float* de, float* dq, const PackOut& dqp, int B, int S, int H);
+
+}  // namespace aocr
