@@ -12,8 +12,9 @@ from parity_util import train_parity, decode_parity  # noqa: E402
 
 mode = int(os.environ.get("AOCR_GEMM_MODE", "2"))
 B = int(os.environ.get("DIAG_B", "4"))
-cfg = Config(batch_size=B, max_encoder_l=30, max_decoder_l=12)
-batch = make_batch(B, 100, 7, seed=3)
+W = int(os.environ.get("DIAG_W", "100"))
+cfg = Config(batch_size=B, max_encoder_l=40, max_decoder_l=12, input_feed=not os.environ.get("DIAG_NOFEED"))
+batch = make_batch(B, W, 7, seed=int(os.environ.get("DIAG_SEED", "3")))
 t = time.time()
 out, (lg, lo) = train_parity(cfg, batch, gemm_mode=mode, verbose=True)
 print("train loss gpu/oracle", lg, lo, "time", time.time() - t)
