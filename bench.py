@@ -159,18 +159,13 @@ def main():
     batch = make_inputs(rank)
     lr = 0.1
     stream = torch.cuda.ExternalStream(h.stream(), device=local)
-    gptr, gn = h.grad_buffer()
-    gflat = cuda_tensor_from_ptr(gptr, gn, torch) if world > 1 else None
+    if world > 1:
+        from aocr import dist as aocr_dist
+        aocr_dist.attach(h, local)      # NCCL exchange hook: SyncBN statistics + 3 overlapped gradient buckets
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     def step_resident():
-        if world > 1:
-            h.forward_backward_staged()
-            with torch.cuda.stream(stream):
-                dist.all_reduce(gflat)
-            h.sgd_update_async(lr)
-        else:
-            h.train_step_staged(lr, sync=False)
+        h.train_step_staged(lr, sync=False)     # dp: the engine calls the exchange hook at its bucket boundaries
 
     def barrier():
         if world > 1:
@@ -206,13 +201,6 @@ def main():
     hb = [pin["images"], pin["targets"], pin["targets_eval"], batch["num_nonzeros"], None]
 
     def step_e2e():
-        if world > 1:
-            h.stage_batch(hb[0], hb[1], hb[2])
-            h.forward_backward_staged()
-            with torch.cuda.stream(stream):
-                dist.all_reduce(gflat)
-            h.sgd_update_async(lr)
-            return h.read_loss()
         return model.step(hb, False)[0]
 
     for _ in range(warmup):

@@ -109,6 +109,15 @@ int aocr_forward_backward_staged(aocr_handle* h);          /* enqueue only (no s
 int aocr_sgd_update_async(aocr_handle* h, double lr, double clip);
 int aocr_read_loss(aocr_handle* h, double* loss_sum);      /* syncs */
 int aocr_stream(aocr_handle* h, void** cuda_stream);       /* cudaStream_t the engine enqueues on */
+/* Data-parallel exchange hook (dp_world > 1).  The engine calls fn at its exchange points with a device buffer
+ * that must be SUM-all-reduced over the ranks:
+ *   kind 0: batch-norm statistics (a few KB) - must be ordered on the engine stream (the next kernel reads it);
+ *   kind 1: a finished bucket of the flat gradient buffer - may run on another stream concurrently with the rest
+ *           of backward; the engine does not touch it again before the join;
+ *   kind 2: join - dev_ptr NULL; make the engine stream wait for every outstanding kind-1 reduction.
+ * The host runtime implements it with NCCL (aocr/dist.py: torch.distributed). */
+typedef void (*aocr_allreduce_fn)(void* user, void* dev_ptr, int64_t n_floats, int kind);
+int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user);
 int aocr_synchronize(aocr_handle* h);
 /* number of kernel launches the library has issued on this handle (bench `gpu_launches`) */
 int64_t aocr_launch_count(const aocr_handle* h);

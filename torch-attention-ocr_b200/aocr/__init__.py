@@ -11,3 +11,4 @@ from .capi import Lib, AocrError, AocrConfig, GROUPS, lib_path  # noqa: F401
 from .model import Model  # noqa: F401
 from .optim import sgd_list  # noqa: F401
 from .data import SyntheticDataGen, str2numlist, numlist2str  # noqa: F401
+from . import dist  # noqa: F401

@@ -60,6 +60,7 @@ _SYMBOLS = {
     "aocr_sgd_update_async": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "aocr_read_loss": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "aocr_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "aocr_set_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "aocr_synchronize": (C.c_int, [C.c_void_p]),
     "aocr_launch_count": (C.c_int64, [C.c_void_p]),
     "aocr_prof_enable": (C.c_int, [C.c_void_p, C.c_int]),
@@ -273,6 +274,10 @@ class Handle:
         p = C.c_void_p()
         self._ck(self.lib.dll.aocr_stream(self.h, C.byref(p)))
         return p.value or 0
+
+    def set_allreduce(self, cb):
+        self._ar_cb = cb     # keep the ctypes callback alive
+        self._ck(self.lib.dll.aocr_set_allreduce(self.h, C.cast(cb, C.c_void_p), None))
 
     def synchronize(self):
         self._ck(self.lib.dll.aocr_synchronize(self.h))

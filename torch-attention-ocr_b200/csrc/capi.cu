@@ -173,6 +173,11 @@ int aocr_read_loss(aocr_handle* h, double* loss_sum) {
   if (loss_sum) *loss_sum = l;
   AOCR_API_END(h)
 }
+int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user) {
+  AOCR_API_BEGIN(h)
+  h->eng->ar_fn = fn; h->eng->ar_user = user;
+  AOCR_API_END(h)
+}
 int aocr_stream(aocr_handle* h, void** cuda_stream) {
   AOCR_API_BEGIN(h)
   if (cuda_stream) *cuda_stream = (void*)h->eng->ctx_.st;

@@ -357,8 +357,9 @@ void Engine::cnn_forward(bool train) {
     if (c.bn >= 0) {
       const float *mean, *var;
       if (train) {
-        bn_stats(ctx_, zb[l + 1], rows, c.cout, bn_mean[c.bn], bn_var[c.bn], partial);
-        bn_update_running(ctx_, bn_mean[c.bn], bn_var[c.bn], bn_rmean[c.bn], bn_rvar[c.bn], c.cout, rows);
+        bn_stats(ctx_, zb[l + 1], rows, c.cout, bn_mean[c.bn], bn_var[c.bn], partial, stat_sync());
+        bn_update_running(ctx_, bn_mean[c.bn], bn_var[c.bn], bn_rmean[c.bn], bn_rvar[c.bn], c.cout,
+                          rows * (cfg.dp_world > 1 ? cfg.dp_world : 1));
         mean = bn_mean[c.bn]; var = bn_var[c.bn];
       } else {
         mean = bn_rmean[c.bn]; var = bn_rvar[c.bn];
@@ -389,7 +390,8 @@ void Engine::cnn_backward() {
       const float* mean = cnn_train_ ? bn_mean[c.bn] : bn_rmean[c.bn];
       const float* var = cnn_train_ ? bn_var[c.bn] : bn_rvar[c.bn];
       bn_relu_bwd(ctx_, dcur, act[l + 1], zb[l + 1], mean, var, d_params + L.bn_g[c.bn], dz, d_grads + L.bn_g[c.bn],
-                  d_grads + L.bn_b[c.bn], partial, rows, c.cout, last ? S_ : 0, last ? B : 0, cnn_train_ ? 1 : 0);
+                  d_grads + L.bn_b[c.bn], partial, rows, c.cout, last ? S_ : 0, last ? B : 0, cnn_train_ ? 1 : 0,
+                  cnn_train_ ? stat_sync() : StatSync());
     } else {
       relu_pool_bwd(ctx_, dcur, act[l + 1], pidx[l + 1], dz, B, Hout, Wout, c.cout, c.pool_kw);
     }

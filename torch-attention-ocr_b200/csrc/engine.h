@@ -58,6 +58,13 @@ class Engine {
   void get_logprobs(int which, float* out, int64_t n);
   void debug_read(const char* name, float* out, int64_t n);
   void sync() { AOCR_CUDA(cudaStreamSynchronize(ctx_.st)); }
+  // data-parallel hook (aocr_set_allreduce): kind 0 = small sum ordered on the engine stream (BN statistics),
+  // 1 = gradient bucket that may run concurrently with later kernels, 2 = join all outstanding buckets
+  aocr_allreduce_fn ar_fn = nullptr;
+  void* ar_user = nullptr;
+  StatSync stat_sync();
+  void grad_bucket(int first_group, int last_group);
+  void grad_join();
   void mark_weights_dirty() { weights_dirty_ = true; weights_version_++; }
 
   aocr_config cfg;

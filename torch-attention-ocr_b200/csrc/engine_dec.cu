@@ -254,6 +254,31 @@ void Engine::decoder_backward() {
   taps_["dctx"] = {Dctx, (int64_t)B * S * Hd};
 }
 
+// ---- data-parallel hooks (no reference counterpart) ------------------------------------------
+static void stat_sync_tramp(void* user, float* buf, int64_t n) {
+  Engine* e = static_cast<Engine*>(user);
+  e->ar_fn(e->ar_user, buf, n, 0);
+}
+StatSync Engine::stat_sync() {
+  StatSync s;
+  if (cfg.dp_world > 1) {
+    AOCR_CHECK(ar_fn != nullptr, "dp_world > 1 needs aocr_set_allreduce before a training step");
+    s.fn = stat_sync_tramp; s.user = this; s.world = cfg.dp_world;
+  }
+  return s;
+}
+// groups are laid out [proj | decoder | enc_fw | enc_bw | cnn] = the order in which backward completes them
+void Engine::grad_bucket(int first_group, int last_group) {
+  if (cfg.dp_world <= 1) return;
+  AOCR_CHECK(ar_fn != nullptr, "dp_world > 1 needs aocr_set_allreduce before a training step");
+  const int64_t off = L.goff[first_group];
+  const int64_t end = L.goff[last_group] + L.gphys[last_group];
+  ar_fn(ar_user, d_grads + off, end - off, 1);
+}
+void Engine::grad_join() {
+  if (cfg.dp_world > 1) ar_fn(ar_user, nullptr, 0, 2);
+}
+
 // feval, train branch (model.lua:284-316,537-569,634-695)
 void Engine::forward_backward_enqueue() {
   AOCR_CHECK(have_batch_, "no batch staged");
@@ -271,9 +296,13 @@ void Engine::forward_backward_enqueue() {
   taps_["a_all"] = {A_all, (int64_t)T * B * Hd};
   taps_["alpha"] = {ALPHA, (int64_t)T * B * S_};
   decoder_backward();
+  grad_bucket(G_PROJ, G_DEC);      // [proj | decoder] is complete: its all-reduce overlaps the encoder/CNN backward
   encoder_backward();
+  grad_bucket(G_ENC_FW, G_ENC_BW);
   taps_["dsrc"] = {dsrc, (int64_t)S_ * B * 512};
   cnn_backward();
+  grad_bucket(G_CNN, G_CNN);
+  grad_join();
   have_grads_ = true;
   last_logp_rows_[0] = T * B;
 }

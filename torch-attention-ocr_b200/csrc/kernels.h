@@ -21,7 +21,10 @@ void relu_pool_bwd(Ctx&, const float* da, const float* a, const uint8_t* idx, fl
 void im2col(Ctx&, const float* a, float* col, int B, int H, int Wi, int C, int k, int pad);
 // column statistics of z (R,C): sum and (two-pass) centred sum of squares; deterministic.
 void col_sum(Ctx&, const float* z, int64_t R, int C, float* out /*[C]*/, float* partial, int accumulate);
-void bn_stats(Ctx&, const float* z, int64_t R, int C, float* mean, float* var /*biased*/, float* partial);
+// cross-rank summation hook for batch-norm statistics (data parallelism); world == 1: unused
+struct StatSync { void (*fn)(void* user, float* buf, int64_t n) = nullptr; void* user = nullptr; int world = 1; };
+void bn_stats(Ctx&, const float* z, int64_t R, int C, float* mean, float* var /*biased*/, float* partial,
+              const StatSync& sync);
 // running stats update (momentum 0.1, unbiased var) [T7 nn.SpatialBatchNormalization]
 void bn_update_running(Ctx&, const float* mean, const float* var, float* rmean, float* rvar, int C, int64_t R);
 // y = relu(gamma*(z-mean)/sqrt(var+eps)+beta).  If tm_S>0 rows (n,s) are written time-major to row s*tm_B+n.
@@ -31,7 +34,7 @@ void bn_relu_fwd(Ctx&, const float* z, const float* mean, const float* var, cons
 // step 2: dz = gamma*inv*(dy - s1/R - xhat*s2/R) (train) or gamma*inv*dy (eval stats).  dgamma=s2, dbeta=s1.
 void bn_relu_bwd(Ctx&, const float* da, const float* a, const float* z, const float* mean, const float* var,
                  const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial, int64_t R, int C,
-                 int tm_S, int tm_B, int train);
+                 int tm_S, int tm_B, int train, const StatSync& sync);
 
 // ---------------- LSTM cells (reference: src/model/LSTM.lua:79-105) ---------------------------
 // One encoder step for both directions: g = xg[t] + h_prev W_h^T ; cell.  Layouts in DESIGN.md §4.

@@ -382,9 +382,22 @@ void col_sum(Ctx& ctx, const float* z, int64_t R, int C, float* out, float* part
   col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, 1.0f, accumulate, out, partial);
 }
 
-void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* var, float* partial) {
-  col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, 1.0f / (float)R, 0, mean, partial);
-  col_reduce(ctx, z, nullptr, mean, nullptr, R, C, 1, 1.0f / (float)R, 0, var, partial);
+// Batch statistics.  Under data parallelism (sync.world > 1) the local column sums are summed across ranks
+// through sync.fn (an all-reduce ordered on the engine stream) before they are normalised by the GLOBAL row
+// count, so every rank normalises with the statistics of the whole batch, as the single-device reference does.
+void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* var, float* partial, const StatSync& sync) {
+  const float invR = 1.0f / ((float)R * (float)sync.world);
+  if (sync.world <= 1) {
+    col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, invR, 0, mean, partial);
+    col_reduce(ctx, z, nullptr, mean, nullptr, R, C, 1, invR, 0, var, partial);
+    return;
+  }
+  col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, 1.0f, 0, mean, partial);
+  sync.fn(sync.user, mean, C);
+  scale_vec(ctx, mean, C, invR);
+  col_reduce(ctx, z, nullptr, mean, nullptr, R, C, 1, 1.0f, 0, var, partial);
+  sync.fn(sync.user, var, C);
+  scale_vec(ctx, var, C, invR);
 }
 
 void bn_update_running(Ctx& ctx, const float* mean, const float* var, float* rmean, float* rvar, int C, int64_t R) {
@@ -402,15 +415,23 @@ void bn_relu_fwd(Ctx& ctx, const float* z, const float* mean, const float* var, 
 
 void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, const float* mean, const float* var,
                  const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial, int64_t R, int C, int tm_S,
-                 int tm_B, int train) {
+                 int tm_B, int train, const StatSync& sync) {
   relu_mask_kernel<<<grid_for(R * (C / 4), 256, ctx.num_sms), 256, 0, ctx.st>>>(da, a, dz, R, C, tm_S, tm_B);
   AOCR_LAUNCH_CHECK(ctx);
   // dbeta = s1 ; dgamma = s2 (each BN parameter receives gradient exactly once per step)
   col_reduce(ctx, dz, nullptr, nullptr, nullptr, R, C, 0, 1.0f, 0, dbeta, partial);
   col_reduce(ctx, dz, z, mean, var, R, C, 2, 1.0f, 0, dgamma, partial);
-  bn_bwd_apply_kernel<<<grid_for(R * C, 256, ctx.num_sms), 256, 0, ctx.st>>>(dz, z, mean, var, gamma, dbeta, dgamma, R,
-                                                                           C, train);
+  if (sync.world > 1) {   // global sums of dy and dy*xhat (dgamma, dbeta are adjacent: one all-reduce when contiguous)
+    if (dbeta == dgamma + C) sync.fn(sync.user, dgamma, 2 * (int64_t)C);
+    else { sync.fn(sync.user, dgamma, C); sync.fn(sync.user, dbeta, C); }
+  }
+  bn_bwd_apply_kernel<<<grid_for(R * C, 256, ctx.num_sms), 256, 0, ctx.st>>>(dz, z, mean, var, gamma, dbeta, dgamma,
+                                                                           R * sync.world, C, train);
   AOCR_LAUNCH_CHECK(ctx);
+  if (sync.world > 1) {   // the gradient all-reduce will sum these again over ranks: pre-divide
+    scale_vec(ctx, dgamma, C, 1.0f / (float)sync.world);
+    scale_vec(ctx, dbeta, C, 1.0f / (float)sync.world);
+  }
 }
 
 }  // namespace aocr
