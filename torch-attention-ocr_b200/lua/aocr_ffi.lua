@@ -1,0 +1,43 @@
+--[[ aocr_ffi.lua — LuaJIT FFI binding of include/aocr.h (libaocr.so).
+     This is the Lua twin of aocr/capi.py; keep the two mechanically identical.  It cannot be executed in the build
+     container (no LuaJIT/Torch7 there): every entry point is exercised through the Python twin instead. ]]
+local ffi = require 'ffi'
+
+ffi.cdef[[
+typedef struct aocr_handle aocr_handle;
+typedef struct aocr_config {
+  int32_t batch_size, max_encoder_l, max_decoder_l, encoder_num_hidden, encoder_num_layers, decoder_num_layers,
+          target_vocab_size, target_embedding_size, input_feed;
+  float dropout, learning_rate;
+  int32_t dp_rank, dp_world, global_batch, gemm_mode;
+} aocr_config;
+int aocr_create(const aocr_config* cfg, int device, aocr_handle** out);
+void aocr_destroy(aocr_handle* h);
+const char* aocr_last_error(const aocr_handle* h);
+int aocr_param_groups(const aocr_handle* h, int32_t* n_groups, int64_t sizes[5]);
+int aocr_set_params(aocr_handle* h, int group, const float* host, int64_t n);
+int aocr_get_params(aocr_handle* h, int group, float* host, int64_t n);
+int aocr_get_grads(aocr_handle* h, int group, float* host, int64_t n);
+int aocr_set_bn_stats(aocr_handle* h, int layer, const float* mean, const float* var, int64_t n);
+int aocr_get_bn_stats(aocr_handle* h, int layer, float* mean, float* var, int64_t n);
+int aocr_forward_backward(aocr_handle* h, const float* images, int b, int W, const int32_t* targets,
+                          const int32_t* targets_eval, int T, double* loss_sum);
+int aocr_group_norms(aocr_handle* h, double pnorm[5], double gnorm[5]);
+int aocr_sgd_update(aocr_handle* h, double lr, double clip);
+int aocr_grad_scale(aocr_handle* h, int group, double s);
+int aocr_param_axpy(aocr_handle* h, int group, double a);
+int aocr_train_step(aocr_handle* h, const float* images, int b, int W, const int32_t* targets,
+                    const int32_t* targets_eval, int T, double lr, double* loss_sum);
+int aocr_decode_greedy(aocr_handle* h, const float* images, int b, int W, const int32_t* targets,
+                       const int32_t* targets_eval, int T, int32_t* labels, double* pred_scores,
+                       double* gold_scores, double* loss_sum, int32_t* num_correct);
+int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n);
+]]
+
+local lib = ffi.load(os.getenv('AOCR_LIB') or 'torch-attention-ocr_b200/lib/libaocr.so')
+local M = { lib = lib, ffi = ffi }
+
+function M.check(h, rc)
+  if rc ~= 0 then error(ffi.string(lib.aocr_last_error(h)), 2) end   -- same texts as the reference's asserts
+end
+return M
