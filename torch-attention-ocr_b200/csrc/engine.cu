@@ -347,13 +347,19 @@ void Engine::cnn_forward(bool train) {
     conv_dims(l, Hin, Win, Hout, Wout);
     const int64_t rows = (int64_t)B * Hout * Wout;
     const int Kc = c.k * c.k * c.cin;
-    im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
-    Gemm g;
-    g.M = (int)rows; g.N = c.cout; g.K = Kc;
-    g.A = col; g.sam = Kc; g.sak = 1;
-    g.B = d_params + L.conv_w[l]; g.sbk = 1; g.sbn = Kc;
-    g.C = zb[l + 1]; g.ldc = c.cout; g.bias_n = d_params + L.conv_b[l];
-    gemm(g);
+    if (cfg.gemm_mode != 2) {
+      // implicit GEMM: the NHWC activation is the A operand (4-D tensor map, halo by TMA zero fill); no im2col
+      conv_tc(act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, d_params + L.conv_w[l], c.cout, zb[l + 1],
+              d_params + L.conv_b[l]);
+    } else {
+      im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
+      Gemm g;
+      g.M = (int)rows; g.N = c.cout; g.K = Kc;
+      g.A = col; g.sam = Kc; g.sak = 1;
+      g.B = d_params + L.conv_w[l]; g.sbk = 1; g.sbn = Kc;
+      g.C = zb[l + 1]; g.ldc = c.cout; g.bias_n = d_params + L.conv_b[l];
+      gemm(g);
+    }
     if (c.bn >= 0) {
       const float *mean, *var;
       if (train) {
@@ -407,15 +413,19 @@ void Engine::cnn_backward() {
     gemm(gw);
     // data grad: correlation of dz with flipped, in/out-swapped weights, padding k-1-pad
     const int padd = c.k - 1 - c.pad;
-    im2col(ctx_, dz, col, B, Hout, Wout, c.cout, c.k, padd);
-    const int Kd = c.k * c.k * c.cout;
-    const int64_t rows_in = (int64_t)B * Hin * Win;
-    Gemm gd;
-    gd.M = (int)rows_in; gd.N = c.cin; gd.K = Kd;
-    gd.A = col; gd.sam = Kd; gd.sak = 1;
-    gd.B = wt[l]; gd.sbk = 1; gd.sbn = Kd;
-    gd.C = gB; gd.ldc = c.cin;
-    gemm(gd);
+    if (cfg.gemm_mode != 2) {
+      conv_tc(dz, B, Hout, Wout, c.cout, c.k, padd, Hin, Win, wt[l], c.cin, gB, nullptr);
+    } else {
+      im2col(ctx_, dz, col, B, Hout, Wout, c.cout, c.k, padd);
+      const int Kd = c.k * c.k * c.cout;
+      const int64_t rows_in = (int64_t)B * Hin * Win;
+      Gemm gd;
+      gd.M = (int)rows_in; gd.N = c.cin; gd.K = Kd;
+      gd.A = col; gd.sam = Kd; gd.sak = 1;
+      gd.B = wt[l]; gd.sbk = 1; gd.sbn = Kd;
+      gd.C = gB; gd.ldc = c.cin;
+      gemm(gd);
+    }
     dcur = gB;
     // next iteration writes dz into gA again and reads dcur=gB: fine (distinct buffers)
   }

@@ -96,6 +96,8 @@ class Engine {
   void decoder_backward_steps_simt();
   void decoder_backward_steps_tc();
   void build_decoder_packs();
+  void conv_tc(const float* x, int N, int H, int W, int C, int k, int pad, int Ho, int Wo, const float* Wk, int Cout,
+               float* out, const float* bias);
   void conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const;
   Pack alloc_pack(int64_t rows, int64_t kp);
   bool is_param(const float* p) const;

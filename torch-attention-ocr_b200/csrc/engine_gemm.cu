@@ -65,6 +65,30 @@ void Engine::gemm(const Gemm& g, int cls) {
   prof_end(cls, 2.0 * g.M * g.N * (double)g.K * g.batch);
 }
 
+// Convolution as implicit GEMM on the tcgen05 core: out (N,Ho,Wo,Cout) = conv(x (N,H,W,C), Wk [Cout][k*k*C]) + bias.
+// Used for the forward convolutions (x = activation, Wk = parameters) and for the data gradient (x = dz,
+// Wk = flipped / in-out-swapped weights, pad = k-1-pad).  Only the small NHWC activation is converted to bf16 planes.
+void Engine::conv_tc(const float* x, int N, int H, int W, int C, int k, int pad, int Ho, int Wo, const float* Wk, int Cout,
+                     float* out, const float* bias) {
+  const int64_t rows_in = (int64_t)N * H * W;
+  const int Kc = k * k * C;
+  prof_begin(0);
+  Pack xp;
+  xp.rows = rows_in; xp.kp = C; xp.hi = scratch_[0].hi; xp.lo = scratch_[0].lo;
+  AOCR_CHECK(C % 64 == 0 && rows_in * C <= scratch_elems_, "conv_tc: channel count must be a multiple of 64");
+  split_to_pack(ctx_, x, rows_in, C, C, 1, xp);
+  Pack wp = operand_pack(Wk, Cout, Kc, Kc, 1, 1);
+  ConvView v;
+  v.N = N; v.H = H; v.W = W; v.C = C; v.k = k; v.pad = pad; v.Ho = Ho; v.Wo = Wo;
+  TcGemm t;
+  t.A = xp; t.B = wp; t.conv = &v;
+  t.M = N * Ho * Wo; t.N = Cout; t.K = Kc;
+  t.C = out; t.ldc = Cout; t.bias_n = bias;
+  t.terms = cfg.gemm_mode == 1 ? 1 : 3;
+  gemm_tc(ctx_, t);
+  prof_end(0, 2.0 * N * Ho * Wo * (double)Cout * Kc);
+}
+
 }  // namespace aocr
 
 // ---------------------------------------------------------------------------------------------
