@@ -404,13 +404,17 @@ void Engine::cnn_backward() {
     // bias grad
     col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);
     // weight grad: dW[co][tap,ci] = sum_rows dz[row][co] * col[row][tap,ci]
-    im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
-    Gemm gw;
-    gw.M = c.cout; gw.N = Kc; gw.K = (int)rows;
-    gw.A = dz; gw.sam = 1; gw.sak = c.cout;
-    gw.B = col; gw.sbk = Kc; gw.sbn = 1;
-    gw.C = d_grads + L.conv_w[l]; gw.ldc = Kc;
-    gemm(gw);
+    if (cfg.gemm_mode != 2) {
+      conv_wgrad_tc(dz, act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, c.cout, d_grads + L.conv_w[l]);
+    } else {
+      im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
+      Gemm gw;
+      gw.M = c.cout; gw.N = Kc; gw.K = (int)rows;
+      gw.A = dz; gw.sam = 1; gw.sak = c.cout;
+      gw.B = col; gw.sbk = Kc; gw.sbn = 1;
+      gw.C = d_grads + L.conv_w[l]; gw.ldc = Kc;
+      gemm(gw);
+    }
     // data grad: correlation of dz with flipped, in/out-swapped weights, padding k-1-pad
     const int padd = c.k - 1 - c.pad;
     if (cfg.gemm_mode != 2) {

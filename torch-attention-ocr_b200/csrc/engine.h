@@ -96,6 +96,8 @@ class Engine {
   void decoder_backward_steps_simt();
   void decoder_backward_steps_tc();
   void build_decoder_packs();
+  void conv_wgrad_tc(const float* dz, const float* x, int N, int H, int W, int Cin, int k, int pad, int Ho, int Wo,
+                     int Cout, float* dW);
   void conv_tc(const float* x, int N, int H, int W, int C, int k, int pad, int Ho, int Wo, const float* Wk, int Cout,
                float* out, const float* bias);
   void conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const;

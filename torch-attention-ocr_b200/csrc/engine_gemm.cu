@@ -46,6 +46,24 @@ void Engine::gemm(const Gemm& g, int cls) {
   const bool tc = cfg.gemm_mode != 2 && g.batch == 1 && g.K >= 64 && (g.M >= 64 || g.N >= 64);
   if (!tc) {
     gemm_simt(ctx_, g);
+  } else if (g.sam == 1 && g.sbn == 1 && g.sak >= g.M && g.sbk >= g.N) {
+    // dW = dY^T X with dY (K x M) and X (K x N) stored row-major: both operands are MN-major as they lie in
+    // memory - no transposing conversion, the contraction index K (time*batch) is the TMA row coordinate
+    TcGemm t;
+    Pack pa, pb;
+    pa.rows = g.K; pa.kp = pad64(g.M); pa.hi = scratch_[0].hi; pa.lo = scratch_[0].lo;
+    pb.rows = g.K; pb.kp = pad64(g.N); pb.hi = scratch_[1].hi; pb.lo = scratch_[1].lo;
+    AOCR_CHECK(pa.rows * pa.kp <= scratch_elems_ && pb.rows * pb.kp <= scratch_elems_, "wgrad operand exceeds scratch");
+    split_to_pack(ctx_, g.A, g.K, g.M, g.sak, 1, pa);
+    split_to_pack(ctx_, g.B, g.K, g.N, g.sbk, 1, pb);
+    t.mn = 1; t.K = g.K; t.C = g.C; t.ldc = g.ldc; t.act = g.act; t.accumulate = g.accumulate;
+    t.terms = cfg.gemm_mode == 1 ? 1 : 3;
+    if (g.M >= g.N) {
+      t.A = pa; t.B = pb; t.M = g.M; t.N = g.N; t.transpose_out = false; t.bias_m = g.bias_m; t.bias_n = g.bias_n;
+    } else {
+      t.A = pb; t.B = pa; t.M = g.N; t.N = g.M; t.transpose_out = true; t.bias_m = g.bias_n; t.bias_n = g.bias_m;
+    }
+    gemm_tc(ctx_, t);
   } else {
     TcGemm t;
     const bool swap = g.M < g.N;   // the larger side becomes the 128-row M side of the UMMA tile
@@ -87,6 +105,30 @@ void Engine::conv_tc(const float* x, int N, int H, int W, int C, int k, int pad,
   t.terms = cfg.gemm_mode == 1 ? 1 : 3;
   gemm_tc(ctx_, t);
   prof_end(0, 2.0 * N * Ho * Wo * (double)Cout * Kc);
+}
+
+// Convolution weight gradient as an implicit GEMM with MN-major operands: dW[co][tap*Cin+ci] =
+// sum over output pixels of dz[pix][co] * x[pix + tap][ci].  Both operands are the NHWC tensors as stored; the
+// filter tap is a shift of the TMA box origin of x (zero fill = padding).  No im2col, no transposes.
+void Engine::conv_wgrad_tc(const float* dz, const float* x, int N, int H, int W, int Cin, int k, int pad, int Ho, int Wo,
+                           int Cout, float* dW) {
+  const int64_t rows_out = (int64_t)N * Ho * Wo, rows_in = (int64_t)N * H * W;
+  prof_begin(0);
+  Pack zp, xp;
+  zp.rows = rows_out; zp.kp = Cout; zp.hi = scratch_[0].hi; zp.lo = scratch_[0].lo;
+  xp.rows = rows_in; xp.kp = Cin; xp.hi = scratch_[1].hi; xp.lo = scratch_[1].lo;
+  AOCR_CHECK(rows_out * Cout <= scratch_elems_ && rows_in * Cin <= scratch_elems_, "conv wgrad operand exceeds scratch");
+  split_to_pack(ctx_, dz, rows_out, Cout, Cout, 1, zp);
+  split_to_pack(ctx_, x, rows_in, Cin, Cin, 1, xp);
+  ConvView v;
+  v.N = N; v.H = H; v.W = W; v.C = Cin; v.k = k; v.pad = pad; v.Ho = Ho; v.Wo = Wo;
+  TcGemm t;
+  t.mn = 2; t.conv = &v; t.A = zp; t.B = xp;
+  t.M = Cout; t.N = k * k * Cin; t.K = (int)rows_out;
+  t.C = dW; t.ldc = k * k * Cin;
+  t.terms = cfg.gemm_mode == 1 ? 1 : 3;
+  gemm_tc(ctx_, t);
+  prof_end(0, 2.0 * rows_out * (double)Cout * k * k * Cin);
 }
 
 }  // namespace aocr
@@ -131,12 +173,26 @@ extern "C" int aocr_selftest_gemm(int M, int N, int K, int ta, int tb, int mode,
       Pack pa, pb;
       pa.hi = planes[0]; pa.lo = planes[1]; pa.rows = M; pa.kp = kp;
       pb.hi = planes[2]; pb.lo = planes[3]; pb.rows = N; pb.kp = kp;
-      split_to_pack(ctx, dA, M, K, sam, sak, pa);
-      split_to_pack(ctx, dB, N, K, sbn, sbk, pb);
       TcGemm t;
       t.K = K; t.C = dC; t.ldc = N; t.terms = mode == 1 ? 1 : 3; t.force_splits = splits;
-      if (!swap) { t.A = pa; t.B = pb; t.M = M; t.N = N; t.transpose_out = false; }
-      else { t.A = pb; t.B = pa; t.M = N; t.N = M; t.transpose_out = true; }
+      if (swap == 2) {
+        // MN-major test: operands as [K][M] and [K][N] planes (pitch padded to 64), no transposition
+        int64_t mp = pad64(M), np_ = pad64(N);
+        for (auto& q : planes) { cudaFree(q); q = nullptr; }
+        AOCR_CUDA(cudaMalloc(&planes[0], (size_t)K * mp * 2)); AOCR_CUDA(cudaMalloc(&planes[1], (size_t)K * mp * 2));
+        AOCR_CUDA(cudaMalloc(&planes[2], (size_t)K * np_ * 2)); AOCR_CUDA(cudaMalloc(&planes[3], (size_t)K * np_ * 2));
+        Pack ka, kb;
+        ka.hi = planes[0]; ka.lo = planes[1]; ka.rows = K; ka.kp = mp;
+        kb.hi = planes[2]; kb.lo = planes[3]; kb.rows = K; kb.kp = np_;
+        split_to_pack(ctx, dA, K, M, sak, sam, ka);     // rows = k, cols = m
+        split_to_pack(ctx, dB, K, N, sbk, sbn, kb);
+        t.A = ka; t.B = kb; t.M = M; t.N = N; t.mn = 1; t.transpose_out = false;
+      } else {
+        split_to_pack(ctx, dA, M, K, sam, sak, pa);
+        split_to_pack(ctx, dB, N, K, sbn, sbk, pb);
+        if (!swap) { t.A = pa; t.B = pb; t.M = M; t.N = N; t.transpose_out = false; }
+        else { t.A = pb; t.B = pa; t.M = N; t.N = M; t.transpose_out = true; }
+      }
       gemm_tc(ctx, t);
     }
     AOCR_CUDA(cudaStreamSynchronize(ctx.st));

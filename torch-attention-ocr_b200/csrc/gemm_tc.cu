@@ -41,6 +41,8 @@ struct TcParams {
   int terms;
   // conv mode
   int conv;
+  int mn;          // 0: both operands K-major; 1: both MN-major (K = rows), 2-D maps; 2: MN-major conv weight gradient (4-D maps)
+  int wg_cin;      // mn == 2: input channels (N index = tap*Cin + ci)
   int cin_blocks, ksz, pad;
   int bw, bh, bn, tiles_w, tiles_h;
   int Nimg, Ho, Wo;
@@ -124,9 +126,23 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor (InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major operand (the contraction index is the OUTER, row index of the stored matrix), 128-byte swizzle:
+// a tile is a stack of [64 k-rows x 64 elements (128 B)] TMA boxes (8 KB each).  Canonical layout
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units (cute make_umma_desc<Major::MN>): SBO = 1024 B between
+// groups of 8 k-rows, LBO = 8192 B between consecutive 64-element blocks along M/N.
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (InstrDescriptor): D=f32, A=B=bf16, N>>3 at bit 17, M>>4 at bit 24, bits 15/16 = A/B MN-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+         (mn ? ((1u << 15) | (1u << 16)) : 0u);
 }
 
 template <int BN>
@@ -191,6 +207,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const uint32_t sa = base + s * C_::kStageBytes;
         const uint32_t sb = sa + 2 * A_PLANE_BYTES;
         mbar_expect_tx(full_bar(s), tx);
+        if (p.mn) {
+          // MN-major: k-block kb = 64 contraction rows; each operand tile = BM/64 (BN/64) boxes of [64 rows][64 elems]
+          int kc1 = kb * BK, kc2 = 0, kc3 = 0;          // contraction coordinates (2-D: row ; 4-D: w, h, n)
+          int bs1 = 0, bs2 = 0, bco = n0;               // B shift (conv wgrad) and B inner coordinate
+          if (p.mn == 2) {
+            int id = kb;
+            const int wb = id % p.tiles_w; id /= p.tiles_w;
+            const int hb = id % p.tiles_h; id /= p.tiles_h;
+            kc1 = wb * p.bw; kc2 = hb * p.bh; kc3 = id * p.bn;
+            const int tap = n0 / p.wg_cin;
+            bco = n0 % p.wg_cin;
+            bs1 = tap % p.ksz - p.pad; bs2 = tap / p.ksz - p.pad;
+          }
+          for (int pl = 0; pl < (p.terms == 3 ? 2 : 1); pl++) {
+            const CUtensorMap* ta = pl ? &tmAl : &tmAh;
+            const CUtensorMap* tb = pl ? &tmBl : &tmBh;
+#pragma unroll
+            for (int j = 0; j < BM / 64; j++) {
+              const uint32_t dst = sa + pl * A_PLANE_BYTES + j * 8192;
+              if (p.mn == 2) tma_load_4d(dst, ta, full_bar(s), m0 + 64 * j, kc1, kc2, kc3);
+              else tma_load_2d(dst, ta, full_bar(s), m0 + 64 * j, kc1);
+            }
+#pragma unroll
+            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); j++) {
+              const uint32_t dst = sb + pl * C_::kBPlane + j * 8192;
+              if (p.mn == 2) tma_load_4d(dst, tb, full_bar(s), bco + 64 * j, kc1 + bs1, kc2 + bs2, kc3);
+              else tma_load_2d(dst, tb, full_bar(s), n0 + 64 * j, kc1);
+            }
+          }
+        } else {
         if (p.conv) {
           const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
           const int kh = tap / p.ksz, kw = tap % p.ksz;
@@ -203,11 +249,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
         tma_load_2d(sb, &tmBh, full_bar(s), kb * BK, n0);
         if (p.terms == 3) tma_load_2d(sb + C_::kBPlane, &tmBl, full_bar(s), kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
-    const uint32_t idesc = make_idesc(BN);
+    const uint32_t idesc = make_idesc(BN, p.mn);
     for (int i = 0; i < nkb; i++) {
       const int s = i % C_::kStages;
       const uint32_t ph = (uint32_t)(i / C_::kStages) & 1u;
@@ -216,11 +263,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       if (lane == 0) {
         const uint32_t sa = base + s * C_::kStageBytes;
         const uint32_t sb = sa + 2 * A_PLANE_BYTES;
-        const uint64_t dah = make_desc_kmajor_sw128(sa), dal = make_desc_kmajor_sw128(sa + A_PLANE_BYTES);
-        const uint64_t dbh = make_desc_kmajor_sw128(sb), dbl = make_desc_kmajor_sw128(sb + C_::kBPlane);
+        const uint64_t dah = p.mn ? make_desc_mnmajor_sw128(sa) : make_desc_kmajor_sw128(sa);
+        const uint64_t dal = p.mn ? make_desc_mnmajor_sw128(sa + A_PLANE_BYTES) : make_desc_kmajor_sw128(sa + A_PLANE_BYTES);
+        const uint64_t dbh = p.mn ? make_desc_mnmajor_sw128(sb) : make_desc_kmajor_sw128(sb);
+        const uint64_t dbl = p.mn ? make_desc_mnmajor_sw128(sb + C_::kBPlane) : make_desc_kmajor_sw128(sb + C_::kBPlane);
+        // per k-step (16 contraction elements): K-major +32 B inside the swizzle row; MN-major +16 rows = 2048 B
+        const uint64_t kstep = p.mn ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; k++) {
-          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 bytes per k-step inside the swizzle row
+          const uint64_t adv = kstep * k;
           tc_mma(tmem_base, dah + adv, dbh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
           if (p.terms == 3) {
             tc_mma(tmem_base, dah + adv, dbl + adv, idesc, 1u);
@@ -481,13 +532,43 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   if (!g_encode) throw CudaError("cuTensorMapEncodeTiled entry point not found (driver too old?)");
   AOCR_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "gemm_tc: empty problem");
   int BN = g.N > 64 ? 128 : (g.N > 32 ? 64 : (g.N > 16 ? 32 : 16));
+  if (g.mn && BN < 64) BN = 64;                     // MN-major boxes are 64 elements wide
+  if (g.mn == 2 && g.conv && g.conv->C < 128) BN = 64;   // an N tile must not straddle two filter taps
   TcParams p{};
-  p.M = g.M; p.N = g.N; p.K = g.K; p.terms = g.terms;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.terms = g.terms; p.mn = g.mn;
   p.C = g.C; p.ldc = g.ldc; p.transpose_out = g.transpose_out ? 1 : 0;
   p.bias_m = g.bias_m; p.bias_n = g.bias_n; p.act = g.act; p.accumulate = g.accumulate;
   dim3 grid;
   grid.x = (g.N + BN - 1) / BN;
-  const CUtensorMap *ah, *al;
+  const CUtensorMap *ah, *al, *bhp, *blp;
+  if (g.mn == 2) {
+    // convolution weight gradient, implicit: dW[co][tap*Cin+ci] = sum_pixels dz[pix][co] * x[pix+tap][ci]
+    const ConvView& c = *g.conv;
+    AOCR_CHECK(c.C % 64 == 0 && g.B.kp == c.C && g.A.kp >= g.M && g.M % 64 == 0, "conv wgrad: channels must be multiples of 64");
+    AOCR_CHECK(g.N == c.k * c.k * c.C && c.C % BN == 0, "conv wgrad: N must be k*k*Cin");
+    int bw = 8;
+    while (bw < c.Wo && bw < 64) bw *= 2;
+    int bh = 1;
+    while (bh * 2 * bw <= 64 && bh < c.Ho) bh *= 2;
+    const int bn = 64 / (bw * bh);
+    p.bw = bw; p.bh = bh; p.bn = bn; p.ksz = c.k; p.pad = c.pad; p.wg_cin = c.C;
+    p.tiles_w = (c.Wo + bw - 1) / bw; p.tiles_h = (c.Ho + bh - 1) / bh;
+    p.num_kb = p.tiles_w * p.tiles_h * ((c.N + bn - 1) / bn);
+    grid.y = (g.M + BM - 1) / BM;
+    ah = &map_4d(g.A.hi, c.N, c.Ho, c.Wo, (int)g.A.kp, bw, bh, bn);
+    al = &map_4d(g.A.lo, c.N, c.Ho, c.Wo, (int)g.A.kp, bw, bh, bn);
+    bhp = &map_4d(g.B.hi, c.N, c.H, c.W, c.C, bw, bh, bn);
+    blp = &map_4d(g.B.lo, c.N, c.H, c.W, c.C, bw, bh, bn);
+  } else if (g.mn == 1) {
+    // both operands stored [K rows][M or N columns]
+    AOCR_CHECK(g.A.rows >= g.K && g.B.rows >= g.K && g.A.kp >= g.M && g.B.kp >= g.N, "gemm_tc(mn): pack too small");
+    p.num_kb = (g.K + BK - 1) / BK;
+    grid.y = (g.M + BM - 1) / BM;
+    ah = &map_2d(g.A.hi, g.K, g.A.kp, 64);
+    al = &map_2d(g.A.lo, g.K, g.A.kp, 64);
+    bhp = &map_2d(g.B.hi, g.K, g.B.kp, 64);
+    blp = &map_2d(g.B.lo, g.K, g.B.kp, 64);
+  } else {
   if (g.conv) {
     const ConvView& c = *g.conv;
     AOCR_CHECK(c.C % BK == 0 && g.A.kp == c.C, "conv A pack must be NHWC with C a multiple of 64");
@@ -512,8 +593,11 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     ah = &map_2d(g.A.hi, g.A.rows, g.A.kp, BM);
     al = &map_2d(g.A.lo, g.A.rows, g.A.kp, BM);
   }
-  const CUtensorMap& bh_ = map_2d(g.B.hi, g.B.rows, g.B.kp, BN);
-  const CUtensorMap& bl_ = map_2d(g.B.lo, g.B.rows, g.B.kp, BN);
+  bhp = &map_2d(g.B.hi, g.B.rows, g.B.kp, BN);
+  blp = &map_2d(g.B.lo, g.B.rows, g.B.kp, BN);
+  }
+  const CUtensorMap& bh_ = *bhp;
+  const CUtensorMap& bl_ = *blp;
   // split-K when the output tiles alone cannot fill the machine (per-timestep decoder GEMMs, weight gradients)
   const long long tiles = (long long)grid.x * grid.y;
   const long long crows = g.transpose_out ? g.N : g.M, ccols = g.transpose_out ? g.M : g.N;

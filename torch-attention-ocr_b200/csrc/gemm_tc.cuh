@@ -32,6 +32,10 @@ struct TcGemm {
   Pack A, B;
   int M = 0, N = 0, K = 0;             // logical sizes (K <= A.kp == B.kp), or K = k*k*C in conv mode
   const ConvView* conv = nullptr;      // if set: A is an NHWC activation pack, M = N*Ho*Wo output pixels
+  // mn = 1: both operands are stored [K rows][M|N columns] ("MN-major": weight gradients dW = dY^T X need no
+  // transposes).  mn = 2: implicit convolution weight gradient: A = dz NHWC pack (N*Ho*Wo x Cout), B = x NHWC pack
+  // (N*H*W x Cin), conv = geometry of x; M = Cout, N = k*k*Cin, K = output pixels.
+  int mn = 0;
   float* C = nullptr; int64_t ldc = 0;
   bool transpose_out = false;          // false: C[m*ldc+n] ; true: C[n*ldc+m]
   const float* bias_m = nullptr;       // indexed by m
