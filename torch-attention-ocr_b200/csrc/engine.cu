@@ -161,6 +161,12 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     dUp = alloc_pack(B, Hd_); dQp = alloc_pack(B, Hd_); dG2p = alloc_pack(B, 4 * Hd_); dG1p = alloc_pack(B, 4 * Hd_);
     dec_ws_floats = (int64_t)16 * B * 4 * Hd_ + 1024;
     for (int i = 0; i < 4; i++) dec_ws[i] = alloc<float>(dec_ws_floats);
+    // tensor-core encoder recurrence (engine_enc_tc.cu)
+    const int64_t He_ = c.encoder_num_hidden;
+    for (int d = 0; d < 2; d++) {
+      Whp[d] = alloc_pack(4 * He_, He_); WhTp[d] = alloc_pack(He_, 4 * He_);
+      HencP[d] = alloc_pack((S + 1) * B, He_); dGeP[d] = alloc_pack(B, 4 * He_);
+    }
   }
   for (int l = 1; l < 7; l++) wt[l] = alloc<float>((int64_t)kConv[l].cout * kConv[l].cin * kConv[l].k * kConv[l].k);
 
@@ -455,15 +461,19 @@ void Engine::encoder_forward() {
   fill_zero(ctx_, Cenc, slot * sizeof(float));
   fill_zero(ctx_, Henc + ((int64_t)(S + 1) + S) * slot, slot * sizeof(float));   // bw slot S
   fill_zero(ctx_, Cenc + ((int64_t)(S + 1) + S) * slot, slot * sizeof(float));
-  EncStep p;
-  p.xg = xg; p.Wh[0] = d_params + L.enc_wh[0]; p.Wh[1] = d_params + L.enc_wh[1];
-  p.H = Henc; p.Cst = Cenc; p.acts = acts_enc; p.ctx = ctx; p.B = B; p.S = S; p.He = He;
-  prof_begin(2);
-  for (int i = 0; i < S; i++) {
-    p.step = i;
-    enc_step_fwd(ctx_, p);
+  if (cfg.gemm_mode != 2) {
+    encoder_forward_steps_tc();
+  } else {
+    EncStep p;
+    p.xg = xg; p.Wh[0] = d_params + L.enc_wh[0]; p.Wh[1] = d_params + L.enc_wh[1];
+    p.H = Henc; p.Cst = Cenc; p.acts = acts_enc; p.ctx = ctx; p.B = B; p.S = S; p.He = He;
+    prof_begin(2);
+    for (int i = 0; i < S; i++) {
+      p.step = i;
+      enc_step_fwd(ctx_, p);
+    }
+    prof_end(2, 2.0 * 2 * S * (double)B * He * 4 * He);
   }
-  prof_end(2, 2.0 * 2 * S * (double)B * He * 4 * He);
   taps_["context"] = {ctx, (int64_t)B * S * 2 * He};
 }
 
@@ -475,22 +485,26 @@ void Engine::encoder_backward() {
     copy_strided(ctx_, enc_dc + d * slot, He, dc1 + d * He, Hd, B, He);
     copy_strided(ctx_, enc_dh + d * slot, He, dX1 + h1off + d * He, K1, B, He);
   }
-  EncStepBwd p;
-  p.Wh[0] = d_params + L.enc_wh[0]; p.Wh[1] = d_params + L.enc_wh[1];
-  p.Cst = Cenc; p.acts = acts_enc; p.Dctx = Dctx; p.dh = enc_dh; p.dc = enc_dc; p.dG = dGe;
-  p.B = B; p.S = S; p.He = He;
-  for (int i = 0; i < S; i++) {
-    p.step = i;
-    enc_cell_bwd(ctx_, p);
-    // dh_prev[d] = dG_t[d] W_h[d]   (B x 4He) x (4He x He), both directions in one batched launch
-    for (int d = 0; d < 2; d++) {
-      int t = d == 0 ? S - 1 - i : i;
-      Gemm g;
-      g.M = B; g.N = He; g.K = 4 * He;
-      g.A = dGe + (int64_t)t * B * 8 * He + d * 4 * He; g.sam = 8 * He; g.sak = 1;
-      g.B = d_params + L.enc_wh[d]; g.sbk = He; g.sbn = 1;
-      g.C = enc_dh + d * slot; g.ldc = He;
-      gemm(g, 2);
+  if (cfg.gemm_mode != 2) {
+    encoder_backward_steps_tc();
+  } else {
+    EncStepBwd p;
+    p.Wh[0] = d_params + L.enc_wh[0]; p.Wh[1] = d_params + L.enc_wh[1];
+    p.Cst = Cenc; p.acts = acts_enc; p.Dctx = Dctx; p.dh = enc_dh; p.dc = enc_dc; p.dG = dGe;
+    p.B = B; p.S = S; p.He = He;
+    for (int i = 0; i < S; i++) {
+      p.step = i;
+      enc_cell_bwd(ctx_, p);
+      // dh_prev[d] = dG_t[d] W_h[d]   (B x 4He) x (4He x He)
+      for (int d = 0; d < 2; d++) {
+        int t = d == 0 ? S - 1 - i : i;
+        Gemm g;
+        g.M = B; g.N = He; g.K = 4 * He;
+        g.A = dGe + (int64_t)t * B * 8 * He + d * 4 * He; g.sam = 8 * He; g.sak = 1;
+        g.B = d_params + L.enc_wh[d]; g.sbk = He; g.sbn = 1;
+        g.C = enc_dh + d * slot; g.ldc = He;
+        gemm(g, 2);
+      }
     }
   }
   // time-batched parameter and input gradients

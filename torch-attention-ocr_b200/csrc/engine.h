@@ -96,6 +96,8 @@ class Engine {
   void decoder_backward_steps_simt();
   void decoder_backward_steps_tc();
   void build_decoder_packs();
+  void encoder_forward_steps_tc();
+  void encoder_backward_steps_tc();
   void conv_wgrad_tc(const float* dz, const float* x, int N, int H, int W, int Cin, int k, int pad, int Ho, int Wo,
                      int Cout, float* dW);
   void conv_tc(const float* x, int N, int H, int W, int C, int k, int pad, int Ho, int Wo, const float* Wk, int Cout,
@@ -115,9 +117,11 @@ class Engine {
   // tensor-core decoder path: concatenated weight packs, per-step operand packs, split-K partial regions
   Pack Wcat1p, Wcat2p, Wap, Wcp, Wcat1Tp, Wcat2Tp, WaTp, WcTp;
   Pack X1p, X2p, CATp, dUp, dQp, dG2p, dG1p;
+  Pack Whp[2], WhTp[2], HencP[2], dGeP[2];
   float* dec_ws[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t dec_ws_floats = 0;
   int64_t dec_packs_version_ = -1;
+  int64_t enc_packs_version_ = -1;
   int64_t scratch_elems_ = 0;
   int He, Hd, E, V, K1, h1off, Bmax, Smax, Tmax, Wmax;
   std::vector<void*> allocs_;

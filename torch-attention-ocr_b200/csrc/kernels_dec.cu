@@ -281,6 +281,63 @@ __global__ void __launch_bounds__(256) attn_bwd_tc_kernel(const float* __restric
   }
 }
 
+// encoder cell, both directions (grid-stride over dir x batch x unit); slot convention of engine.cu
+__global__ void __launch_bounds__(256) enc_cell_fwd_tc_kernel(EncCellFwdTc p) {
+  const int He = p.He, B = p.B, S = p.S;
+  const int64_t total = (int64_t)2 * B * He;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int unit = (int)(e % He);
+    const int64_t b = (e / He) % B;
+    const int d = (int)(e / ((int64_t)He * B));
+    const int t = d == 0 ? p.step : S - 1 - p.step;
+    const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
+    const float* xg = p.xg + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
+    const PartIn& G = p.G[d];
+    const float i_ = sigmoidf_(part_load(G, b, unit) + xg[0]);
+    const float f_ = sigmoidf_(part_load(G, b, He + unit) + xg[He]);
+    const float o_ = sigmoidf_(part_load(G, b, 2 * He + unit) + xg[2 * He]);
+    const float g_ = tanhf(part_load(G, b, 3 * He + unit) + xg[3 * He]);
+    const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
+    const float c = f_ * cp + i_ * g_;
+    const float h = o_ * tanhf(c);
+    p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit] = c;
+    p.H[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit] = h;
+    float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
+    a[0] = i_; a[He] = f_; a[2 * He] = o_; a[3 * He] = g_;
+    p.ctx[((int64_t)b * S + t) * (2 * He) + d * He + unit] = h;
+    pack_store(p.hp[d], b, unit, h);
+  }
+}
+
+__global__ void __launch_bounds__(256) enc_cell_bwd_tc_kernel(EncCellBwdTc p) {
+  const int He = p.He, B = p.B, S = p.S;
+  const int64_t total = (int64_t)2 * B * He;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int unit = (int)(e % He);
+    const int64_t b = (e / He) % B;
+    const int d = (int)(e / ((int64_t)He * B));
+    const int t = d == 0 ? S - 1 - p.step : p.step;
+    const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
+    const float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
+    const float i_ = a[0], f_ = a[He], o_ = a[2 * He], g_ = a[3 * He];
+    const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
+    const float tc = tanhf(p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit]);
+    const float dh = part_load(p.dh[d], b, unit) + p.Dctx[((int64_t)b * S + t) * (2 * He) + d * He + unit];
+    const float dc = p.dc[e] + dh * o_ * (1.f - tc * tc);
+    const float d0 = dc * g_ * i_ * (1.f - i_);
+    const float d1 = dc * cp * f_ * (1.f - f_);
+    const float d2 = dh * tc * o_ * (1.f - o_);
+    const float d3 = dc * i_ * (1.f - g_ * g_);
+    float* dg = p.dG + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
+    dg[0] = d0; dg[He] = d1; dg[2 * He] = d2; dg[3 * He] = d3;
+    pack_store(p.dgp[d], b, unit, d0);
+    pack_store(p.dgp[d], b, He + unit, d1);
+    pack_store(p.dgp[d], b, 2 * He + unit, d2);
+    pack_store(p.dgp[d], b, 3 * He + unit, d3);
+    p.dc[e] = dc * f_;
+  }
+}
+
 __global__ void part_to_dense_kernel(PartIn in, float* dst, int64_t ld, int B, int cols) {
   const int64_t total = (int64_t)B * cols;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -297,6 +354,14 @@ void part_to_dense(Ctx& ctx, const PartIn& in, float* dst, int64_t ld, int B, in
   AOCR_LAUNCH_CHECK(ctx);
 }
 
+void enc_cell_fwd_tc(Ctx& ctx, const EncCellFwdTc& p) {
+  enc_cell_fwd_tc_kernel<<<grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+void enc_cell_bwd_tc(Ctx& ctx, const EncCellBwdTc& p) {
+  enc_cell_bwd_tc_kernel<<<grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
+  AOCR_LAUNCH_CHECK(ctx);
+}
 void cell_fwd_tc(Ctx& ctx, const CellFwdTc& p) {
   cell_fwd_tc_kernel<<<grid_for((int64_t)p.B * p.H, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
   AOCR_LAUNCH_CHECK(ctx);

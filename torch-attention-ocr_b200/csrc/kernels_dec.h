@@ -46,3 +46,24 @@ void attn_bwd_tc(Ctx&, const float* ctx, const float* alpha, const PartIn& dcv, 
                  float* de, float* dq, const PackOut& dqp, int B, int S, int H);
 
 }  // namespace aocr
+
+namespace aocr {
+// ---- encoder recurrence on tensor cores: one cell kernel per step handles both directions
+struct EncCellFwdTc {
+  PartIn G[2];          // h_prev W_h^T per direction, (B, 4He), split-K partials
+  const float* xg;      // (S*B, 8He) input projections incl. biases, [fw | bw]
+  float* H; float* Cst; float* acts; float* ctx;     // layouts of kernels.h:EncStep
+  PackOut hp[2];        // h_t as bf16 planes = next step's GEMM operand, per direction (row 0 = batch row 0)
+  int B, S, He, step;
+};
+void enc_cell_fwd_tc(Ctx&, const EncCellFwdTc&);
+struct EncCellBwdTc {
+  PartIn dh[2];         // recurrent part of d h_t per direction (B, He)
+  const float* Cst; const float* acts; const float* Dctx;
+  float* dc;            // (2,B,He) carry
+  float* dG;            // (S*B, 8He)
+  PackOut dgp[2];       // d gates of this step as bf16 planes (B, 4He) per direction
+  int B, S, He, step;
+};
+void enc_cell_bwd_tc(Ctx&, const EncCellBwdTc&);
+}  // namespace aocr
