@@ -227,13 +227,19 @@ void Engine::decoder_backward() {
   AOCR_CUDA(cudaMemcpyAsync(d_grads + L.l1_bh, d_grads + L.l1_bi, (size_t)4 * Hd * sizeof(float), cudaMemcpyDeviceToDevice,
                             ctx_.st));
   // embedding path: dP[v] = sum of dg1 rows whose input token is v (LookupTable has no paddingValue: PAD rows count)
-  token_segment_sum(ctx_, dG1, tgt_tb, dP, R, 4 * Hd, V);
-  g = Gemm();                                             // dEmb = dP W_i1[:, :E]
-  g.M = V; g.N = E; g.K = 4 * Hd;
-  g.A = dP; g.sam = 4 * Hd; g.sak = 1;
-  g.B = d_params + L.l1_wi; g.sbk = in1; g.sbn = 1;
-  g.C = d_grads + L.emb; g.ldc = E;
-  gemm(g);
+  if (cfg.gemm_mode != 2) {
+    onehot(ctx_, tgt_tb, dZ /* reused as (R x V) one-hot scratch: dZ is dead by now */, R, V);
+    g = Gemm();                                           // dP = onehot^T dG1   (MN-major tensor-core GEMM)
+    g.M = V; g.N = 4 * Hd; g.K = (int)R;
+    g.A = dZ; g.sam = 1; g.sak = V;
+    g.B = dG1; g.sbk = 4 * Hd; g.sbn = 1;
+    g.C = dP; g.ldc = 4 * Hd;
+    gemm(g);
+  } else {
+    token_segment_sum(ctx_, dG1, tgt_tb, dP, R, 4 * Hd, V);
+  }
+  // dEmb = dP W_i1[:, :E]
+  thin_n_gemm(ctx_, dP, 4 * Hd, d_params + L.l1_wi, in1, d_grads + L.emb, E, V, 4 * Hd, E);
   g = Gemm();                                             // dW_i1[:, :E] = dP^T Emb
   g.M = 4 * Hd; g.N = E; g.K = V;
   g.A = dP; g.sam = 1; g.sak = 4 * Hd;

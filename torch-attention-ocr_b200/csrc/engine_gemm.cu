@@ -206,3 +206,49 @@ extern "C" int aocr_selftest_gemm(int M, int N, int K, int ta, int tb, int mode,
   if (ctx.st) cudaStreamDestroy(ctx.st);
   return rc;
 }
+
+// micro-benchmark of the tcgen05 GEMM core on device-resident random operands (warm L2, CUDA events):
+// returns the average microseconds per call.  layout: 0 = K-major (N side = batch when swap), 1 = MN-major.
+extern "C" int aocr_bench_gemm(int M, int N, int K, int terms, int mn, int splits, int reps, float* us_out) {
+  using namespace aocr;
+  Ctx ctx;
+  __nv_bfloat16* pl[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* dC = nullptr;
+  int rc = 0;
+  try {
+    AOCR_CUDA(cudaStreamCreate(&ctx.st));
+    cudaDeviceProp prop; AOCR_CUDA(cudaGetDeviceProperties(&prop, 0)); ctx.num_sms = prop.multiProcessorCount;
+    ctx.tc_ws_floats = (int64_t)32 * 148 * 128 * 128;
+    AOCR_CUDA(cudaMalloc(&ctx.tc_ws, ctx.tc_ws_floats * 4));
+    const int64_t kp = pad64(K), mp = pad64(M), np_ = pad64(N);
+    const size_t ea = mn ? (size_t)K * mp : (size_t)M * kp, eb = mn ? (size_t)K * np_ : (size_t)N * kp;
+    AOCR_CUDA(cudaMalloc(&pl[0], ea * 2)); AOCR_CUDA(cudaMalloc(&pl[1], ea * 2));
+    AOCR_CUDA(cudaMalloc(&pl[2], eb * 2)); AOCR_CUDA(cudaMalloc(&pl[3], eb * 2));
+    for (int i = 0; i < 4; i++) AOCR_CUDA(cudaMemset(pl[i], 0x11, (i < 2 ? ea : eb) * 2));
+    AOCR_CUDA(cudaMalloc(&dC, (size_t)M * N * 4));
+    TcGemm t;
+    t.A.hi = pl[0]; t.A.lo = pl[1]; t.B.hi = pl[2]; t.B.lo = pl[3];
+    if (mn) { t.A.rows = K; t.A.kp = mp; t.B.rows = K; t.B.kp = np_; t.mn = 1; }
+    else { t.A.rows = M; t.A.kp = kp; t.B.rows = N; t.B.kp = kp; }
+    t.M = M; t.N = N; t.K = K; t.C = dC; t.ldc = N; t.terms = terms; t.force_splits = splits;
+    t.defer_reduce = true; t.ws = ctx.tc_ws; t.ws_floats = ctx.tc_ws_floats;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; i++) gemm_tc(ctx, t);
+    AOCR_CUDA(cudaEventRecord(e0, ctx.st));
+    for (int i = 0; i < reps; i++) gemm_tc(ctx, t);
+    AOCR_CUDA(cudaEventRecord(e1, ctx.st));
+    AOCR_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *us_out = ms * 1000.f / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "aocr_bench_gemm: %s\n", e.what());
+    rc = -2;
+  }
+  for (auto q : pl) cudaFree(q);
+  cudaFree(dC); cudaFree(ctx.tc_ws);
+  if (ctx.st) cudaStreamDestroy(ctx.st);
+  return rc;
+}

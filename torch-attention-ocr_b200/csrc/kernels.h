@@ -103,6 +103,10 @@ void gather_tokens(Ctx&, const int32_t* tgt_bt /*(B,T)*/, int32_t* out_tb /*(T,B
                    int32_t padval);
 // segment-sum of dG1 rows by token id: dP[v] = sum_{r: y[r]==v} dG[r]  (V x N); deterministic per column
 void token_segment_sum(Ctx&, const float* dG, const int32_t* y_tb, float* dP, int64_t R, int N, int V);
+void onehot(Ctx&, const int32_t* y, float* oh, int64_t R, int V);
+// out (M x E) = A (M x K, lda) * W (K x E, ldw) for E <= 32 (embedding-sized right-hand sides)
+void thin_n_gemm(Ctx&, const float* A, int64_t lda, const float* W, int64_t ldw, float* out, int64_t ldo, int M, int K,
+                 int E);
 
 // ---------------- optimiser (src/optim/optim_sgd.lua:49-52,90) --------------------------------
 void sumsq_partial(Ctx&, const float* v, int64_t n, double* partial, int nblk);   // partial[nblk]

@@ -443,6 +443,44 @@ __global__ void __launch_bounds__(256) token_segment_sum_kernel(const float* __r
   dP[(int64_t)v * N + n] = s;
 }
 
+// oh[r][v] = 1 if token y[r] == v+1 : turns the embedding-row segment sum into a GEMM
+__global__ void onehot_kernel(const int32_t* __restrict__ y, float* __restrict__ oh, int64_t R, int V) {
+  const int64_t total = R * V;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    oh[e] = (y[e / V] - 1 == (int)(e % V)) ? 1.f : 0.f;
+}
+// out[m][e] = sum_k A[m*lda + k] * W[k*ldw + e], e < E <= 32 : one CTA per row m, K split over the threads
+__global__ void __launch_bounds__(256) thin_n_gemm_kernel(const float* __restrict__ A, int64_t lda,
+                                                          const float* __restrict__ W, int64_t ldw,
+                                                          float* __restrict__ out, int64_t ldo, int K, int E) {
+  __shared__ float red[8][32];
+  const int m = blockIdx.x, lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  float acc[32];
+#pragma unroll
+  for (int e = 0; e < 32; e++) acc[e] = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) {          // coalesced over k; each thread owns whole rows of W
+    const float a = A[(int64_t)m * lda + k];
+    const float* w = W + (int64_t)k * ldw;
+#pragma unroll
+    for (int e = 0; e < 32; e++)
+      if (e < E) acc[e] = fmaf(a, w[e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 32; e++) {
+    float v = acc[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][e] = v;
+  }
+  __syncthreads();
+  if (warp == 0 && lane < E) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += red[w][lane];
+    out[(int64_t)m * ldo + lane] = s;
+  }
+}
+
 // ------------------------------------------------------------------ optimiser
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ v, int64_t n,
                                                             double* __restrict__ partial) {
@@ -460,12 +498,17 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   }
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
-__global__ void sumsq_final_kernel(const double* partial, int nblk, double* out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < nblk; i++) s += partial[i];
-    *out = s;
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const double* partial, int nblk, double* out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 256) s += partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) *out = red[0];
 }
 __global__ void __launch_bounds__(256) sgd_apply_kernel(float* __restrict__ p, float* __restrict__ g, int64_t n,
                                                         const double* __restrict__ sumsq, double lr, double clip) {
@@ -553,12 +596,22 @@ void token_segment_sum(Ctx& ctx, const float* dG, const int32_t* y, float* dP, i
   token_segment_sum_kernel<<<grid, 256, 0, ctx.st>>>(dG, y, dP, R, N);
   AOCR_LAUNCH_CHECK(ctx);
 }
+void onehot(Ctx& ctx, const int32_t* y, float* oh, int64_t R, int V) {
+  onehot_kernel<<<grid_for(R * V, 256, ctx.num_sms), 256, 0, ctx.st>>>(y, oh, R, V);
+  AOCR_LAUNCH_CHECK(ctx);
+}
+void thin_n_gemm(Ctx& ctx, const float* A, int64_t lda, const float* W, int64_t ldw, float* out, int64_t ldo, int M, int K,
+                 int E) {
+  AOCR_CHECK(E <= 32, "thin_n_gemm: N must be <= 32");
+  thin_n_gemm_kernel<<<M, 256, 0, ctx.st>>>(A, lda, W, ldw, out, ldo, K, E);
+  AOCR_LAUNCH_CHECK(ctx);
+}
 void sumsq_partial(Ctx& ctx, const float* v, int64_t n, double* partial, int nblk) {
   sumsq_partial_kernel<<<nblk, 256, 0, ctx.st>>>(v, n, partial);
   AOCR_LAUNCH_CHECK(ctx);
 }
 void sumsq_final(Ctx& ctx, const double* partial, int nblk, double* out) {
-  sumsq_final_kernel<<<1, 32, 0, ctx.st>>>(partial, nblk, out);
+  sumsq_final_kernel<<<1, 256, 0, ctx.st>>>(partial, nblk, out);
   AOCR_LAUNCH_CHECK(ctx);
 }
 void sgd_apply(Ctx& ctx, float* p, float* g, int64_t n, const double* sumsq, double lr, double clip) {
