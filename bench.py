@@ -41,6 +41,14 @@ def load_peaks():
     return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)"""
+    p = os.path.join(ROOT, "profiles", "r01_tc_gemm_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    return None
+
+
 class ClockSampler(threading.Thread):
     """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -214,20 +222,43 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # ---- per-kernel-class timing for the roofline (separate profiled steps: events around each launch)
+    # ---- greedy decode (the metric's second half): greedy pass + gold pass, max_decoder_l = 50 steps each
+    nd = max(3, steps // 2)
+    for _ in range(2):
+        h.decode_greedy_staged(sync=True)
+    evd = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nd)]
+    barrier()
+    for i in range(nd):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            evd[i][0].record(stream)
+        h.decode_greedy_staged(sync=False)
+        with torch.cuda.stream(stream):
+            evd[i][1].record(stream)
+    barrier()
+    ms_dec = sum(a.elapsed_time(b) for a, b in evd) / nd
+    t0 = time.perf_counter()
+    for _ in range(nd):
+        model.step(hb, True)
+    barrier()
+    ms_dec_e2e = (time.perf_counter() - t0) * 1e3 / nd
+
+    # ---- per-kernel-class timing for the roofline: CUDA events recorded on the engine stream around every call of
+    # the class during extra (untimed) steps; no host sync inside the step
     peaks = load_peaks()
+    h.stage_batch(batch["images"], batch["targets"], batch["targets_eval"])
     h.prof_enable(True)
-    nprof = 2
+    nprof = 3
     for _ in range(nprof):
         step_resident()
     h.synchronize()
     prof = [h.prof_read(c) for c in range(3)]
     h.prof_enable(False)
 
-    t = torch.tensor([ms_resident, ms_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_resident, ms_e2e, ms_dec, ms_dec_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_resident, ms_e2e = float(t[0]), float(t[1])
+    ms_resident, ms_e2e, ms_dec, ms_dec_e2e = (float(x) for x in t)
     if rank == 0:
         total_imgs = B_PER_GPU * world
         value = total_imgs / (ms_resident / 1e3)
@@ -235,10 +266,11 @@ def main():
         att_ms, att_n, att_bytes = prof[1]
         rec_ms, rec_n, rec_flops = prof[2]
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "GEMM/conv class (all contractions of the step)",
+        roof = {"bound": "tensor",
+                "kernel": "tc_gemm_kernel (tcgen05 GEMM / implicit-GEMM conv incl. operand conversion and split-K reduce)",
                 "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_sustained"], "peak_source": peaks["src"] + " (sustained bf16)",
-                "traffic": None, "launches_per_step": gemm_n / nprof, "ms_per_step_in_class": gemm_ms / nprof,
+                "traffic": load_traffic(), "launches_per_step": gemm_n / nprof, "ms_per_step_in_class": gemm_ms / nprof,
                 "share_of_step": (gemm_ms / nprof) / ms_resident,
                 "attention_step": {"bound": "hbm", "achieved": att_bytes / (att_ms * 1e-3) / 1e9 if att_ms > 0 else 0.0,
                                    "peak": peaks["hbm"], "unit": "GB/s",
@@ -258,6 +290,11 @@ def main():
                 "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
                 "gpu_launches": int(launches),
+                "decode": {"metric": "greedy_decode_images_per_sec", "value": total_imgs / (ms_dec / 1e3),
+                           "unit": "images/s", "ms_per_batch": ms_dec,
+                           "workload": "greedy decode + gold pass, batch 64/GPU, 32x100, 2 x 50 decoder steps",
+                           "e2e": {"value": total_imgs / (ms_dec_e2e / 1e3), "unit": "images/s",
+                                   "ms_per_batch": ms_dec_e2e}},
                 "roofline": roof,
                 "step_model_flops_frac_of_peak": value * FLOP_PER_IMG_TRAIN / 1e12 / world / peaks["bf16_sustained"]}
         if not args.no_cpu_baseline and world >= 1:

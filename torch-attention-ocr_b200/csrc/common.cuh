@@ -41,9 +41,18 @@ struct Ctx {
   int64_t tc_ws_floats = 0;
   int* tc_counters = nullptr;
   int tc_counters_n = 0;
+  bool pdl = true;   // AOCR_PDL=0 disables programmatic dependent launch
 };
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL): kernels of the per-timestep chains are launched with
+// programmaticStreamSerialization so the next kernel's launch + prologue overlaps the tail of the current one.
+// Contract: a kernel launched through launch_pdl() touches no global memory before pdl_wait().
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 #define AOCR_LAUNCH_CHECK(ctx)                \
   do {                                        \
@@ -67,5 +76,19 @@ struct Gemm {
   int batch = 1; int64_t bsa = 0, bsb = 0, bsc = 0;
 };
 void gemm_simt(Ctx& ctx, const Gemm& g);
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(Ctx& ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx.st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ctx.pdl ? 1 : 0;
+  AOCR_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  ctx.launches++;
+}
+#endif
 
 }  // namespace aocr

@@ -107,6 +107,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   AOCR_CUDA(cudaGetDeviceProperties(&prop, device));
   AOCR_CHECK(prop.major == 10, "libaocr is built for sm_100a (B200) only");
   ctx_.num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("AOCR_PDL")) ctx_.pdl = atoi(e) != 0;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));
   AOCR_CUDA(cudaEventCreate(&ev1_));
@@ -203,6 +204,7 @@ Engine::~Engine() {
   for (void* p : allocs_) cudaFree(p);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
+  for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
   if (ctx_.st) cudaStreamDestroy(ctx_.st);
 }
 
@@ -294,18 +296,37 @@ void Engine::stage_batch(const float* images, int b, int W, const int32_t* tgt, 
   have_batch_ = true;
 }
 
+// Per-class device timing for bench.py's roofline: CUDA events recorded on the engine stream around every call
+// of a class, no host synchronisation (the elapsed times are read once, after the step).
 void Engine::prof_begin(int cls) {
-  if (prof_on) AOCR_CUDA(cudaEventRecord(ev0_, ctx_.st));
+  if (!prof_on) return;
+  if (prof_used_ * 2 + 2 > prof_pool_.size()) {
+    for (int i = 0; i < 512; i++) {
+      cudaEvent_t e;
+      AOCR_CUDA(cudaEventCreate(&e));
+      prof_pool_.push_back(e);
+    }
+  }
+  AOCR_CUDA(cudaEventRecord(prof_pool_[prof_used_ * 2], ctx_.st));
 }
 void Engine::prof_end(int cls, double work) {
   if (!prof_on) return;
-  AOCR_CUDA(cudaEventRecord(ev1_, ctx_.st));
-  AOCR_CUDA(cudaEventSynchronize(ev1_));
-  float ms = 0.f;
-  AOCR_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
-  prof_ms[cls] += ms; prof_launches[cls] += 1; prof_work[cls] += work;
+  AOCR_CUDA(cudaEventRecord(prof_pool_[prof_used_ * 2 + 1], ctx_.st));
+  prof_recs_.push_back({cls, work});
+  prof_used_++;
 }
-
+void Engine::prof_collect() {
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  for (size_t i = 0; i < prof_recs_.size(); i++) {
+    float ms = 0.f;
+    AOCR_CUDA(cudaEventElapsedTime(&ms, prof_pool_[2 * i], prof_pool_[2 * i + 1]));
+    prof_ms[prof_recs_[i].first] += ms;
+    prof_launches[prof_recs_[i].first] += 1;
+    prof_work[prof_recs_[i].first] += prof_recs_[i].second;
+  }
+  prof_recs_.clear();
+  prof_used_ = 0;
+}
 
 void Engine::conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const {
   // l = 1..6 (0-based index into kConv): input of conv_{l+1}

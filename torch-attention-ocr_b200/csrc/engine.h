@@ -108,6 +108,12 @@ class Engine {
   Pack operand_pack(const float* ptr, int64_t rows, int64_t K, int64_t srs, int64_t sks, int slot);
   void prof_begin(int cls);
   void prof_end(int cls, double work);
+ public:
+  void prof_collect();
+ private:
+  std::vector<cudaEvent_t> prof_pool_;
+  std::vector<std::pair<int, double>> prof_recs_;
+  size_t prof_used_ = 0;
 
   int device_;
   struct WeightPack { Pack pack; int64_t version; };

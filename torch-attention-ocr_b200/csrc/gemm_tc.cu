@@ -151,6 +151,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const TcParams p) {
   using C_ = Cfg<BN>;
+  pdl_launch_dependents();   // let the next kernel's prologue start; it waits on this grid before touching memory
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B tiles need 1024-byte alignment
@@ -194,6 +195,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                // barrier init / TMEM alloc / tensor-map prefetch above overlap the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -364,6 +366,8 @@ __global__ void __launch_bounds__(256) split_kfast_kernel(const float* __restric
                                                           int64_t srs, int64_t kp, int64_t kw,
                                                           __nv_bfloat16* __restrict__ hi,
                                                           __nv_bfloat16* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t kq = kw / 4;   // kw = columns written (zero padded past K), kp = row pitch of the planes
   const int64_t total = rows * kq;
   const bool vec = ((srs & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -389,6 +393,8 @@ __global__ void __launch_bounds__(256) split_kfast_kernel(const float* __restric
 __global__ void __launch_bounds__(256) split_tile_kernel(const float* __restrict__ src, int64_t rows, int64_t K,
                                                          int64_t srs, int64_t sks, int64_t kp, int64_t kw,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
@@ -417,6 +423,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             float* __restrict__ C, long long rows, long long cols,
                                                             long long ldc, const float* __restrict__ bias_r,
                                                             const float* __restrict__ bias_c, int act, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = rows * cols;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / cols, c = e % cols;
@@ -495,8 +503,8 @@ void launch(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtens
     AOCR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  tc_gemm_kernel<BN><<<grid, 192, Cfg<BN>::kSmemBytes, ctx.st>>>(ah, al, bh, bl, p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, tc_gemm_kernel<BN>, grid, dim3(192), (size_t)Cfg<BN>::kSmemBytes, ah, al, bh, bl, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 }  // namespace
@@ -518,13 +526,13 @@ void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t 
     int64_t total = rows * (kw / 4);
     int64_t g = (total + 255) / 256;
     int64_t cap = (int64_t)ctx.num_sms * 8;
-    split_kfast_kernel<<<(unsigned)(g < cap ? (g > 0 ? g : 1) : cap), 256, 0, ctx.st>>>(src, rows, K, srs, dst.kp, kw,
-                                                                                    dst.hi, dst.lo);
+    launch_pdl(ctx, split_kfast_kernel, dim3((unsigned)(g < cap ? (g > 0 ? g : 1) : cap)), dim3(256), 0, src, rows, K, srs,
+               dst.kp, kw, dst.hi, dst.lo);
   } else {
     dim3 grid((unsigned)((kw + 31) / 32), (unsigned)((rows + 31) / 32));
-    split_tile_kernel<<<grid, 256, 0, ctx.st>>>(src, rows, K, srs, sks, dst.kp, kw, dst.hi, dst.lo);
+    launch_pdl(ctx, split_tile_kernel, grid, dim3(256), 0, src, rows, K, srs, sks, dst.kp, kw, dst.hi, dst.lo);
   }
-  AOCR_LAUNCH_CHECK(ctx);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
@@ -637,9 +645,9 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     const long long total = crows * ccols;
     long long nb = (total + 255) / 256;
     if (nb > (long long)ctx.num_sms * 8) nb = (long long)ctx.num_sms * 8;
-    splitk_reduce_kernel<<<(unsigned)nb, 256, 0, ctx.st>>>(wsbase, p.splits, part_stride, g.C, crows, ccols, g.ldc,
-                                                           bias_r, bias_c, g.act, g.accumulate);
-    AOCR_LAUNCH_CHECK(ctx);
+    launch_pdl(ctx, splitk_reduce_kernel, dim3((unsigned)nb), dim3(256), 0, (const float*)wsbase, p.splits, part_stride,
+               g.C, crows, ccols, (long long)g.ldc, bias_r, bias_c, g.act, g.accumulate);
+    AOCR_CUDA(cudaGetLastError());
   }
   return out;
 }

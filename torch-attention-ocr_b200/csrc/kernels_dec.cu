@@ -55,6 +55,8 @@ inline int grid_for(int64_t total, int threads, int num_sms) {
 }
 
 __global__ void __launch_bounds__(256) cell_fwd_tc_kernel(CellFwdTc p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(256) cell_fwd_tc_kernel(CellFwdTc p) {
 
 // a = tanh(u): the decoder output / next step's input feed
 __global__ void __launch_bounds__(256) dec_out_tc_kernel(DecOutTc p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -93,6 +97,8 @@ __global__ void __launch_bounds__(256) dec_out_tc_kernel(DecOutTc p) {
 
 // du = (da_carry + da_gen) * (1 - a^2)
 __global__ void __launch_bounds__(256) du_tc_kernel(DuTc p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -108,6 +114,8 @@ __global__ void __launch_bounds__(256) du_tc_kernel(DuTc p) {
 }
 
 __global__ void __launch_bounds__(256) cell_bwd_tc_kernel(CellBwdTc p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -142,6 +150,8 @@ constexpr int ATT_MAXV = 8;
 __global__ void __launch_bounds__(256) attn_fwd_tc_kernel(const float* __restrict__ ctx, PartIn q,
                                                           float* __restrict__ alpha, float* __restrict__ cv, int64_t ldcv,
                                                           PackOut cvp, int S, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* es = sm;
   float* wm = es + ((S + 3) & ~3);
@@ -216,6 +226,8 @@ __global__ void __launch_bounds__(256) attn_bwd_tc_kernel(const float* __restric
                                                           PartIn dcv, float* __restrict__ dcv_out, int64_t ld_dcv_out,
                                                           float* __restrict__ de, float* __restrict__ dq, PackOut dqp,
                                                           int S, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* das = sm;
   float* red = das + ((S + 3) & ~3);
@@ -283,6 +295,8 @@ __global__ void __launch_bounds__(256) attn_bwd_tc_kernel(const float* __restric
 
 // encoder cell, both directions (grid-stride over dir x batch x unit); slot convention of engine.cu
 __global__ void __launch_bounds__(256) enc_cell_fwd_tc_kernel(EncCellFwdTc p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int He = p.He, B = p.B, S = p.S;
   const int64_t total = (int64_t)2 * B * He;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -310,6 +324,8 @@ __global__ void __launch_bounds__(256) enc_cell_fwd_tc_kernel(EncCellFwdTc p) {
 }
 
 __global__ void __launch_bounds__(256) enc_cell_bwd_tc_kernel(EncCellBwdTc p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int He = p.He, B = p.B, S = p.S;
   const int64_t total = (int64_t)2 * B * He;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -339,6 +355,8 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_tc_kernel(EncCellBwdTc p) {
 }
 
 __global__ void part_to_dense_kernel(PartIn in, float* dst, int64_t ld, int B, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = (int64_t)B * cols;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(e % cols);
@@ -350,46 +368,46 @@ __global__ void part_to_dense_kernel(PartIn in, float* dst, int64_t ld, int B, i
 }  // namespace
 
 void part_to_dense(Ctx& ctx, const PartIn& in, float* dst, int64_t ld, int B, int cols) {
-  part_to_dense_kernel<<<grid_for((int64_t)B * cols, 256, ctx.num_sms), 256, 0, ctx.st>>>(in, dst, ld, B, cols);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, part_to_dense_kernel, dim3(grid_for((int64_t)B * cols, 256, ctx.num_sms)), dim3(256), 0, in, dst, ld, B, cols);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 void enc_cell_fwd_tc(Ctx& ctx, const EncCellFwdTc& p) {
-  enc_cell_fwd_tc_kernel<<<grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, enc_cell_fwd_tc_kernel, dim3(grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void enc_cell_bwd_tc(Ctx& ctx, const EncCellBwdTc& p) {
-  enc_cell_bwd_tc_kernel<<<grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, enc_cell_bwd_tc_kernel, dim3(grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void cell_fwd_tc(Ctx& ctx, const CellFwdTc& p) {
-  cell_fwd_tc_kernel<<<grid_for((int64_t)p.B * p.H, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, cell_fwd_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void dec_out_tc(Ctx& ctx, const DecOutTc& p) {
-  dec_out_tc_kernel<<<grid_for((int64_t)p.B * p.H, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, dec_out_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void du_tc(Ctx& ctx, const DuTc& p) {
-  du_tc_kernel<<<grid_for((int64_t)p.B * p.H, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, du_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void cell_bwd_tc(Ctx& ctx, const CellBwdTc& p) {
-  cell_bwd_tc_kernel<<<grid_for((int64_t)p.B * p.H, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, cell_bwd_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void attn_fwd_tc(Ctx& ctx, const float* c, const PartIn& q, float* alpha, float* cv, int64_t ldcv, const PackOut& cvp,
                  int B, int S, int H) {
   AOCR_CHECK(H % 128 == 0 && H <= 128 * ATT_MAXV, "attention kernel needs decoder hidden size in {128,...,1024}");
   size_t smem = (size_t)(((S + 3) & ~3) + 2 * ATT_WARPS + ATT_WARPS * H) * sizeof(float);
-  attn_fwd_tc_kernel<<<B, 256, smem, ctx.st>>>(c, q, alpha, cv, ldcv, cvp, S, H);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, attn_fwd_tc_kernel, dim3(B), dim3(256), smem, c, q, alpha, cv, ldcv, cvp, S, H);
+  AOCR_CUDA(cudaGetLastError());
 }
 void attn_bwd_tc(Ctx& ctx, const float* c, const float* alpha, const PartIn& dcv, float* dcv_out, int64_t ld_dcv_out,
                  float* de, float* dq, const PackOut& dqp, int B, int S, int H) {
   size_t smem = (size_t)(((S + 3) & ~3) + 4 + ATT_WARPS * H) * sizeof(float);
-  attn_bwd_tc_kernel<<<B, 256, smem, ctx.st>>>(c, alpha, dcv, dcv_out, ld_dcv_out, de, dq, dqp, S, H);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, attn_bwd_tc_kernel, dim3(B), dim3(256), smem, c, alpha, dcv, dcv_out, ld_dcv_out, de, dq, dqp, S, H);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 }  // namespace aocr
