@@ -10,6 +10,8 @@ namespace {
 constexpr int TM = 64, TN = 64, TK = 16;
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -81,8 +83,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
 void gemm_simt(Ctx& ctx, const Gemm& g) {
   if (g.M <= 0 || g.N <= 0) return;
   dim3 grid(cdiv(g.N, TN), cdiv(g.M, TM), g.batch);
-  gemm_simt_kernel<<<grid, 256, 0, ctx.st>>>(g);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, gemm_simt_kernel, dim3(grid), dim3(256), 0, g);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 }  // namespace aocr

@@ -15,6 +15,8 @@ constexpr float BN_EPS = 1e-5f;
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ a1,
                                                         uint8_t* __restrict__ idx, int B, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float ws[64 * 9];
   __shared__ float bs[64];
   for (int i = threadIdx.x; i < 576; i += blockDim.x) ws[i] = w[i];
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(256) conv1_bwd_partial_kernel(const float* __r
                                                                 const uint8_t* __restrict__ idx,
                                                                 const float* __restrict__ da1, float* __restrict__ partial,
                                                                 int B, int W, int64_t pix_per_blk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = threadIdx.x % 64, lane = threadIdx.x / 64;   // 4 pixel lanes
   const int W1 = W / 2;
   const int64_t npix = (int64_t)B * 16 * W1;
@@ -109,6 +113,8 @@ __global__ void __launch_bounds__(256) conv1_bwd_partial_kernel(const float* __r
 }
 __global__ void conv1_bwd_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw,
                                        float* __restrict__ db) {
+  pdl_launch_dependents();
+  pdl_wait();
   int e = blockIdx.x * blockDim.x + threadIdx.x;   // 640 outputs
   if (e >= 640) return;
   int i = e / 64, c = e % 64;
@@ -121,6 +127,8 @@ __global__ void conv1_bwd_final_kernel(const float* __restrict__ partial, int nb
 template <int KW>
 __global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restrict__ z, float* __restrict__ a,
                                                             uint8_t* __restrict__ idx, int B, int H, int Wi, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = Wi / KW;
   const int64_t total = (int64_t)B * Ho * Wo * C;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -150,6 +158,8 @@ template <int KW>
 __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a,
                                                             const uint8_t* __restrict__ idx, float* __restrict__ dz,
                                                             int B, int H, int Wi, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = Wi / KW;
   const int64_t total = (int64_t)B * H * Wi * C;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -172,6 +182,8 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restr
 // ------------------------------------------------------------------ im2col
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ a, float* __restrict__ col, int B, int H,
                                                      int Wi, int C, int k, int pad, int Ho, int Wo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C4 = C / 4;
   const int64_t total = (int64_t)B * Ho * Wo * k * k * C4;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -197,6 +209,8 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
                                                          const float* __restrict__ mean, const float* __restrict__ var,
                                                          int64_t R, int C, int64_t rows_per, int mode,
                                                          float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + tx;
   int64_t r0 = (int64_t)blockIdx.y * rows_per;
@@ -225,6 +239,8 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
 // out[c] (op)= scale * sum_slab partial ; op: 0 set, 1 add
 __global__ void col_reduce_final_kernel(const float* __restrict__ partial, int nslab, int C, float scale, int accumulate,
                                         float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
@@ -235,6 +251,8 @@ __global__ void col_reduce_final_kernel(const float* __restrict__ partial, int n
 
 __global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var,
                                          float* __restrict__ rmean, float* __restrict__ rvar, int C, float unbias) {
+  pdl_launch_dependents();
+  pdl_wait();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   rmean[c] = 0.9f * rmean[c] + 0.1f * mean[c];
@@ -245,6 +263,8 @@ __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restric
                                                           const float* __restrict__ var, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ a, int64_t R,
                                                           int C, int tm_S, int tm_B) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C4 = C / 4;
   const int64_t total = R * C4;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -269,6 +289,8 @@ __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restric
 // dy = da * (a > 0), rows optionally read time-major
 __global__ void __launch_bounds__(256) relu_mask_kernel(const float* __restrict__ da, const float* __restrict__ a,
                                                         float* __restrict__ dy, int64_t R, int C, int tm_S, int tm_B) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C4 = C / 4;
   const int64_t total = R * C4;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -292,6 +314,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
                                                            const float* __restrict__ mean, const float* __restrict__ var,
                                                            const float* __restrict__ gamma, const float* __restrict__ s1,
                                                            const float* __restrict__ s2, int64_t R, int C, int train) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = R * C;
   const float invR = 1.0f / (float)R;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -330,28 +354,28 @@ void col_reduce(Ctx& ctx, const float* z, const float* z2, const float* mean, co
   int ns = nslabs_for(R, ctx.num_sms, C);
   int64_t rows_per = (R + ns - 1) / ns;
   dim3 grid(cdiv(C, 32), ns);
-  col_reduce_kernel<<<grid, 256, 0, ctx.st>>>(z, z2, mean, var, R, C, rows_per, mode, partial);
-  AOCR_LAUNCH_CHECK(ctx);
-  col_reduce_final_kernel<<<cdiv(C, 128), 128, 0, ctx.st>>>(partial, ns, C, scale, accumulate, out);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, col_reduce_kernel, dim3(grid), dim3(256), 0, z, z2, mean, var, R, C, rows_per, mode, partial);
+  AOCR_CUDA(cudaGetLastError());
+  launch_pdl(ctx, col_reduce_final_kernel, dim3(cdiv(C, 128)), dim3(128), 0, partial, ns, C, scale, accumulate, out);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 }  // namespace
 
 void conv1_fwd(Ctx& ctx, const float* x, const float* w, const float* bias, float* a1, uint8_t* idx, int B, int W) {
   int64_t total = (int64_t)B * 16 * (W / 2) * 64;
-  conv1_fwd_kernel<<<grid_for(total, 256, ctx.num_sms), 256, 0, ctx.st>>>(x, w, bias, a1, idx, B, W);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, conv1_fwd_kernel, dim3(grid_for(total, 256, ctx.num_sms)), dim3(256), 0, x, w, bias, a1, idx, B, W);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 void conv1_bwd(Ctx& ctx, const float* x, const float* a1, const uint8_t* idx, const float* da1, float* dw, float* db,
                float* partial, int nblk, int B, int W) {
   int64_t npix = (int64_t)B * 16 * (W / 2);
   int64_t per = (npix + nblk - 1) / nblk;
-  conv1_bwd_partial_kernel<<<nblk, 256, 0, ctx.st>>>(x, a1, idx, da1, partial, B, W, per);
-  AOCR_LAUNCH_CHECK(ctx);
-  conv1_bwd_final_kernel<<<cdiv(640, 128), 128, 0, ctx.st>>>(partial, nblk, dw, db);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, conv1_bwd_partial_kernel, dim3(nblk), dim3(256), 0, x, a1, idx, da1, partial, B, W, per);
+  AOCR_CUDA(cudaGetLastError());
+  launch_pdl(ctx, conv1_bwd_final_kernel, dim3(cdiv(640, 128)), dim3(128), 0, partial, nblk, dw, db);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 void relu_pool_fwd(Ctx& ctx, const float* z, float* a, uint8_t* idx, int B, int H, int Wi, int C, int kw) {
@@ -374,8 +398,8 @@ void relu_pool_bwd(Ctx& ctx, const float* da, const float* a, const uint8_t* idx
 void im2col(Ctx& ctx, const float* a, float* col, int B, int H, int Wi, int C, int k, int pad) {
   int Ho = H + 2 * pad - k + 1, Wo = Wi + 2 * pad - k + 1;
   int64_t total = (int64_t)B * Ho * Wo * k * k * (C / 4);
-  im2col_kernel<<<grid_for(total, 256, ctx.num_sms), 256, 0, ctx.st>>>(a, col, B, H, Wi, C, k, pad, Ho, Wo);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, im2col_kernel, dim3(grid_for(total, 256, ctx.num_sms)), dim3(256), 0, a, col, B, H, Wi, C, k, pad, Ho, Wo);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 void col_sum(Ctx& ctx, const float* z, int64_t R, int C, float* out, float* partial, int accumulate) {
@@ -402,22 +426,22 @@ void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* va
 
 void bn_update_running(Ctx& ctx, const float* mean, const float* var, float* rmean, float* rvar, int C, int64_t R) {
   float unbias = R > 1 ? (float)((double)R / (double)(R - 1)) : 1.f;
-  bn_update_running_kernel<<<cdiv(C, 128), 128, 0, ctx.st>>>(mean, var, rmean, rvar, C, unbias);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, bn_update_running_kernel, dim3(cdiv(C, 128)), dim3(128), 0, mean, var, rmean, rvar, C, unbias);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 void bn_relu_fwd(Ctx& ctx, const float* z, const float* mean, const float* var, const float* gamma, const float* beta,
                  float* a, int64_t R, int C, int tm_S, int tm_B) {
-  bn_relu_fwd_kernel<<<grid_for(R * (C / 4), 256, ctx.num_sms), 256, 0, ctx.st>>>(z, mean, var, gamma, beta, a, R, C,
+  launch_pdl(ctx, bn_relu_fwd_kernel, dim3(grid_for(R * (C / 4), 256, ctx.num_sms)), dim3(256), 0, z, mean, var, gamma, beta, a, R, C,
                                                                                  tm_S, tm_B);
-  AOCR_LAUNCH_CHECK(ctx);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, const float* mean, const float* var,
                  const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial, int64_t R, int C, int tm_S,
                  int tm_B, int train, const StatSync& sync) {
-  relu_mask_kernel<<<grid_for(R * (C / 4), 256, ctx.num_sms), 256, 0, ctx.st>>>(da, a, dz, R, C, tm_S, tm_B);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, relu_mask_kernel, dim3(grid_for(R * (C / 4), 256, ctx.num_sms)), dim3(256), 0, da, a, dz, R, C, tm_S, tm_B);
+  AOCR_CUDA(cudaGetLastError());
   // dbeta = s1 ; dgamma = s2 (each BN parameter receives gradient exactly once per step)
   col_reduce(ctx, dz, nullptr, nullptr, nullptr, R, C, 0, 1.0f, 0, dbeta, partial);
   col_reduce(ctx, dz, z, mean, var, R, C, 2, 1.0f, 0, dgamma, partial);
@@ -425,9 +449,9 @@ void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, cons
     if (dbeta == dgamma + C) sync.fn(sync.user, dgamma, 2 * (int64_t)C);
     else { sync.fn(sync.user, dgamma, C); sync.fn(sync.user, dbeta, C); }
   }
-  bn_bwd_apply_kernel<<<grid_for(R * C, 256, ctx.num_sms), 256, 0, ctx.st>>>(dz, z, mean, var, gamma, dbeta, dgamma,
+  launch_pdl(ctx, bn_bwd_apply_kernel, dim3(grid_for(R * C, 256, ctx.num_sms)), dim3(256), 0, dz, z, mean, var, gamma, dbeta, dgamma,
                                                                            R * sync.world, C, train);
-  AOCR_LAUNCH_CHECK(ctx);
+  AOCR_CUDA(cudaGetLastError());
   if (sync.world > 1) {   // the gradient all-reduce will sum these again over ranks: pre-divide
     scale_vec(ctx, dgamma, C, 1.0f / (float)sync.world);
     scale_vec(ctx, dbeta, C, 1.0f / (float)sync.world);

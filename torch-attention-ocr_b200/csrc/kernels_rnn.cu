@@ -30,6 +30,8 @@ inline int grid_for(int64_t total, int threads, int num_sms) {
 // ------------------------------------------------------------------ encoder step (both directions)
 // grid (He/8, 2, ceil(B/32)); CTA tile = 32 batch rows x (8 hidden units x 4 gates); K = He in chunks of 32.
 __global__ void __launch_bounds__(256) enc_step_fwd_kernel(EncStep p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float hs[32][33];
   __shared__ float ws[32][33];
   __shared__ float gs[32][33];
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(256) enc_step_fwd_kernel(EncStep p) {
 
 // elementwise over (dir, b, unit)
 __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(EncStepBwd p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int He = p.He, B = p.B, S = p.S;
   const int64_t total = (int64_t)2 * B * He;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -116,6 +120,8 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(EncStepBwd p) {
 
 // ------------------------------------------------------------------ decoder cells
 __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(DecCell p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -138,6 +144,8 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(DecCell p) {
 }
 
 __global__ void __launch_bounds__(256) dec_cell_bwd_kernel(DecCellBwd p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -170,6 +178,8 @@ constexpr int ATT_MAXV = 8;   // H <= 1024
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ ctx, const float* __restrict__ q,
                                                        float* __restrict__ alpha, float* __restrict__ cv, int64_t ldcv,
                                                        int S, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* es = sm;                       // S scores
   float* wm = es + ((S + 3) & ~3);      // ATT_WARPS maxima
@@ -243,6 +253,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const float* __restrict__ ctx, const float* __restrict__ alpha,
                                                        const float* __restrict__ dcv, int64_t lddcv,
                                                        float* __restrict__ de, float* __restrict__ dq, int S, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* das = sm;                        // S: dalpha then de
   float* red = das + ((S + 3) & ~3);      // 1
@@ -314,6 +326,8 @@ __global__ void __launch_bounds__(128) generator_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, const int32_t* __restrict__ y,
                                                         float* __restrict__ logp, float* __restrict__ dz,
                                                         float* __restrict__ rowloss, int H, int V, float inv_bn) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float zs[GEN_MAXV];
   const int64_t r = blockIdx.x;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -359,6 +373,8 @@ __global__ void __launch_bounds__(128) generator_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(1024) reduce_sum_double_kernel(const float* __restrict__ v, int64_t n,
                                                                  double* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[1024];
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += 1024) s += (double)v[i];
@@ -373,6 +389,8 @@ __global__ void __launch_bounds__(1024) reduce_sum_double_kernel(const float* __
 
 __global__ void greedy_select_kernel(float* __restrict__ logp, int32_t* __restrict__ tok, double* __restrict__ score,
                                      int32_t* __restrict__ labels, int64_t ldl, int t, int B, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float* lp = logp + (int64_t)b * V;
@@ -393,10 +411,14 @@ __global__ void greedy_select_kernel(float* __restrict__ logp, int32_t* __restri
 
 // ------------------------------------------------------------------ helpers
 __global__ void add_vec_kernel(float* out, const float* a, const float* b, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
     out[e] = a[e] + b[e];
 }
 __global__ void copy_strided_kernel(float* dst, int64_t ldd, const float* src, int64_t lds, int rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = (int64_t)rows * cols;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(e % cols);
@@ -405,6 +427,8 @@ __global__ void copy_strided_kernel(float* dst, int64_t ldd, const float* src, i
   }
 }
 __global__ void concat2_kernel(const float* s0, const float* s1, float* dst, int64_t ldd, int B, int He) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = (int64_t)B * 2 * He;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(e % (2 * He));
@@ -415,6 +439,8 @@ __global__ void concat2_kernel(const float* s0, const float* s1, float* dst, int
 // du = (da_carry + da_gen) * (1 - a^2)
 __global__ void du_from_da_kernel(const float* da_carry, int64_t ldc, const float* da_gen, const float* a, float* du,
                                   int64_t n, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     int u = (int)(e % H);
     int64_t b = e / H;
@@ -424,6 +450,8 @@ __global__ void du_from_da_kernel(const float* da_carry, int64_t ldc, const floa
   }
 }
 __global__ void gather_tokens_kernel(const int32_t* tgt_bt, int32_t* out_tb, int B, int T, int Tpad, int32_t padval) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int total = B * Tpad;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     int b = e % B, t = e / B;
@@ -434,6 +462,8 @@ __global__ void gather_tokens_kernel(const int32_t* tgt_bt, int32_t* out_tb, int
 __global__ void __launch_bounds__(256) token_segment_sum_kernel(const float* __restrict__ dG,
                                                                 const int32_t* __restrict__ y, float* __restrict__ dP,
                                                                 int64_t R, int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   int v = blockIdx.y;
   if (n >= N) return;
@@ -445,6 +475,8 @@ __global__ void __launch_bounds__(256) token_segment_sum_kernel(const float* __r
 
 // oh[r][v] = 1 if token y[r] == v+1 : turns the embedding-row segment sum into a GEMM
 __global__ void onehot_kernel(const int32_t* __restrict__ y, float* __restrict__ oh, int64_t R, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t total = R * V;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
     oh[e] = (y[e / V] - 1 == (int)(e % V)) ? 1.f : 0.f;
@@ -453,6 +485,8 @@ __global__ void onehot_kernel(const int32_t* __restrict__ y, float* __restrict__
 __global__ void __launch_bounds__(256) thin_n_gemm_kernel(const float* __restrict__ A, int64_t lda,
                                                           const float* __restrict__ W, int64_t ldw,
                                                           float* __restrict__ out, int64_t ldo, int K, int E) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][32];
   const int m = blockIdx.x, lane = threadIdx.x % 32, warp = threadIdx.x / 32;
   float acc[32];
@@ -484,6 +518,8 @@ __global__ void __launch_bounds__(256) thin_n_gemm_kernel(const float* __restric
 // ------------------------------------------------------------------ optimiser
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ v, int64_t n,
                                                             double* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[256];
   double s = 0.0;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
@@ -499,6 +535,8 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 __global__ void __launch_bounds__(256) sumsq_final_kernel(const double* partial, int nblk, double* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < nblk; i += 256) s += partial[i];
@@ -512,6 +550,8 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const double* partial,
 }
 __global__ void __launch_bounds__(256) sgd_apply_kernel(float* __restrict__ p, float* __restrict__ g, int64_t n,
                                                         const double* __restrict__ sumsq, double lr, double clip) {
+  pdl_launch_dependents();
+  pdl_wait();
   const double norm = sqrt(*sumsq);
   const float scale = norm > clip ? (float)(clip / norm) : 1.0f;   // optim_sgd.lua:50-52
   const float flr = (float)lr;
@@ -526,97 +566,97 @@ __global__ void __launch_bounds__(256) sgd_apply_kernel(float* __restrict__ p, f
 
 void enc_step_fwd(Ctx& ctx, const EncStep& p) {
   dim3 grid(p.He / 8, 2, cdiv(p.B, 32));
-  enc_step_fwd_kernel<<<grid, 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, enc_step_fwd_kernel, dim3(grid), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void enc_cell_bwd(Ctx& ctx, const EncStepBwd& p) {
-  enc_cell_bwd_kernel<<<grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, enc_cell_bwd_kernel, dim3(grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void dec_cell_fwd(Ctx& ctx, const DecCell& p) {
-  dec_cell_fwd_kernel<<<grid_for((int64_t)p.B * p.H, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, dec_cell_fwd_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void dec_cell_bwd(Ctx& ctx, const DecCellBwd& p) {
-  dec_cell_bwd_kernel<<<grid_for((int64_t)p.B * p.H, 256, ctx.num_sms), 256, 0, ctx.st>>>(p);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, dec_cell_bwd_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
+  AOCR_CUDA(cudaGetLastError());
 }
 void attn_fwd(Ctx& ctx, const float* c, const float* q, float* alpha, float* cv, int64_t ldcv, int B, int S, int H) {
   AOCR_CHECK(H % 128 == 0 && H <= 128 * ATT_MAXV, "attention kernel needs decoder hidden size in {128,...,1024}");
   size_t smem = (size_t)(((S + 3) & ~3) + 2 * ATT_WARPS + ATT_WARPS * H) * sizeof(float);
-  attn_fwd_kernel<<<B, 256, smem, ctx.st>>>(c, q, alpha, cv, ldcv, S, H);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, attn_fwd_kernel, dim3(B), dim3(256), smem, c, q, alpha, cv, ldcv, S, H);
+  AOCR_CUDA(cudaGetLastError());
 }
 void attn_bwd(Ctx& ctx, const float* c, const float* alpha, const float* dcv, int64_t lddcv, float* de, float* dq, int B,
               int S, int H) {
   size_t smem = (size_t)(((S + 3) & ~3) + 4 + ATT_WARPS * H) * sizeof(float);
-  attn_bwd_kernel<<<B, 256, smem, ctx.st>>>(c, alpha, dcv, lddcv, de, dq, S, H);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, attn_bwd_kernel, dim3(B), dim3(256), smem, c, alpha, dcv, lddcv, de, dq, S, H);
+  AOCR_CUDA(cudaGetLastError());
 }
 void generator_fwd(Ctx& ctx, const float* a, const float* W, const float* bias, const int32_t* y, float* logp, float* dz,
                    float* rowloss, int64_t R, int H, int V, float inv_bn) {
   AOCR_CHECK(V <= GEN_MAXV && H % 128 == 0 && H <= 128 * ATT_MAXV, "generator kernel: V<=64, H in {128..1024}");
-  generator_kernel<<<(unsigned)R, 128, 0, ctx.st>>>(a, W, bias, y, logp, dz, rowloss, H, V, inv_bn);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, generator_kernel, dim3((unsigned)R), dim3(128), 0, a, W, bias, y, logp, dz, rowloss, H, V, inv_bn);
+  AOCR_CUDA(cudaGetLastError());
 }
 void reduce_sum_double(Ctx& ctx, const float* v, int64_t n, double* out) {
-  reduce_sum_double_kernel<<<1, 1024, 0, ctx.st>>>(v, n, out);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, reduce_sum_double_kernel, dim3(1), dim3(1024), 0, v, n, out);
+  AOCR_CUDA(cudaGetLastError());
 }
 void greedy_select(Ctx& ctx, float* logp, int32_t* tok, double* score, int32_t* labels, int64_t ldl, int t, int B, int V) {
-  greedy_select_kernel<<<cdiv(B, 128), 128, 0, ctx.st>>>(logp, tok, score, labels, ldl, t, B, V);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, greedy_select_kernel, dim3(cdiv(B, 128)), dim3(128), 0, logp, tok, score, labels, ldl, t, B, V);
+  AOCR_CUDA(cudaGetLastError());
 }
 void fill_zero(Ctx& ctx, void* p, size_t bytes) {
   if (bytes) AOCR_CUDA(cudaMemsetAsync(p, 0, bytes, ctx.st));
 }
 void add_vec(Ctx& ctx, float* out, const float* a, const float* b, int64_t n) {
-  add_vec_kernel<<<grid_for(n, 256, ctx.num_sms), 256, 0, ctx.st>>>(out, a, b, n);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, add_vec_kernel, dim3(grid_for(n, 256, ctx.num_sms)), dim3(256), 0, out, a, b, n);
+  AOCR_CUDA(cudaGetLastError());
 }
 void copy_strided(Ctx& ctx, float* dst, int64_t ldd, const float* src, int64_t lds, int rows, int cols) {
-  copy_strided_kernel<<<grid_for((int64_t)rows * cols, 256, ctx.num_sms), 256, 0, ctx.st>>>(dst, ldd, src, lds, rows, cols);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, copy_strided_kernel, dim3(grid_for((int64_t)rows * cols, 256, ctx.num_sms)), dim3(256), 0, dst, ldd, src, lds, rows, cols);
+  AOCR_CUDA(cudaGetLastError());
 }
 void concat_enc_finals(Ctx& ctx, const float* s0, const float* s1, float* dst, int64_t ldd, int B, int He) {
-  concat2_kernel<<<grid_for((int64_t)B * 2 * He, 256, ctx.num_sms), 256, 0, ctx.st>>>(s0, s1, dst, ldd, B, He);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, concat2_kernel, dim3(grid_for((int64_t)B * 2 * He, 256, ctx.num_sms)), dim3(256), 0, s0, s1, dst, ldd, B, He);
+  AOCR_CUDA(cudaGetLastError());
 }
 void du_from_da(Ctx& ctx, const float* da_carry, int64_t ldc, const float* da_gen, const float* a, float* du, int64_t n,
                 int H) {
-  du_from_da_kernel<<<grid_for(n, 256, ctx.num_sms), 256, 0, ctx.st>>>(da_carry, ldc, da_gen, a, du, n, H);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, du_from_da_kernel, dim3(grid_for(n, 256, ctx.num_sms)), dim3(256), 0, da_carry, ldc, da_gen, a, du, n, H);
+  AOCR_CUDA(cudaGetLastError());
 }
 void gather_tokens(Ctx& ctx, const int32_t* tgt_bt, int32_t* out_tb, int B, int T, int Tpad, int32_t padval) {
-  gather_tokens_kernel<<<cdiv((int64_t)B * Tpad, 256), 256, 0, ctx.st>>>(tgt_bt, out_tb, B, T, Tpad, padval);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, gather_tokens_kernel, dim3(cdiv((int64_t)B * Tpad, 256)), dim3(256), 0, tgt_bt, out_tb, B, T, Tpad, padval);
+  AOCR_CUDA(cudaGetLastError());
 }
 void token_segment_sum(Ctx& ctx, const float* dG, const int32_t* y, float* dP, int64_t R, int N, int V) {
   dim3 grid(cdiv(N, 256), V);
-  token_segment_sum_kernel<<<grid, 256, 0, ctx.st>>>(dG, y, dP, R, N);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, token_segment_sum_kernel, dim3(grid), dim3(256), 0, dG, y, dP, R, N);
+  AOCR_CUDA(cudaGetLastError());
 }
 void onehot(Ctx& ctx, const int32_t* y, float* oh, int64_t R, int V) {
-  onehot_kernel<<<grid_for(R * V, 256, ctx.num_sms), 256, 0, ctx.st>>>(y, oh, R, V);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, onehot_kernel, dim3(grid_for(R * V, 256, ctx.num_sms)), dim3(256), 0, y, oh, R, V);
+  AOCR_CUDA(cudaGetLastError());
 }
 void thin_n_gemm(Ctx& ctx, const float* A, int64_t lda, const float* W, int64_t ldw, float* out, int64_t ldo, int M, int K,
                  int E) {
   AOCR_CHECK(E <= 32, "thin_n_gemm: N must be <= 32");
-  thin_n_gemm_kernel<<<M, 256, 0, ctx.st>>>(A, lda, W, ldw, out, ldo, K, E);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, thin_n_gemm_kernel, dim3(M), dim3(256), 0, A, lda, W, ldw, out, ldo, K, E);
+  AOCR_CUDA(cudaGetLastError());
 }
 void sumsq_partial(Ctx& ctx, const float* v, int64_t n, double* partial, int nblk) {
-  sumsq_partial_kernel<<<nblk, 256, 0, ctx.st>>>(v, n, partial);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, sumsq_partial_kernel, dim3(nblk), dim3(256), 0, v, n, partial);
+  AOCR_CUDA(cudaGetLastError());
 }
 void sumsq_final(Ctx& ctx, const double* partial, int nblk, double* out) {
-  sumsq_final_kernel<<<1, 256, 0, ctx.st>>>(partial, nblk, out);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, sumsq_final_kernel, dim3(1), dim3(256), 0, partial, nblk, out);
+  AOCR_CUDA(cudaGetLastError());
 }
 void sgd_apply(Ctx& ctx, float* p, float* g, int64_t n, const double* sumsq, double lr, double clip) {
-  sgd_apply_kernel<<<grid_for(n, 256, ctx.num_sms), 256, 0, ctx.st>>>(p, g, n, sumsq, lr, clip);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, sgd_apply_kernel, dim3(grid_for(n, 256, ctx.num_sms)), dim3(256), 0, p, g, n, sumsq, lr, clip);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 }  // namespace aocr
@@ -624,19 +664,23 @@ void sgd_apply(Ctx& ctx, float* p, float* g, int64_t n, const double* sumsq, dou
 namespace aocr {
 namespace {
 __global__ void scale_vec_kernel(float* v, int64_t n, float s) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) v[e] *= s;
 }
 __global__ void axpy_vec_kernel(float* y, const float* x, int64_t n, float a) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
     y[e] = fmaf(a, x[e], y[e]);
 }
 }  // namespace
 void scale_vec(Ctx& ctx, float* v, int64_t n, float s) {
-  scale_vec_kernel<<<1184, 256, 0, ctx.st>>>(v, n, s);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, scale_vec_kernel, dim3(1184), dim3(256), 0, v, n, s);
+  AOCR_CUDA(cudaGetLastError());
 }
 void axpy_vec(Ctx& ctx, float* y, const float* x, int64_t n, float a) {
-  axpy_vec_kernel<<<1184, 256, 0, ctx.st>>>(y, x, n, a);
-  AOCR_LAUNCH_CHECK(ctx);
+  launch_pdl(ctx, axpy_vec_kernel, dim3(1184), dim3(256), 0, y, x, n, a);
+  AOCR_CUDA(cudaGetLastError());
 }
 }  // namespace aocr
