@@ -108,6 +108,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   AOCR_CHECK(prop.major == 10, "libaocr is built for sm_100a (B200) only");
   ctx_.num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("AOCR_PDL")) ctx_.pdl = atoi(e) != 0;
+  if (const char* e = getenv("AOCR_PHASES")) phases_on_ = atoi(e) != 0;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));
   AOCR_CUDA(cudaEventCreate(&ev1_));
@@ -314,6 +315,28 @@ void Engine::prof_end(int cls, double work) {
   AOCR_CUDA(cudaEventRecord(prof_pool_[prof_used_ * 2 + 1], ctx_.st));
   prof_recs_.push_back({cls, work});
   prof_used_++;
+}
+void Engine::phase_mark(const char* name) {
+  if (!phases_on_) return;
+  cudaEvent_t e;
+  AOCR_CUDA(cudaEventCreate(&e));
+  AOCR_CUDA(cudaEventRecord(e, ctx_.st));
+  phase_marks_.push_back({name, e});
+}
+void Engine::phase_report() {
+  if (!phases_on_ || phase_marks_.size() < 2) return;
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  fprintf(stderr, "[aocr phases]");
+  for (size_t i = 1; i < phase_marks_.size(); i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, phase_marks_[i - 1].second, phase_marks_[i].second);
+    fprintf(stderr, " %s=%.3fms", phase_marks_[i].first.c_str(), ms);
+  }
+  float tot = 0.f;
+  cudaEventElapsedTime(&tot, phase_marks_.front().second, phase_marks_.back().second);
+  fprintf(stderr, " total=%.3fms\n", tot);
+  for (auto& m : phase_marks_) cudaEventDestroy(m.second);
+  phase_marks_.clear();
 }
 void Engine::prof_collect() {
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));

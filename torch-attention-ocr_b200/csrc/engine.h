@@ -111,6 +111,11 @@ class Engine {
  public:
   void prof_collect();
  private:
+  // AOCR_PHASES=1: per-phase device time of a training step (diagnostic, prints to stderr)
+  bool phases_on_ = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> phase_marks_;
+  void phase_mark(const char* name);
+  void phase_report();
   std::vector<cudaEvent_t> prof_pool_;
   std::vector<std::pair<int, double>> prof_recs_;
   size_t prof_used_ = 0;

@@ -293,22 +293,30 @@ void Engine::forward_backward_enqueue() {
   prep_weights();
   gather_tokens(ctx_, tgt_bt, tgt_tb, B, T, T, 1);
   gather_tokens(ctx_, tev_bt, tev_tb, B, T, T, 1);
+  phase_mark("start");
   fill_zero(ctx_, d_grads, (size_t)L.total * sizeof(float));   // model.lua:637-639
   cnn_forward(true);
+  phase_mark("cnn_fwd");
   encoder_forward();
+  phase_mark("enc_fwd");
   decoder_init();
   dec_steps_ = T;
   for (int t = 0; t < T; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
+  phase_mark("dec_fwd");
   taps_["a_all"] = {A_all, (int64_t)T * B * Hd};
   taps_["alpha"] = {ALPHA, (int64_t)T * B * S_};
   decoder_backward();
+  phase_mark("dec_bwd");
   grad_bucket(G_PROJ, G_DEC);      // [proj | decoder] is complete: its all-reduce overlaps the encoder/CNN backward
   encoder_backward();
+  phase_mark("enc_bwd");
   grad_bucket(G_ENC_FW, G_ENC_BW);
   taps_["dsrc"] = {dsrc, (int64_t)S_ * B * 512};
   cnn_backward();
+  phase_mark("cnn_bwd");
   grad_bucket(G_CNN, G_CNN);
   grad_join();
+  phase_report();
   have_grads_ = true;
   last_logp_rows_[0] = T * B;
 }
