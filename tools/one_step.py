@@ -17,3 +17,12 @@ for i in range(n):
 if os.environ.get("STEP_DECODE"):
     h.decode_greedy_staged(sync=True)
     print("decode done", flush=True)
+import time
+h.synchronize()
+for i in range(3):
+    t0 = time.perf_counter()
+    h.train_step_staged(0.1, sync=False)
+    t1 = time.perf_counter()
+    h.synchronize()
+    t2 = time.perf_counter()
+    print(f"host enqueue {1e3*(t1-t0):.3f} ms, enqueue+drain {1e3*(t2-t0):.3f} ms", flush=True)

@@ -101,8 +101,7 @@ int aocr_train_step(aocr_handle* h, const float* images, int b, int W, const int
                     const int32_t* targets_eval, int T, double lr, double* loss_sum) {
   AOCR_API_BEGIN(h)
   h->eng->stage_batch(images, b, W, targets, targets_eval, T);
-  h->eng->forward_backward_enqueue();
-  h->eng->sgd_enqueue(lr, 5.0);
+  h->eng->train_step_enqueue(lr, 5.0);
   double l = h->eng->read_loss();
   if (loss_sum) *loss_sum = l;
   AOCR_API_END(h)
@@ -113,7 +112,7 @@ int aocr_decode_greedy(aocr_handle* h, const float* images, int b, int W, const 
                        double* loss_sum, int32_t* num_correct) {
   AOCR_API_BEGIN(h)
   h->eng->stage_batch(images, b, W, targets, targets_eval, T);
-  h->eng->decode_enqueue();
+  h->eng->decode_step_enqueue();
   h->eng->decode_collect(labels, pred_scores, gold_scores, loss_sum, num_correct);
   AOCR_API_END(h)
 }
@@ -134,8 +133,7 @@ int aocr_stage_batch(aocr_handle* h, const float* images, int b, int W, const in
 }
 int aocr_train_step_staged(aocr_handle* h, double lr, int sync, double* loss_sum) {
   AOCR_API_BEGIN(h)
-  h->eng->forward_backward_enqueue();
-  h->eng->sgd_enqueue(lr, 5.0);
+  h->eng->train_step_enqueue(lr, 5.0);
   if (sync) {
     double l = h->eng->read_loss();
     if (loss_sum) *loss_sum = l;
@@ -144,7 +142,7 @@ int aocr_train_step_staged(aocr_handle* h, double lr, int sync, double* loss_sum
 }
 int aocr_decode_greedy_staged(aocr_handle* h, int sync) {
   AOCR_API_BEGIN(h)
-  h->eng->decode_enqueue();
+  h->eng->decode_step_enqueue();
   if (sync) h->eng->sync();
   AOCR_API_END(h)
 }

@@ -109,6 +109,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   ctx_.num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("AOCR_PDL")) ctx_.pdl = atoi(e) != 0;
   if (const char* e = getenv("AOCR_PHASES")) phases_on_ = atoi(e) != 0;
+  if (const char* e = getenv("AOCR_GRAPHS")) graphs_on_ = atoi(e) != 0;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));
   AOCR_CUDA(cudaEventCreate(&ev1_));
@@ -206,6 +207,7 @@ Engine::~Engine() {
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
+  for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (ctx_.st) cudaStreamDestroy(ctx_.st);
 }
 

@@ -58,6 +58,10 @@ class Engine {
   void get_logprobs(int which, float* out, int64_t n);
   void debug_read(const char* name, float* out, int64_t n);
   void sync() { AOCR_CUDA(cudaStreamSynchronize(ctx_.st)); }
+  // whole-step CUDA graphs: the fixed launch sequence of a (b, W, T, lr) train step / (b, W, T) decode is captured
+  // once (after one eager warm-up that fills every cache) and replayed; AOCR_GRAPHS=0 disables
+  void train_step_enqueue(double lr, double clip);
+  void decode_step_enqueue();
   // data-parallel hook (aocr_set_allreduce): kind 0 = small sum ordered on the engine stream (BN statistics),
   // 1 = gradient bucket that may run concurrently with later kernels, 2 = join all outstanding buckets
   aocr_allreduce_fn ar_fn = nullptr;
@@ -112,6 +116,12 @@ class Engine {
   void prof_collect();
  private:
   // AOCR_PHASES=1: per-phase device time of a training step (diagnostic, prints to stderr)
+  bool graphs_on_ = true;
+  int64_t graph_launches_train_ = 0, graph_launches_decode_ = 0;
+  struct GraphKey { int kind, b, W, T; double lr, clip; bool operator<(const GraphKey& o) const {
+    return std::tie(kind, b, W, T, lr, clip) < std::tie(o.kind, o.b, o.W, o.T, o.lr, o.clip); } };
+  struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; };
+  std::map<GraphKey, GraphEntry> graphs_;
   bool phases_on_ = false;
   std::vector<std::pair<std::string, cudaEvent_t>> phase_marks_;
   void phase_mark(const char* name);

@@ -360,6 +360,82 @@ void Engine::sgd_enqueue(double lr, double clip) {
   mark_weights_dirty();
 }
 
+// ---- whole-step CUDA graphs ------------------------------------------------------------------------------
+// A step is a fixed sequence of ~700 dependent launches whose per-launch latency (4-5 us on this part), not their
+// work, bounds the step at batch 64.  The second time a (shape, lr) key is seen the sequence is stream-captured and
+// instantiated; from then on one cudaGraphLaunch replays it.  Eager first (fills the weight-pack / tensor-map
+// caches: no allocation may happen during capture).  Not used under data parallelism (the exchange hook calls
+// into the host runtime) nor while profiling.
+void Engine::train_step_enqueue(double lr, double clip) {
+  const bool eligible = graphs_on_ && cfg.dp_world <= 1 && !prof_on && !phases_on_;
+  if (!eligible) {
+    forward_backward_enqueue();
+    sgd_enqueue(lr, clip);
+    return;
+  }
+  GraphKey key{0, b_, W_, T_, lr, clip};
+  GraphEntry& e = graphs_[key];
+  if (e.exec == nullptr && e.seen >= 1) {
+    mark_weights_dirty();          // the captured sequence must contain the weight-pack refresh
+    cudaGraph_t graph = nullptr;
+    AOCR_CUDA(cudaStreamBeginCapture(ctx_.st, cudaStreamCaptureModeThreadLocal));
+    try {
+      forward_backward_enqueue();
+      sgd_enqueue(lr, clip);
+    } catch (...) {
+      cudaStreamEndCapture(ctx_.st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    AOCR_CUDA(cudaStreamEndCapture(ctx_.st, &graph));
+    AOCR_CUDA(cudaGraphInstantiate(&e.exec, graph, 0));
+    AOCR_CUDA(cudaGraphDestroy(graph));
+  }
+  e.seen++;
+  if (e.exec) {
+    AOCR_CUDA(cudaGraphLaunch(e.exec, ctx_.st));
+    ctx_.launches += graph_launches_train_;
+    have_grads_ = true;
+    mark_weights_dirty();
+  } else {
+    const int64_t l0 = ctx_.launches;
+    forward_backward_enqueue();
+    sgd_enqueue(lr, clip);
+    graph_launches_train_ = ctx_.launches - l0;
+  }
+}
+
+void Engine::decode_step_enqueue() {
+  const bool eligible = graphs_on_ && !prof_on && !phases_on_;
+  if (!eligible) { decode_enqueue(); return; }
+  GraphKey key{1, b_, W_, T_, 0.0, 0.0};
+  GraphEntry& e = graphs_[key];
+  if (e.exec == nullptr && e.seen >= 1 && !weights_dirty_) {
+    cudaGraph_t graph = nullptr;
+    AOCR_CUDA(cudaStreamBeginCapture(ctx_.st, cudaStreamCaptureModeThreadLocal));
+    try {
+      decode_enqueue();
+    } catch (...) {
+      cudaStreamEndCapture(ctx_.st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    AOCR_CUDA(cudaStreamEndCapture(ctx_.st, &graph));
+    AOCR_CUDA(cudaGraphInstantiate(&e.exec, graph, 0));
+    AOCR_CUDA(cudaGraphDestroy(graph));
+  }
+  e.seen++;
+  if (e.exec && !weights_dirty_) {
+    AOCR_CUDA(cudaGraphLaunch(e.exec, ctx_.st));
+    ctx_.launches += graph_launches_decode_;
+    last_logp_rows_[1] = last_logp_rows_[2] = Tmax * b_;
+  } else {
+    const int64_t l0 = ctx_.launches;
+    decode_enqueue();
+    if (!weights_dirty_) graph_launches_decode_ = ctx_.launches - l0;
+  }
+}
+
 // forward_only branch, beam 1, no trie (model.lua:360-404,446-459,516-536,570-627)
 void Engine::decode_enqueue() {
   AOCR_CHECK(have_batch_, "no batch staged");

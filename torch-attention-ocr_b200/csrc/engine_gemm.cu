@@ -232,6 +232,9 @@ extern "C" int aocr_bench_gemm(int M, int N, int K, int terms, int mn, int split
     else { t.A.rows = M; t.A.kp = kp; t.B.rows = N; t.B.kp = kp; }
     t.M = M; t.N = N; t.K = K; t.C = dC; t.ldc = N; t.terms = terms; t.force_splits = splits;
     t.defer_reduce = true; t.ws = ctx.tc_ws; t.ws_floats = ctx.tc_ws_floats;
+    if (const char* e = getenv("AOCR_TC_DBG")) t.dbg = atoi(e);
+    t.transpose_out = getenv("AOCR_TC_TRANSPOSE") != nullptr;
+    if (t.transpose_out) t.ldc = M;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int i = 0; i < 3; i++) gemm_tc(ctx, t);

@@ -58,6 +58,7 @@ struct TcParams {
   int splits, kb_per;
   float* ws;
   long long part_stride;
+  int dbg;   // bench-only ablations: 1 = no TMA/MMA, 2 = no epilogue stores, 4 = no TMEM alloc wait path
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -185,7 +186,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
   }
-  if (warp == 1) {   // TMEM allocation (whole warp, .sync.aligned)
+  if (warp == 1 && !(p.dbg & 4)) {   // TMEM allocation (whole warp, .sync.aligned)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "n"(C_::kTmemCols)
                  : "memory");
@@ -199,7 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && !(p.dbg & 1)) {
       const uint32_t tx = (uint32_t)(p.terms == 3 ? 2 : 1) * (A_PLANE_BYTES + C_::kBPlane);
       for (int i = 0; i < nkb; i++) {
         const int kb = kb_begin + i;
@@ -257,7 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
     const uint32_t idesc = make_idesc(BN, p.mn);
-    for (int i = 0; i < nkb; i++) {
+    for (int i = 0; i < ((p.dbg & 1) ? 0 : nkb); i++) {
       const int s = i % C_::kStages;
       const uint32_t ph = (uint32_t)(i / C_::kStages) & 1u;
       mbar_wait(full_bar(s), ph);
@@ -288,7 +289,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;                            // TMEM lane quadrant this warp may access
-    mbar_wait(tmem_full_bar, 0);
+    if (!(p.dbg & 1)) mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int ml = q * 32 + lane;                      // row inside the tile
     long long row = (long long)m0 + ml;
@@ -308,12 +309,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t r[16];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if (p.dbg & 4) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = 0;
+      } else {
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
           : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
             "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
       if (!row_ok) continue;
       const int nb = n0 + c0;
       float bias[16], old[16];
@@ -343,14 +349,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             v += old[j];
           }
           float* dst = p.transpose_out ? outp + (long long)n * p.ldc + row : outp + row * p.ldc + n;
-          *dst = v;
+          if (!(p.dbg & 2)) *dst = v;
         }
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 1 && !(p.dbg & 4)) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::kTmemCols) : "memory");
   }
@@ -503,7 +509,7 @@ void launch(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtens
     AOCR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  launch_pdl(ctx, tc_gemm_kernel<BN>, grid, dim3(192), (size_t)Cfg<BN>::kSmemBytes, ah, al, bh, bl, p);
+  launch_pdl(ctx, tc_gemm_kernel<BN>, grid, dim3(192), (p.dbg & 8) ? (size_t)4096 : (size_t)Cfg<BN>::kSmemBytes, ah, al, bh, bl, p);
   AOCR_CUDA(cudaGetLastError());
 }
 
@@ -623,7 +629,7 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   if (splits < 1) splits = 1;
   p.kb_per = (p.num_kb + splits - 1) / splits;
   p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;
-  p.ws = wsbase; p.part_stride = part_stride;
+  p.ws = wsbase; p.part_stride = part_stride; p.dbg = g.dbg;
   if (g.defer_reduce) {   // raw sums only: the consumer kernel adds the partials (and any bias / activation)
     AOCR_CHECK(!g.bias_m && !g.bias_n && g.act == ACT_NONE && !g.accumulate && g.ws, "deferred GEMM takes no epilogue");
     AOCR_CHECK(part_stride <= wscap, "deferred GEMM workspace too small");

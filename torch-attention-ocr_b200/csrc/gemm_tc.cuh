@@ -44,6 +44,7 @@ struct TcGemm {
   int accumulate = 0;
   int terms = 3;                       // 3: hi*hi + hi*lo + lo*hi (fp32-grade) ; 1: hi*hi (plain bf16)
   int force_splits = 0;                // test hook: force a split-K factor
+  int dbg = 0;                         // bench-only ablation bits (see TcParams::dbg)
   // deferred reduction: leave the split-K partial sums in `ws` (ws_floats capacity) for the consumer kernel
   bool defer_reduce = false;
   float* ws = nullptr;
