@@ -172,6 +172,21 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     }
   }
   for (int l = 1; l < 7; l++) wt[l] = alloc<float>((int64_t)kConv[l].cout * kConv[l].cin * kConv[l].k * kConv[l].k);
+  // side lanes (lane 0 = the members above)
+  if (const char* e = getenv("AOCR_LANES")) lanes_on_ = atoi(e) != 0;
+  for (int i = 0; i < 8; i++) AOCR_CUDA(cudaEventCreateWithFlags(&lane_ev_[i], cudaEventDisableTiming));
+  lanes_[0].st = ctx_.st; lanes_[0].tc_ws = ctx_.tc_ws; lanes_[0].scratch[0] = scratch_[0]; lanes_[0].scratch[1] = scratch_[1];
+  lanes_[0].partial = partial; lanes_[0].tmpvec = tmpvec;
+  for (int i = 1; i < 3; i++) {
+    if (!lanes_on_) { lanes_[i] = lanes_[0]; continue; }
+    AOCR_CUDA(cudaStreamCreateWithFlags(&lanes_[i].st, cudaStreamNonBlocking));
+    lanes_[i].partial = alloc<float>((int64_t)256 * 8192);
+    lanes_[i].tmpvec = alloc<float>(8192);
+    if (cfg.gemm_mode != 2) {
+      lanes_[i].tc_ws = alloc<float>(ctx_.tc_ws_floats);
+      if (i == 1) for (int k = 0; k < 2; k++) lanes_[i].scratch[k] = alloc_pack(1, scratch_elems_);
+    }
+  }
 
   xg = alloc<float>(S * B * 8 * He);
   Henc = alloc<float>(2 * (S + 1) * B * He); Cenc = alloc<float>(2 * (S + 1) * B * He);
@@ -202,7 +217,11 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
 
 Engine::~Engine() {
   cudaSetDevice(device_);
+  use_lane(0);
   if (ctx_.st) cudaStreamSynchronize(ctx_.st);
+  for (int i = 1; i < 3; i++)
+    if (lanes_on_ && lanes_[i].st) { cudaStreamSynchronize(lanes_[i].st); cudaStreamDestroy(lanes_[i].st); }
+  for (int i = 0; i < 8; i++) if (lane_ev_[i]) cudaEventDestroy(lane_ev_[i]);
   for (void* p : allocs_) cudaFree(p);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -317,6 +336,28 @@ void Engine::prof_end(int cls, double work) {
   AOCR_CUDA(cudaEventRecord(prof_pool_[prof_used_ * 2 + 1], ctx_.st));
   prof_recs_.push_back({cls, work});
   prof_used_++;
+}
+void Engine::use_lane(int i) {
+  if (i == cur_lane_) return;
+  Lane& o = lanes_[cur_lane_];
+  o.st = ctx_.st; o.tc_ws = ctx_.tc_ws; o.scratch[0] = scratch_[0]; o.scratch[1] = scratch_[1]; o.partial = partial; o.tmpvec = tmpvec;
+  const Lane& n = lanes_[i];
+  ctx_.st = n.st; ctx_.tc_ws = n.tc_ws; scratch_[0] = n.scratch[0]; scratch_[1] = n.scratch[1]; partial = n.partial; tmpvec = n.tmpvec;
+  cur_lane_ = i;
+}
+// lane i starts after everything enqueued so far on lane 0
+void Engine::fork_to(int i) {
+  if (!lanes_on_) return;
+  cudaEvent_t ev = lane_ev_[lane_ev_next_++ % 8];
+  AOCR_CUDA(cudaEventRecord(ev, lanes_[0].st));
+  AOCR_CUDA(cudaStreamWaitEvent(lanes_[i].st, ev, 0));
+}
+// lane 0 continues after everything enqueued so far on lane i
+void Engine::join_from(int i) {
+  if (!lanes_on_) return;
+  cudaEvent_t ev = lane_ev_[lane_ev_next_++ % 8];
+  AOCR_CUDA(cudaEventRecord(ev, lanes_[i].st));
+  AOCR_CUDA(cudaStreamWaitEvent(lanes_[0].st, ev, 0));
 }
 void Engine::phase_mark(const char* name) {
   if (!phases_on_) return;
@@ -553,7 +594,18 @@ void Engine::encoder_backward() {
       }
     }
   }
-  // time-batched parameter and input gradients
+  // d src = dG_fw W_i_fw + dG_bw W_i_bw  (model.lua:675,689): needed next by the CNN backward, stays on lane 0
+  for (int d = 0; d < 2; d++) {
+    Gemm g;
+    g.M = S * B; g.N = 512; g.K = 4 * He;
+    g.A = dGe + d * 4 * He; g.sam = 8 * He; g.sak = 1;
+    g.B = d_params + L.enc_wi[d]; g.sbk = 512; g.sbn = 1;
+    g.C = dsrc; g.ldc = 512; g.accumulate = d;
+    gemm(g);
+  }
+  // time-batched parameter gradients: independent of the CNN backward -> lane 1
+  fork_to(1);
+  use_lane(1);
   for (int d = 0; d < 2; d++) {
     const float* dG = dGe + d * 4 * He;
     Gemm gi;   // dW_i = dG^T src
@@ -578,15 +630,7 @@ void Engine::encoder_backward() {
     AOCR_CUDA(cudaMemcpyAsync(d_grads + L.enc_bh[d], tmpvec + d * 4 * He, (size_t)4 * He * sizeof(float),
                               cudaMemcpyDeviceToDevice, ctx_.st));
   }
-  // d src = dG_fw W_i_fw + dG_bw W_i_bw  (model.lua:675,689)
-  for (int d = 0; d < 2; d++) {
-    Gemm g;
-    g.M = S * B; g.N = 512; g.K = 4 * He;
-    g.A = dGe + d * 4 * He; g.sam = 8 * He; g.sak = 1;
-    g.B = d_params + L.enc_wi[d]; g.sbk = 512; g.sbn = 1;
-    g.C = dsrc; g.ldc = 512; g.accumulate = d;
-    gemm(g);
-  }
+  use_lane(0);
 }
 
 }  // namespace aocr

@@ -116,6 +116,18 @@ class Engine {
   void prof_collect();
  private:
   // AOCR_PHASES=1: per-phase device time of a training step (diagnostic, prints to stderr)
+  // lanes: independent work runs on side streams (encoder backward direction on lane 2; time-batched weight
+  // gradients on lane 1) while the latency-bound per-timestep chain keeps lane 0 busy.  use_lane() swaps the
+  // stream and the stream-private scratch into ctx_/scratch_, so the code that runs on a lane is unchanged.
+  struct Lane { cudaStream_t st = nullptr; float* tc_ws = nullptr; Pack scratch[2]; float* partial = nullptr; float* tmpvec = nullptr; };
+  Lane lanes_[3];
+  int cur_lane_ = 0;
+  bool lanes_on_ = true;
+  cudaEvent_t lane_ev_[8] = {};
+  int lane_ev_next_ = 0;
+  void use_lane(int i);
+  void fork_to(int i);
+  void join_from(int i);
   bool graphs_on_ = true;
   int64_t graph_launches_train_ = 0, graph_launches_decode_ = 0;
   struct GraphKey { int kind, b, W, T; double lr, clip; bool operator<(const GraphKey& o) const {

@@ -205,6 +205,10 @@ void Engine::decoder_backward() {
   col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
 
   if (cfg.gemm_mode != 2) decoder_backward_steps_tc(); else decoder_backward_steps_simt();
+  // the time-batched parameter gradients below depend only on the saved per-step tensors: lane 1, concurrently
+  // with D_ctx + the encoder/CNN backward that continue on lane 0
+  fork_to(1);
+  use_lane(1);
   // ---- time-batched parameter gradients (weights are tied across t: clone_many_times, model_utils.lua:3-50)
   auto wgrad = [&](const float* dY, int M, const float* X, int64_t ldx, int N, float* dW, int64_t ldw) {
     Gemm w;
@@ -246,6 +250,7 @@ void Engine::decoder_backward() {
   g.B = d_params + L.emb; g.sbk = E; g.sbn = 1;
   g.C = d_grads + L.l1_wi; g.ldc = in1;
   gemm(g);
+  use_lane(0);
   // D_ctx[b] = sum_t alpha_t[b]^T dcv_t[b] + de_t[b]^T q_t[b]   (replaces the per-step RMW of model.lua:652-653)
   g = Gemm();
   g.M = S; g.N = Hd; g.K = T; g.batch = B;
@@ -307,13 +312,17 @@ void Engine::forward_backward_enqueue() {
   taps_["alpha"] = {ALPHA, (int64_t)T * B * S_};
   decoder_backward();
   phase_mark("dec_bwd");
-  grad_bucket(G_PROJ, G_DEC);      // [proj | decoder] is complete: its all-reduce overlaps the encoder/CNN backward
   encoder_backward();
   phase_mark("enc_bwd");
-  grad_bucket(G_ENC_FW, G_ENC_BW);
   taps_["dsrc"] = {dsrc, (int64_t)S_ * B * 512};
+  if (cfg.dp_world > 1) {
+    join_from(1);                  // decoder weight gradients (lane 1) are complete
+    grad_bucket(G_PROJ, G_DEC);    // [proj | decoder] all-reduce overlaps the CNN backward
+  }
   cnn_backward();
   phase_mark("cnn_bwd");
+  join_from(1);                    // encoder (and decoder) weight gradients
+  grad_bucket(G_ENC_FW, G_ENC_BW);
   grad_bucket(G_CNN, G_CNN);
   grad_join();
   phase_report();

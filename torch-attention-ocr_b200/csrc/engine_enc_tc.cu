@@ -33,10 +33,12 @@ void Engine::encoder_forward_steps_tc() {
   const size_t slot_bytes = (size_t)B * He * sizeof(__nv_bfloat16);
   fill_zero(ctx_, HencP[0].hi, slot_bytes); fill_zero(ctx_, HencP[0].lo, slot_bytes);
   fill_zero(ctx_, HencP[1].hi + (int64_t)S * B * He, slot_bytes); fill_zero(ctx_, HencP[1].lo + (int64_t)S * B * He, slot_bytes);
+  // the two directions are independent chains: forward direction on lane 0, backward direction on lane 2
   prof_begin(2);
-  for (int i = 0; i < S; i++) {
-    EncCellFwdTc c;
-    for (int d = 0; d < 2; d++) {
+  fork_to(2);
+  for (int d = 0; d < 2; d++) {
+    use_lane(d == 0 ? 0 : 2);
+    for (int i = 0; i < S; i++) {
       const int t = d == 0 ? i : S - 1 - i;
       const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
       TcGemm g;
@@ -44,12 +46,16 @@ void Engine::encoder_forward_steps_tc() {
       g.M = 4 * He; g.N = B; g.K = He; g.ldc = 4 * He; g.transpose_out = true;
       g.terms = terms; g.defer_reduce = true; g.ws = dec_ws[d]; g.ws_floats = dec_ws_floats;
       TcOut o = gemm_tc(ctx_, g);
+      EncCellFwdTc c;
       c.G[d].p = o.base; c.G[d].nz = o.nz; c.G[d].stride = o.stride; c.G[d].ld = 4 * He;
       c.hp[d] = out_of(HencP[d], (int64_t)out_slot * B);
+      c.xg = xg; c.H = Henc; c.Cst = Cenc; c.acts = acts_enc; c.ctx = ctx; c.B = B; c.S = S; c.He = He; c.step = i;
+      c.d_only = d;
+      enc_cell_fwd_tc(ctx_, c);
     }
-    c.xg = xg; c.H = Henc; c.Cst = Cenc; c.acts = acts_enc; c.ctx = ctx; c.B = B; c.S = S; c.He = He; c.step = i;
-    enc_cell_fwd_tc(ctx_, c);
   }
+  use_lane(0);
+  join_from(2);
   prof_end(2, 2.0 * 2 * S * (double)B * He * 4 * He);
 }
 
@@ -59,24 +65,26 @@ void Engine::encoder_backward_steps_tc() {
   const int64_t slot = (int64_t)B * He;
   PartIn dh[2];
   for (int d = 0; d < 2; d++) { dh[d].p = enc_dh + d * slot; dh[d].nz = 1; dh[d].stride = 0; dh[d].ld = He; }   // decoder seeds
-  for (int i = 0; i < S; i++) {
-    EncCellBwdTc c;
-    c.dh[0] = dh[0]; c.dh[1] = dh[1];
-    c.Cst = Cenc; c.acts = acts_enc; c.Dctx = Dctx; c.dc = enc_dc; c.dG = dGe;
-    c.dgp[0] = out_of(dGeP[0], 0); c.dgp[1] = out_of(dGeP[1], 0);
-    c.B = B; c.S = S; c.He = He; c.step = i;
-    enc_cell_bwd_tc(ctx_, c);
-    for (int d = 0; d < 2; d++) {   // dh_prev = dG_t W_h : rows of W_h^T on the M side, K = 4He
-      TcGemm g;
+  fork_to(2);
+  for (int d = 0; d < 2; d++) {
+    use_lane(d == 0 ? 0 : 2);
+    for (int i = 0; i < S; i++) {
+      EncCellBwdTc c;
+      c.dh[d] = dh[d];
+      c.Cst = Cenc; c.acts = acts_enc; c.Dctx = Dctx; c.dc = enc_dc; c.dG = dGe;
+      c.dgp[d] = out_of(dGeP[d], 0);
+      c.B = B; c.S = S; c.He = He; c.step = i; c.d_only = d;
+      enc_cell_bwd_tc(ctx_, c);
+      TcGemm g;                      // dh_prev = dG_t W_h : rows of W_h^T on the M side, K = 4He
       g.A = WhTp[d]; g.B = dGeP[d];
       g.M = He; g.N = B; g.K = 4 * He; g.ldc = He; g.transpose_out = true;
       g.terms = terms; g.defer_reduce = true; g.ws = dec_ws[2 + d]; g.ws_floats = dec_ws_floats;
-      prof_begin(0);
       TcOut o = gemm_tc(ctx_, g);
-      prof_end(0, 2.0 * He * (double)B * 4 * He);
       dh[d].p = o.base; dh[d].nz = o.nz; dh[d].stride = o.stride; dh[d].ld = He;
     }
   }
+  use_lane(0);
+  join_from(2);
 }
 
 }  // namespace aocr

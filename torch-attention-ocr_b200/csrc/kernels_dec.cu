@@ -298,11 +298,11 @@ __global__ void __launch_bounds__(256) enc_cell_fwd_tc_kernel(EncCellFwdTc p) {
   pdl_launch_dependents();
   pdl_wait();
   const int He = p.He, B = p.B, S = p.S;
-  const int64_t total = (int64_t)2 * B * He;
+  const int64_t total = (int64_t)(p.d_only < 0 ? 2 : 1) * B * He;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int unit = (int)(e % He);
     const int64_t b = (e / He) % B;
-    const int d = (int)(e / ((int64_t)He * B));
+    const int d = p.d_only < 0 ? (int)(e / ((int64_t)He * B)) : p.d_only;
     const int t = d == 0 ? p.step : S - 1 - p.step;
     const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
     const float* xg = p.xg + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
@@ -327,11 +327,11 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_tc_kernel(EncCellBwdTc p) {
   pdl_launch_dependents();
   pdl_wait();
   const int He = p.He, B = p.B, S = p.S;
-  const int64_t total = (int64_t)2 * B * He;
+  const int64_t total = (int64_t)(p.d_only < 0 ? 2 : 1) * B * He;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int unit = (int)(e % He);
     const int64_t b = (e / He) % B;
-    const int d = (int)(e / ((int64_t)He * B));
+    const int d = p.d_only < 0 ? (int)(e / ((int64_t)He * B)) : p.d_only;
     const int t = d == 0 ? S - 1 - p.step : p.step;
     const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
     const float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_tc_kernel(EncCellBwdTc p) {
     const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
     const float tc = tanhf(p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit]);
     const float dh = part_load(p.dh[d], b, unit) + p.Dctx[((int64_t)b * S + t) * (2 * He) + d * He + unit];
-    const float dc = p.dc[e] + dh * o_ * (1.f - tc * tc);
+    const int64_t ce = ((int64_t)d * B + b) * He + unit;
+    const float dc = p.dc[ce] + dh * o_ * (1.f - tc * tc);
     const float d0 = dc * g_ * i_ * (1.f - i_);
     const float d1 = dc * cp * f_ * (1.f - f_);
     const float d2 = dh * tc * o_ * (1.f - o_);
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_tc_kernel(EncCellBwdTc p) {
     pack_store(p.dgp[d], b, He + unit, d1);
     pack_store(p.dgp[d], b, 2 * He + unit, d2);
     pack_store(p.dgp[d], b, 3 * He + unit, d3);
-    p.dc[e] = dc * f_;
+    p.dc[ce] = dc * f_;
   }
 }
 
@@ -373,11 +374,11 @@ void part_to_dense(Ctx& ctx, const PartIn& in, float* dst, int64_t ld, int B, in
 }
 
 void enc_cell_fwd_tc(Ctx& ctx, const EncCellFwdTc& p) {
-  launch_pdl(ctx, enc_cell_fwd_tc_kernel, dim3(grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
+  launch_pdl(ctx, enc_cell_fwd_tc_kernel, dim3(grid_for((int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
   AOCR_CUDA(cudaGetLastError());
 }
 void enc_cell_bwd_tc(Ctx& ctx, const EncCellBwdTc& p) {
-  launch_pdl(ctx, enc_cell_bwd_tc_kernel, dim3(grid_for((int64_t)2 * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
+  launch_pdl(ctx, enc_cell_bwd_tc_kernel, dim3(grid_for((int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
   AOCR_CUDA(cudaGetLastError());
 }
 void cell_fwd_tc(Ctx& ctx, const CellFwdTc& p) {

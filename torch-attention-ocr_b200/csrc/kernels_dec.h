@@ -55,6 +55,7 @@ struct EncCellFwdTc {
   float* H; float* Cst; float* acts; float* ctx;     // layouts of kernels.h:EncStep
   PackOut hp[2];        // h_t as bf16 planes = next step's GEMM operand, per direction (row 0 = batch row 0)
   int B, S, He, step;
+  int d_only = -1;      // -1: both directions in one launch; 0/1: that direction only (directions on separate streams)
 };
 void enc_cell_fwd_tc(Ctx&, const EncCellFwdTc&);
 struct EncCellBwdTc {
@@ -64,6 +65,7 @@ struct EncCellBwdTc {
   float* dG;            // (S*B, 8He)
   PackOut dgp[2];       // d gates of this step as bf16 planes (B, 4He) per direction
   int B, S, He, step;
+  int d_only = -1;
 };
 void enc_cell_bwd_tc(Ctx&, const EncCellBwdTc&);
 }  // namespace aocr
