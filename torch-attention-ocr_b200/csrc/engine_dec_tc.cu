@@ -102,11 +102,12 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   Pack h2p = sub_rows(CATp, r0, B);
   h2p.hi += Hd; h2p.lo += Hd;
   TcOut qo = run(Wap, Hd, h2p, Hd, 2);
+  AttnFwdTc af;
+  af.ctx = ctx; af.q = part_in(qo, Hd); af.alpha = ALPHA + (int64_t)t * B * S; af.cv = cat; af.ldcv = 2 * Hd;
+  af.cvp = pack_out(CATp, r0, 0); af.q_out = Q + (int64_t)t * B * Hd; af.B = B; af.S = S; af.H = Hd;
   prof_begin(1);
-  attn_fwd_tc(ctx_, ctx, part_in(qo, Hd), ALPHA + (int64_t)t * B * S, cat, 2 * Hd, pack_out(CATp, r0, 0), B, S, Hd);
+  attn_fwd_tc(ctx_, af);
   prof_end(1, (double)B * S * Hd * 4 + (double)B * (2.0 * Hd + S) * 4);
-  // q itself is needed by the backward (D_ctx product): materialise it once per step
-  part_to_dense(ctx_, part_in(qo, Hd), Q + (int64_t)t * B * Hd, Hd, B, Hd);
   // ---- a_t = tanh(W_c [cv ; h2])
   TcOut uo = run(Wcp, Hd, sub_rows(CATp, r0, B), 2 * Hd, 3);
   DecOutTc d;
@@ -143,9 +144,12 @@ void Engine::decoder_backward_steps_tc() {
     du_tc(ctx_, du);
     // d[cv ; h2] = du W_c
     TcOut dcat = run(WcTp, 2 * Hd, dUp, Hd, 0);
+    AttnBwdTc ab;
+    ab.ctx = ctx; ab.alpha = ALPHA + (int64_t)t * B * S; ab.dcv = part_in(dcat, 2 * Hd, 0);
+    ab.dcv_out = dCAT + (int64_t)t * B * 2 * Hd; ab.ld_dcv_out = 2 * Hd; ab.de = DE + (int64_t)t * B * S;
+    ab.dq = dQ + (int64_t)t * B * Hd; ab.dqp = pack_out(dQp, 0, 0); ab.B = B; ab.S = S; ab.H = Hd;
     prof_begin(1);
-    attn_bwd_tc(ctx_, ctx, ALPHA + (int64_t)t * B * S, part_in(dcat, 2 * Hd, 0), dCAT + (int64_t)t * B * 2 * Hd, 2 * Hd,
-                DE + (int64_t)t * B * S, dQ + (int64_t)t * B * Hd, pack_out(dQp, 0, 0), B, S, Hd);
+    attn_bwd_tc(ctx_, ab);
     prof_end(1, 2.0 * B * S * Hd * 4);
     // dh2 += dq W_a
     TcOut dh2q = run(WaTp, Hd, dQp, Hd, 1);

@@ -2,51 +2,11 @@
 // tcgen05 GEMMs: each one CONSUMES the split-K partial sums of the GEMM before it (summing them in fixed order,
 // so no separate reduction pass and a deterministic result) and PRODUCES the next GEMM's operand directly as
 // bf16 (hi, lo) planes next to the fp32 copy kept for backward.  Math: src/model/LSTM.lua:79-105,124-162.
-#include "kernels_dec.h"
+#include "dec_bodies.cuh"
 
 namespace aocr {
 
 namespace {
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float part_load(const PartIn& a, int64_t b, int64_t j) {
-  const float* p = a.p + b * a.ld + j;
-  float s = 0.f;
-  for (int z = 0; z < a.nz; z++) s += p[(int64_t)z * a.stride];
-  return s;
-}
-__device__ __forceinline__ float4 part_load4(const PartIn& a, int64_t b, int64_t j) {
-  const float* p = a.p + b * a.ld + j;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < a.nz; z++) {
-    float4 t = *reinterpret_cast<const float4*>(p + (int64_t)z * a.stride);
-    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-  }
-  return s;
-}
-__device__ __forceinline__ void pack_store(const PackOut& o, int64_t b, int64_t j, float v) {
-  if (!o.hi) return;
-  __nv_bfloat16 h = __float2bfloat16_rn(v);
-  o.hi[b * o.ld + j] = h;
-  o.lo[b * o.ld + j] = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-__device__ __forceinline__ void pack_store4(const PackOut& o, int64_t b, int64_t j, float4 v) {
-  if (!o.hi) return;
-  __nv_bfloat16 h[4], l[4];
-  const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    h[i] = __float2bfloat16_rn(x[i]);
-    l[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h[i]));
-  }
-  *reinterpret_cast<uint2*>(o.hi + b * o.ld + j) = *reinterpret_cast<uint2*>(h);
-  *reinterpret_cast<uint2*>(o.lo + b * o.ld + j) = *reinterpret_cast<uint2*>(l);
-}
 
 inline int grid_for(int64_t total, int threads, int num_sms) {
   int64_t g = (total + threads - 1) / threads;
@@ -54,316 +14,36 @@ inline int grid_for(int64_t total, int threads, int num_sms) {
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
-__global__ void __launch_bounds__(256) cell_fwd_tc_kernel(CellFwdTc p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int H = p.H;
-  const int64_t total = (int64_t)p.B * H;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int u = (int)(e % H);
-    const int64_t b = e / H;
-    const float* ar = p.addrows + (p.rowsel ? (int64_t)(p.rowsel[b] - 1) * p.addld : 0) + u;
-    const float i_ = sigmoidf_(part_load(p.G, b, u) + ar[0]);
-    const float f_ = sigmoidf_(part_load(p.G, b, H + u) + ar[H]);
-    const float o_ = sigmoidf_(part_load(p.G, b, 2 * H + u) + ar[2 * H]);
-    const float g_ = tanhf(part_load(p.G, b, 3 * H + u) + ar[3 * H]);
-    const float c = f_ * p.c_prev[e] + i_ * g_;
-    const float h = o_ * tanhf(c);
-    p.c_new[e] = c;
-    float* a = p.acts + b * 4 * H + u;
-    a[0] = i_; a[H] = f_; a[2 * H] = o_; a[3 * H] = g_;
-    p.h_out0[b * p.ld0 + u] = h;
-    if (p.h_out1) p.h_out1[b * p.ld1 + u] = h;
-    pack_store(p.pk0, b, u, h);
-    pack_store(p.pk1, b, u, h);
+#define AOCR_WRAP(NAME, PTYPE)                                                     \
+  __global__ void __launch_bounds__(256) NAME##_kernel(PTYPE p) {                  \
+    pdl_launch_dependents();                                                       \
+    pdl_wait();                                                                    \
+    decb::NAME##_body(p, (int)blockIdx.x, (int)gridDim.x, nullptr);                \
   }
-}
+AOCR_WRAP(cell_fwd_tc, CellFwdTc)
+AOCR_WRAP(dec_out_tc, DecOutTc)
+AOCR_WRAP(du_tc, DuTc)
+AOCR_WRAP(cell_bwd_tc, CellBwdTc)
+AOCR_WRAP(enc_cell_fwd_tc, EncCellFwdTc)
+AOCR_WRAP(enc_cell_bwd_tc, EncCellBwdTc)
 
-// a = tanh(u): the decoder output / next step's input feed
-__global__ void __launch_bounds__(256) dec_out_tc_kernel(DecOutTc p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int H = p.H;
-  const int64_t total = (int64_t)p.B * H;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int u = (int)(e % H);
-    const int64_t b = e / H;
-    const float a = tanhf(part_load(p.U, b, u));
-    p.a_out[e] = a;
-    if (p.x_next) p.x_next[b * p.ld_next + u] = a;
-    pack_store(p.pk_next, b, u, a);
-  }
-}
-
-// du = (da_carry + da_gen) * (1 - a^2)
-__global__ void __launch_bounds__(256) du_tc_kernel(DuTc p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int H = p.H;
-  const int64_t total = (int64_t)p.B * H;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int u = (int)(e % H);
-    const int64_t b = e / H;
-    float g = p.da_gen[e];
-    if (p.da_carry.p) g += part_load(p.da_carry, b, u);
-    const float av = p.a[e];
-    const float d = g * (1.f - av * av);
-    p.du[e] = d;
-    pack_store(p.pk, b, u, d);
-  }
-}
-
-__global__ void __launch_bounds__(256) cell_bwd_tc_kernel(CellBwdTc p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int H = p.H;
-  const int64_t total = (int64_t)p.B * H;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int u = (int)(e % H);
-    const int64_t b = e / H;
-    float dh = 0.f;
-    if (p.dh_a.p) dh += part_load(p.dh_a, b, u);
-    if (p.dh_b.p) dh += part_load(p.dh_b, b, u);
-    if (p.dh_c.p) dh += part_load(p.dh_c, b, u);
-    const float* a = p.acts + b * 4 * H + u;
-    const float i_ = a[0], f_ = a[H], o_ = a[2 * H], g_ = a[3 * H];
-    const float tc = tanhf(p.c_new[e]);
-    const float dc = p.dc[e] + dh * o_ * (1.f - tc * tc);
-    const float d0 = dc * g_ * i_ * (1.f - i_);
-    const float d1 = dc * p.c_prev[e] * f_ * (1.f - f_);
-    const float d2 = dh * tc * o_ * (1.f - o_);
-    const float d3 = dc * i_ * (1.f - g_ * g_);
-    float* dg = p.dG + b * 4 * H + u;
-    dg[0] = d0; dg[H] = d1; dg[2 * H] = d2; dg[3 * H] = d3;
-    pack_store(p.pk, b, u, d0);
-    pack_store(p.pk, b, H + u, d1);
-    pack_store(p.pk, b, 2 * H + u, d2);
-    pack_store(p.pk, b, 3 * H + u, d3);
-    p.dc[e] = dc * f_;
-  }
-}
-
-// ------------------------------------------------------------------ attention (see kernels_rnn.cu for the layout notes)
-constexpr int ATT_WARPS = 8;
-constexpr int ATT_MAXV = 8;
-
-__global__ void __launch_bounds__(256) attn_fwd_tc_kernel(const float* __restrict__ ctx, PartIn q,
-                                                          float* __restrict__ alpha, float* __restrict__ cv, int64_t ldcv,
-                                                          PackOut cvp, int S, int H) {
-  pdl_launch_dependents();
-  pdl_wait();
+__global__ void __launch_bounds__(256) attn_fwd_tc_kernel(AttnFwdTc p) {
   extern __shared__ float sm[];
-  float* es = sm;
-  float* wm = es + ((S + 3) & ~3);
-  float* wl = wm + ATT_WARPS;
-  float* accs = wl + ATT_WARPS;
-  const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int nv = H / 128;
-  const float* cb = ctx + (int64_t)b * S * H;
-  float4 qv[ATT_MAXV], acc[ATT_MAXV];
-#pragma unroll
-  for (int i = 0; i < ATT_MAXV; i++) {
-    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    qv[i] = (i < nv) ? part_load4(q, b, lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float m = -INFINITY, l = 0.f;
-  for (int s = warp; s < S; s += ATT_WARPS) {
-    float4 row[ATT_MAXV];
-    float dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++) {
-      if (i < nv) {
-        row[i] = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
-        dot += row[i].x * qv[i].x + row[i].y * qv[i].y + row[i].z * qv[i].z + row[i].w * qv[i].w;
-      }
-    }
-    dot = warp_sum(dot);
-    if (lane == 0) es[s] = dot;
-    const float mn = fmaxf(m, dot);
-    const float sc = expf(m - mn);
-    const float pe = expf(dot - mn);
-    l = l * sc + pe;
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++) {
-      if (i < nv) {
-        acc[i].x = acc[i].x * sc + pe * row[i].x;
-        acc[i].y = acc[i].y * sc + pe * row[i].y;
-        acc[i].z = acc[i].z * sc + pe * row[i].z;
-        acc[i].w = acc[i].w * sc + pe * row[i].w;
-      }
-    }
-    m = mn;
-  }
-  if (lane == 0) { wm[warp] = m; wl[warp] = l; }
-  __syncthreads();
-  float M = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < ATT_WARPS; w++) M = fmaxf(M, wm[w]);
-  float L = 0.f;
-#pragma unroll
-  for (int w = 0; w < ATT_WARPS; w++) L += (wm[w] == -INFINITY) ? 0.f : wl[w] * expf(wm[w] - M);
-  const float myscale = (m == -INFINITY) ? 0.f : expf(m - M) / L;
-#pragma unroll
-  for (int i = 0; i < ATT_MAXV; i++) {
-    if (i < nv) {
-      float4 v = acc[i];
-      v.x *= myscale; v.y *= myscale; v.z *= myscale; v.w *= myscale;
-      *reinterpret_cast<float4*>(accs + warp * H + lane * 4 + 128 * i) = v;
-    }
-  }
-  __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < ATT_WARPS; w++) s += accs[w * H + h];
-    cv[(int64_t)b * ldcv + h] = s;
-    pack_store(cvp, b, h, s);
-  }
-  for (int s = threadIdx.x; s < S; s += blockDim.x) alpha[(int64_t)b * S + s] = expf(es[s] - M) / L;
-}
-
-__global__ void __launch_bounds__(256) attn_bwd_tc_kernel(const float* __restrict__ ctx, const float* __restrict__ alpha,
-                                                          PartIn dcv, float* __restrict__ dcv_out, int64_t ld_dcv_out,
-                                                          float* __restrict__ de, float* __restrict__ dq, PackOut dqp,
-                                                          int S, int H) {
   pdl_launch_dependents();
   pdl_wait();
+  decb::attn_fwd_tc_body(p.ctx, p.q, p.alpha, p.cv, p.ldcv, p.cvp, p.q_out, p.S, p.H, (int)blockIdx.x, (int)gridDim.x, sm);
+}
+__global__ void __launch_bounds__(256) attn_bwd_tc_kernel(AttnBwdTc p) {
   extern __shared__ float sm[];
-  float* das = sm;
-  float* red = das + ((S + 3) & ~3);
-  float* accs = red + 4;
-  const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int nv = H / 128;
-  const float* cb = ctx + (int64_t)b * S * H;
-  float4 gv[ATT_MAXV];
-#pragma unroll
-  for (int i = 0; i < ATT_MAXV; i++)
-    gv[i] = (i < nv) ? part_load4(dcv, b, lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (warp == 0) {   // keep the summed d(context vector) for the time-batched D_ctx product
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++)
-      if (i < nv) *reinterpret_cast<float4*>(dcv_out + (int64_t)b * ld_dcv_out + lane * 4 + 128 * i) = gv[i];
-  }
-  for (int s = warp; s < S; s += ATT_WARPS) {
-    float dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++) {
-      if (i < nv) {
-        float4 r = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
-        dot += r.x * gv[i].x + r.y * gv[i].y + r.z * gv[i].z + r.w * gv[i].w;
-      }
-    }
-    dot = warp_sum(dot);
-    if (lane == 0) das[s] = dot;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    float s_ = 0.f;
-    for (int s = lane; s < S; s += 32) s_ += alpha[(int64_t)b * S + s] * das[s];
-    s_ = warp_sum(s_);
-    if (lane == 0) red[0] = s_;
-  }
-  __syncthreads();
-  const float tot = red[0];
-  for (int s = threadIdx.x; s < S; s += blockDim.x) de[(int64_t)b * S + s] = alpha[(int64_t)b * S + s] * (das[s] - tot);
-  float4 acc[ATT_MAXV];
-#pragma unroll
-  for (int i = 0; i < ATT_MAXV; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = warp; s < S; s += ATT_WARPS) {
-    const float w = alpha[(int64_t)b * S + s] * (das[s] - tot);
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++) {
-      if (i < nv) {
-        float4 r = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
-        acc[i].x = fmaf(w, r.x, acc[i].x); acc[i].y = fmaf(w, r.y, acc[i].y);
-        acc[i].z = fmaf(w, r.z, acc[i].z); acc[i].w = fmaf(w, r.w, acc[i].w);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < ATT_MAXV; i++)
-    if (i < nv) *reinterpret_cast<float4*>(accs + warp * H + lane * 4 + 128 * i) = acc[i];
-  __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < ATT_WARPS; w++) s += accs[w * H + h];
-    dq[(int64_t)b * H + h] = s;
-    pack_store(dqp, b, h, s);
-  }
-}
-
-// encoder cell, both directions (grid-stride over dir x batch x unit); slot convention of engine.cu
-__global__ void __launch_bounds__(256) enc_cell_fwd_tc_kernel(EncCellFwdTc p) {
   pdl_launch_dependents();
   pdl_wait();
-  const int He = p.He, B = p.B, S = p.S;
-  const int64_t total = (int64_t)(p.d_only < 0 ? 2 : 1) * B * He;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int unit = (int)(e % He);
-    const int64_t b = (e / He) % B;
-    const int d = p.d_only < 0 ? (int)(e / ((int64_t)He * B)) : p.d_only;
-    const int t = d == 0 ? p.step : S - 1 - p.step;
-    const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
-    const float* xg = p.xg + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
-    const PartIn& G = p.G[d];
-    const float i_ = sigmoidf_(part_load(G, b, unit) + xg[0]);
-    const float f_ = sigmoidf_(part_load(G, b, He + unit) + xg[He]);
-    const float o_ = sigmoidf_(part_load(G, b, 2 * He + unit) + xg[2 * He]);
-    const float g_ = tanhf(part_load(G, b, 3 * He + unit) + xg[3 * He]);
-    const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
-    const float c = f_ * cp + i_ * g_;
-    const float h = o_ * tanhf(c);
-    p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit] = c;
-    p.H[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit] = h;
-    float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
-    a[0] = i_; a[He] = f_; a[2 * He] = o_; a[3 * He] = g_;
-    p.ctx[((int64_t)b * S + t) * (2 * He) + d * He + unit] = h;
-    pack_store(p.hp[d], b, unit, h);
-  }
+  decb::attn_bwd_tc_body(p.ctx, p.alpha, p.dcv, p.dcv_out, p.ld_dcv_out, p.de, p.dq, p.dqp, p.S, p.H, (int)blockIdx.x,
+                         (int)gridDim.x, sm);
 }
-
-__global__ void __launch_bounds__(256) enc_cell_bwd_tc_kernel(EncCellBwdTc p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int He = p.He, B = p.B, S = p.S;
-  const int64_t total = (int64_t)(p.d_only < 0 ? 2 : 1) * B * He;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int unit = (int)(e % He);
-    const int64_t b = (e / He) % B;
-    const int d = p.d_only < 0 ? (int)(e / ((int64_t)He * B)) : p.d_only;
-    const int t = d == 0 ? S - 1 - p.step : p.step;
-    const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
-    const float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
-    const float i_ = a[0], f_ = a[He], o_ = a[2 * He], g_ = a[3 * He];
-    const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
-    const float tc = tanhf(p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit]);
-    const float dh = part_load(p.dh[d], b, unit) + p.Dctx[((int64_t)b * S + t) * (2 * He) + d * He + unit];
-    const int64_t ce = ((int64_t)d * B + b) * He + unit;
-    const float dc = p.dc[ce] + dh * o_ * (1.f - tc * tc);
-    const float d0 = dc * g_ * i_ * (1.f - i_);
-    const float d1 = dc * cp * f_ * (1.f - f_);
-    const float d2 = dh * tc * o_ * (1.f - o_);
-    const float d3 = dc * i_ * (1.f - g_ * g_);
-    float* dg = p.dG + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
-    dg[0] = d0; dg[He] = d1; dg[2 * He] = d2; dg[3 * He] = d3;
-    pack_store(p.dgp[d], b, unit, d0);
-    pack_store(p.dgp[d], b, He + unit, d1);
-    pack_store(p.dgp[d], b, 2 * He + unit, d2);
-    pack_store(p.dgp[d], b, 3 * He + unit, d3);
-    p.dc[ce] = dc * f_;
-  }
-}
-
 __global__ void part_to_dense_kernel(PartIn in, float* dst, int64_t ld, int B, int cols) {
   pdl_launch_dependents();
   pdl_wait();
-  const int64_t total = (int64_t)B * cols;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(e % cols);
-    const int64_t b = e / cols;
-    dst[b * ld + j] = part_load(in, b, j);
-  }
+  decb::part_to_dense_body(in, dst, ld, B, cols, (int)blockIdx.x, (int)gridDim.x, nullptr);
 }
 
 }  // namespace
@@ -372,42 +52,25 @@ void part_to_dense(Ctx& ctx, const PartIn& in, float* dst, int64_t ld, int B, in
   launch_pdl(ctx, part_to_dense_kernel, dim3(grid_for((int64_t)B * cols, 256, ctx.num_sms)), dim3(256), 0, in, dst, ld, B, cols);
   AOCR_CUDA(cudaGetLastError());
 }
+#define AOCR_LAUNCH_EW(NAME, PTYPE, TOTAL)                                                                   \
+  void NAME(Ctx& ctx, const PTYPE& p) {                                                                      \
+    launch_pdl(ctx, NAME##_kernel, dim3(grid_for((TOTAL), 256, ctx.num_sms)), dim3(256), 0, p);              \
+    AOCR_CUDA(cudaGetLastError());                                                                           \
+  }
+AOCR_LAUNCH_EW(cell_fwd_tc, CellFwdTc, (int64_t)p.B * p.H)
+AOCR_LAUNCH_EW(dec_out_tc, DecOutTc, (int64_t)p.B * p.H)
+AOCR_LAUNCH_EW(du_tc, DuTc, (int64_t)p.B * p.H)
+AOCR_LAUNCH_EW(cell_bwd_tc, CellBwdTc, (int64_t)p.B * p.H)
+AOCR_LAUNCH_EW(enc_cell_fwd_tc, EncCellFwdTc, (int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He)
+AOCR_LAUNCH_EW(enc_cell_bwd_tc, EncCellBwdTc, (int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He)
 
-void enc_cell_fwd_tc(Ctx& ctx, const EncCellFwdTc& p) {
-  launch_pdl(ctx, enc_cell_fwd_tc_kernel, dim3(grid_for((int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
+void attn_fwd_tc(Ctx& ctx, const AttnFwdTc& p) {
+  AOCR_CHECK(p.H % 128 == 0 && p.H <= 1024, "attention kernel needs decoder hidden size in {128,...,1024}");
+  launch_pdl(ctx, attn_fwd_tc_kernel, dim3(p.B), dim3(256), attn_smem_bytes(p.S, p.H), p);
   AOCR_CUDA(cudaGetLastError());
 }
-void enc_cell_bwd_tc(Ctx& ctx, const EncCellBwdTc& p) {
-  launch_pdl(ctx, enc_cell_bwd_tc_kernel, dim3(grid_for((int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He, 256, ctx.num_sms)), dim3(256), 0, p);
-  AOCR_CUDA(cudaGetLastError());
-}
-void cell_fwd_tc(Ctx& ctx, const CellFwdTc& p) {
-  launch_pdl(ctx, cell_fwd_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
-  AOCR_CUDA(cudaGetLastError());
-}
-void dec_out_tc(Ctx& ctx, const DecOutTc& p) {
-  launch_pdl(ctx, dec_out_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
-  AOCR_CUDA(cudaGetLastError());
-}
-void du_tc(Ctx& ctx, const DuTc& p) {
-  launch_pdl(ctx, du_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
-  AOCR_CUDA(cudaGetLastError());
-}
-void cell_bwd_tc(Ctx& ctx, const CellBwdTc& p) {
-  launch_pdl(ctx, cell_bwd_tc_kernel, dim3(grid_for((int64_t)p.B * p.H, 256, ctx.num_sms)), dim3(256), 0, p);
-  AOCR_CUDA(cudaGetLastError());
-}
-void attn_fwd_tc(Ctx& ctx, const float* c, const PartIn& q, float* alpha, float* cv, int64_t ldcv, const PackOut& cvp,
-                 int B, int S, int H) {
-  AOCR_CHECK(H % 128 == 0 && H <= 128 * ATT_MAXV, "attention kernel needs decoder hidden size in {128,...,1024}");
-  size_t smem = (size_t)(((S + 3) & ~3) + 2 * ATT_WARPS + ATT_WARPS * H) * sizeof(float);
-  launch_pdl(ctx, attn_fwd_tc_kernel, dim3(B), dim3(256), smem, c, q, alpha, cv, ldcv, cvp, S, H);
-  AOCR_CUDA(cudaGetLastError());
-}
-void attn_bwd_tc(Ctx& ctx, const float* c, const float* alpha, const PartIn& dcv, float* dcv_out, int64_t ld_dcv_out,
-                 float* de, float* dq, const PackOut& dqp, int B, int S, int H) {
-  size_t smem = (size_t)(((S + 3) & ~3) + 4 + ATT_WARPS * H) * sizeof(float);
-  launch_pdl(ctx, attn_bwd_tc_kernel, dim3(B), dim3(256), smem, c, alpha, dcv, dcv_out, ld_dcv_out, de, dq, dqp, S, H);
+void attn_bwd_tc(Ctx& ctx, const AttnBwdTc& p) {
+  launch_pdl(ctx, attn_bwd_tc_kernel, dim3(p.B), dim3(256), attn_smem_bytes(p.S, p.H), p);
   AOCR_CUDA(cudaGetLastError());
 }
 

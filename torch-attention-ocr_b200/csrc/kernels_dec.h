@@ -40,10 +40,19 @@ void cell_bwd_tc(Ctx&, const CellBwdTc&);
 // dst[b*ld + j] = value(b, j): materialise a split result (used once per step for the encoder seeds)
 void part_to_dense(Ctx&, const PartIn& in, float* dst, int64_t ld, int B, int cols);
 
-void attn_fwd_tc(Ctx&, const float* ctx, const PartIn& q, float* alpha, float* cv, int64_t ldcv, const PackOut& cvp,
-                 int B, int S, int H);
-void attn_bwd_tc(Ctx&, const float* ctx, const float* alpha, const PartIn& dcv, float* dcv_out, int64_t ld_dcv_out,
-                 float* de, float* dq, const PackOut& dqp, int B, int S, int H);
+struct AttnFwdTc {
+  const float* ctx; PartIn q; float* alpha; float* cv; int64_t ldcv; PackOut cvp;
+  float* q_out;        // dense copy of the summed query (needed by the backward), may be null
+  int B, S, H;
+};
+void attn_fwd_tc(Ctx&, const AttnFwdTc&);
+struct AttnBwdTc {
+  const float* ctx; const float* alpha; PartIn dcv; float* dcv_out; int64_t ld_dcv_out;
+  float* de; float* dq; PackOut dqp;
+  int B, S, H;
+};
+void attn_bwd_tc(Ctx&, const AttnBwdTc&);
+inline size_t attn_smem_bytes(int S, int H) { return (size_t)(((S + 3) & ~3) + 16 + 8 * H) * sizeof(float); }
 
 }  // namespace aocr
 
