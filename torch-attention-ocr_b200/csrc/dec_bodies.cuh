@@ -18,14 +18,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float part_load(const PartIn& a, int64_t b, int64_t j) {
   const float* p = a.p + b * a.ld + j;
   float s = 0.f;
-  for (int z = 0; z < a.nz; z++) s += p[(int64_t)z * a.stride];
+  for (int z = 0; z < a.nz; z++) s += __ldcg(p + (int64_t)z * a.stride);   // L2: written by other SMs
   return s;
 }
 __device__ __forceinline__ float4 part_load4(const PartIn& a, int64_t b, int64_t j) {
   const float* p = a.p + b * a.ld + j;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int z = 0; z < a.nz; z++) {
-    float4 t = *reinterpret_cast<const float4*>(p + (int64_t)z * a.stride);
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p + (int64_t)z * a.stride));
     s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
   }
   return s;

@@ -110,6 +110,8 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (const char* e = getenv("AOCR_PDL")) ctx_.pdl = atoi(e) != 0;
   if (const char* e = getenv("AOCR_PHASES")) phases_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_GRAPHS")) graphs_on_ = atoi(e) != 0;
+  if (const char* e = getenv("AOCR_PERSIST")) persist_on_ = atoi(e) != 0;
+  if (c.batch_size > 128 || c.gemm_mode == 2) persist_on_ = false;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));
   AOCR_CUDA(cudaEventCreate(&ev1_));
@@ -227,6 +229,7 @@ Engine::~Engine() {
   if (ev1_) cudaEventDestroy(ev1_);
   for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
   for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : programs_) persist_free(kv.second);
   if (ctx_.st) cudaStreamDestroy(ctx_.st);
 }
 
@@ -330,12 +333,17 @@ void Engine::prof_begin(int cls) {
     }
   }
   AOCR_CUDA(cudaEventRecord(prof_pool_[prof_used_ * 2], ctx_.st));
+  prof_open_.push_back(prof_used_);
+  prof_recs_.push_back({cls, -1.0});
+  prof_used_++;
 }
 void Engine::prof_end(int cls, double work) {
   if (!prof_on) return;
-  AOCR_CUDA(cudaEventRecord(prof_pool_[prof_used_ * 2 + 1], ctx_.st));
-  prof_recs_.push_back({cls, work});
-  prof_used_++;
+  if (prof_open_.empty()) return;
+  const size_t slot = prof_open_.back();
+  prof_open_.pop_back();
+  AOCR_CUDA(cudaEventRecord(prof_pool_[slot * 2 + 1], ctx_.st));
+  prof_recs_[slot].second = work;
 }
 void Engine::use_lane(int i) {
   if (i == cur_lane_) return;
@@ -383,7 +391,9 @@ void Engine::phase_report() {
 }
 void Engine::prof_collect() {
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  for (int l = 1; l < 3; l++) if (lanes_on_ && lanes_[l].st) AOCR_CUDA(cudaStreamSynchronize(lanes_[l].st));
   for (size_t i = 0; i < prof_recs_.size(); i++) {
+    if (prof_recs_[i].second < 0) continue;
     float ms = 0.f;
     AOCR_CUDA(cudaEventElapsedTime(&ms, prof_pool_[2 * i], prof_pool_[2 * i + 1]));
     prof_ms[prof_recs_[i].first] += ms;
@@ -391,6 +401,7 @@ void Engine::prof_collect() {
     prof_work[prof_recs_[i].first] += prof_recs_[i].second;
   }
   prof_recs_.clear();
+  prof_open_.clear();
   prof_used_ = 0;
 }
 

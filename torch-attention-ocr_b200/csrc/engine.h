@@ -8,6 +8,7 @@
 #include "../../include/aocr.h"
 #include "kernels.h"
 #include "kernels_dec.h"
+#include "persist.h"
 #include "gemm_tc.cuh"
 #include <tuple>
 #include <string.h>
@@ -100,6 +101,21 @@ class Engine {
   void decoder_backward_steps_simt();
   void decoder_backward_steps_tc();
   void build_decoder_packs();
+  // emitters: launch a piece of a recurrence as its own kernel, or record it into a persistent program
+  TcOut emit_gemm(const Pack& W, int M, const Pack& X, int64_t row0, int64_t k0, int K, float* ws);
+  void emit(const CellFwdTc& p); void emit(const DecOutTc& p); void emit(const DuTc& p); void emit(const CellBwdTc& p);
+  void emit(const EncCellFwdTc& p); void emit(const EncCellBwdTc& p); void emit(const AttnFwdTc& p); void emit(const AttnBwdTc& p);
+  void emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols);
+  void encoder_dir_forward(int d);
+  void encoder_dir_backward(int d);
+  enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4 };
+  struct ProgKey { int kind, b, S, nsteps, variant; bool operator<(const ProgKey& o) const {
+    return std::tie(kind, b, S, nsteps, variant) < std::tie(o.kind, o.b, o.S, o.nsteps, o.variant); } };
+  std::map<ProgKey, PersistProgram> programs_;
+  PersistProgram* rec_ = nullptr;
+  int rec_max_ctas_ = 128;
+  bool persist_on_ = true;      // AOCR_PERSIST=0: per-kernel chains instead of the persistent executor
+  void run_program(int kind, int nsteps, int variant);
   void encoder_forward_steps_tc();
   void encoder_backward_steps_tc();
   void conv_wgrad_tc(const float* dz, const float* x, int N, int H, int W, int Cin, int k, int pad, int Ho, int Wo,
@@ -141,6 +157,7 @@ class Engine {
   std::vector<cudaEvent_t> prof_pool_;
   std::vector<std::pair<int, double>> prof_recs_;
   size_t prof_used_ = 0;
+  std::vector<size_t> prof_open_;
 
   int device_;
   struct WeightPack { Pack pack; int64_t version; };

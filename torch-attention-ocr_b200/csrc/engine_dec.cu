@@ -204,7 +204,17 @@ void Engine::decoder_backward() {
   gemm(g);
   col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
 
-  if (cfg.gemm_mode != 2) decoder_backward_steps_tc(); else decoder_backward_steps_simt();
+  if (cfg.gemm_mode != 2) {
+    if (persist_on_) {
+      fill_zero(ctx_, dc1, (size_t)B * Hd * sizeof(float));
+      fill_zero(ctx_, dc2, (size_t)B * Hd * sizeof(float));
+      run_program(PK_DEC_BWD, T, 0);
+    } else {
+      decoder_backward_steps_tc();
+    }
+  } else {
+    decoder_backward_steps_simt();
+  }
   // the time-batched parameter gradients below depend only on the saved per-step tensors: lane 1, concurrently
   // with D_ctx + the encoder/CNN backward that continue on lane 0
   fork_to(1);
@@ -306,7 +316,8 @@ void Engine::forward_backward_enqueue() {
   phase_mark("enc_fwd");
   decoder_init();
   dec_steps_ = T;
-  for (int t = 0; t < T; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
+  if (persist_on_ && cfg.gemm_mode != 2) run_program(PK_DEC_FWD, T, 0);
+  else for (int t = 0; t < T; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
   phase_mark("dec_fwd");
   taps_["a_all"] = {A_all, (int64_t)T * B * Hd};
   taps_["alpha"] = {ALPHA, (int64_t)T * B * S_};
@@ -468,7 +479,8 @@ void Engine::decode_enqueue() {
   }
   // gold pass: teacher forced with the padded targets (model.lua:589-627)
   decoder_init();
-  for (int t = 0; t < Ld; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
+  if (persist_on_ && cfg.gemm_mode != 2) run_program(PK_DEC_FWD, Ld, 0);
+  else for (int t = 0; t < Ld; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
   generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[2], nullptr, rowloss, (int64_t)Ld * B, Hd, V,
                 1.0f);
   reduce_sum_double(ctx_, rowloss, (int64_t)Ld * B, d_loss);

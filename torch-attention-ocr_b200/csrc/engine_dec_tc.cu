@@ -1,8 +1,10 @@
 // engine_dec_tc.cu — the decoder schedule on tensor cores (gemm_mode 0/1).  Per timestep: four tcgen05 GEMMs
 // (layer-1 gates, layer-2 gates, attention query, output projection), each followed by ONE memory-bound
-// kernel that sums the GEMM's split-K partials, applies the cell / attention / tanh math and writes the next
+// body that sums the GEMM's split-K partials, applies the cell / attention / tanh math and writes the next
 // GEMM's operand as bf16 planes.  Weights are concatenated along K ([W_i | W_h]) so a cell needs one GEMM,
 // and the batch rides the UMMA N dimension (swap-AB) so the 128-row M tile is filled by weight rows.
+// The same step functions either LAUNCH each piece as its own kernel or RECORD it into the command list of the
+// persistent recurrence executor (persist.cu), which then runs the whole recurrence as one cooperative kernel.
 // Reference schedule: src/model/model.lua:553-568 (forward), :643-661 (backward).
 #include "engine.h"
 
@@ -31,6 +33,63 @@ PartIn part_in(const TcOut& o, int64_t ld, int64_t col0 = 0) {
 }
 }  // namespace
 
+// ---- emitters: launch now, or append to the program being recorded -----------------------------------------
+// weights (M rows) x activation rows [row0, row0+b) of the pack X, K columns starting at k0 -> (b x M) partials in ws
+TcOut Engine::emit_gemm(const Pack& W, int M, const Pack& X, int64_t row0, int64_t k0, int K, float* ws) {
+  const int B = b_;
+  const int terms = cfg.gemm_mode == 1 ? 1 : 3;
+  if (rec_) {
+    PGemmPlan pl = persist_plan_gemm(M, B, K, rec_max_ctas_, dec_ws_floats);
+    PGemm g{};
+    g.map_a = rec_->add_map_pair(tc_map_2d(W.hi, W.rows, W.kp, 128), tc_map_2d(W.lo, W.rows, W.kp, 128));
+    g.map_b = rec_->add_map_pair(tc_map_2d(X.hi, X.rows, X.kp, rec_->bn), tc_map_2d(X.lo, X.rows, X.kp, rec_->bn));
+    g.m_tiles = pl.m_tiles; g.splits = pl.splits; g.kb_per = pl.kb_per; g.num_kb = pl.num_kb;
+    g.b_row0 = (int)row0; g.b_k0 = (int)k0; g.M = M; g.N = B; g.terms = terms;
+    g.ws = ws; g.part_stride = pl.part_stride; g.ldc = M;
+    rec_->add(P_GEMM, g);
+    if (pl.m_tiles * pl.splits > rec_->grid) rec_->grid = pl.m_tiles * pl.splits;
+    TcOut o;
+    o.base = ws; o.nz = pl.splits; o.stride = pl.part_stride;
+    return o;
+  }
+  Pack xs = sub_rows(X, row0, B);
+  xs.hi += k0; xs.lo += k0;
+  TcGemm g;
+  g.A = W; g.B = xs; g.M = M; g.N = B; g.K = K; g.ldc = M; g.transpose_out = true;   // C[b][m]
+  g.terms = terms; g.defer_reduce = true; g.ws = ws; g.ws_floats = dec_ws_floats;
+  prof_begin(0);
+  TcOut o = gemm_tc(ctx_, g);
+  prof_end(0, 2.0 * M * (double)B * K);
+  return o;
+}
+void Engine::emit(const CellFwdTc& p) { if (rec_) rec_->add(P_CELL_FWD, p); else cell_fwd_tc(ctx_, p); }
+void Engine::emit(const DecOutTc& p) { if (rec_) rec_->add(P_DEC_OUT, p); else dec_out_tc(ctx_, p); }
+void Engine::emit(const DuTc& p) { if (rec_) rec_->add(P_DU, p); else du_tc(ctx_, p); }
+void Engine::emit(const CellBwdTc& p) { if (rec_) rec_->add(P_CELL_BWD, p); else cell_bwd_tc(ctx_, p); }
+void Engine::emit(const EncCellFwdTc& p) { if (rec_) rec_->add(P_ENC_CELL_FWD, p); else enc_cell_fwd_tc(ctx_, p); }
+void Engine::emit(const EncCellBwdTc& p) { if (rec_) rec_->add(P_ENC_CELL_BWD, p); else enc_cell_bwd_tc(ctx_, p); }
+void Engine::emit(const AttnFwdTc& p) {
+  if (rec_) { rec_->add(P_ATTN_FWD, p); return; }
+  prof_begin(1);
+  attn_fwd_tc(ctx_, p);
+  prof_end(1, (double)p.B * p.S * p.H * 4 + (double)p.B * (2.0 * p.H + p.S) * 4);
+}
+void Engine::emit(const AttnBwdTc& p) {
+  if (rec_) { rec_->add(P_ATTN_BWD, p); return; }
+  prof_begin(1);
+  attn_bwd_tc(ctx_, p);
+  prof_end(1, 2.0 * p.B * p.S * p.H * 4);
+}
+void Engine::emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols) {
+  if (rec_) {
+    PToDense p;
+    p.in = in; p.dst = dst; p.ld = ld; p.B = B; p.cols = cols;
+    rec_->add(P_TO_DENSE, p);
+  } else {
+    part_to_dense(ctx_, in, dst, ld, B, cols);
+  }
+}
+
 // (re)build the decoder weight packs after a parameter change
 void Engine::build_decoder_packs() {
   if (dec_packs_version_ == weights_version_) return;
@@ -55,27 +114,17 @@ void Engine::build_decoder_packs() {
 
 // One decoder step.  Saved fp32 state (for backward) has the layout of the SIMT path:
 //   X1[t] = [a_{t-1} | h1_{t-1}]   X2[t] = [h1_t | h2_{t-1}]   CAT[t] = [cv_t | h2_t]   A_all[t] = a_t
-// and X1p / X2p / CATp mirror them as bf16 planes (written by the producing kernels, never by a conversion pass).
+// and X1p / X2p / CATp mirror them as bf16 planes (written by the producing bodies, never by a conversion pass).
 void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   const int B = b_, S = S_;
   const int nsteps = dec_steps_;
   const bool has_next = (t + 1 < nsteps);
-  const int terms = cfg.gemm_mode == 1 ? 1 : 3;
   float* x1 = X1 + (int64_t)t * B * K1;
   float* x2 = X2 + (int64_t)t * B * 2 * Hd;
   float* cat = CAT + (int64_t)t * B * 2 * Hd;
   const int64_t r0 = (int64_t)t * B, r1 = (int64_t)(t + 1) * B;
-  auto run = [&](const Pack& W, int M, const Pack& X, int K, int slot) {
-    TcGemm g;
-    g.A = W; g.B = X; g.M = M; g.N = B; g.K = K; g.ldc = M; g.transpose_out = true;   // C[b][m]
-    g.terms = terms; g.defer_reduce = true; g.ws = dec_ws[slot]; g.ws_floats = dec_ws_floats;
-    prof_begin(0);
-    TcOut o = gemm_tc(ctx_, g);
-    prof_end(0, 2.0 * M * (double)B * K);
-    return o;
-  };
   // ---- layer 1
-  TcOut g1 = run(Wcat1p, 4 * Hd, sub_rows(X1p, r0, B), K1, 0);
+  TcOut g1 = emit_gemm(Wcat1p, 4 * Hd, X1p, r0, 0, K1, dec_ws[0]);
   CellFwdTc c1;
   c1.G = part_in(g1, 4 * Hd); c1.addrows = Ptab; c1.rowsel = tokens; c1.addld = 4 * Hd;
   c1.c_prev = C1 + (int64_t)t * B * Hd; c1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
@@ -85,9 +134,9 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   c1.pk0 = pack_out(X2p, r0, 0);
   c1.pk1 = has_next ? pack_out(X1p, r1, h1off) : PackOut();
   c1.B = B; c1.H = Hd;
-  cell_fwd_tc(ctx_, c1);
+  emit(c1);
   // ---- layer 2
-  TcOut g2 = run(Wcat2p, 4 * Hd, sub_rows(X2p, r0, B), 2 * Hd, 1);
+  TcOut g2 = emit_gemm(Wcat2p, 4 * Hd, X2p, r0, 0, 2 * Hd, dec_ws[1]);
   CellFwdTc c2;
   c2.G = part_in(g2, 4 * Hd); c2.addrows = bsum2; c2.rowsel = nullptr; c2.addld = 0;
   c2.c_prev = C2 + (int64_t)t * B * Hd; c2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
@@ -97,42 +146,30 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   c2.pk0 = pack_out(CATp, r0, Hd);
   c2.pk1 = has_next ? pack_out(X2p, r1, Hd) : PackOut();
   c2.B = B; c2.H = Hd;
-  cell_fwd_tc(ctx_, c2);
-  // ---- attention: q = W_a h2 (operand = second half of CATp[t]), fused score/softmax/context kernel
-  Pack h2p = sub_rows(CATp, r0, B);
-  h2p.hi += Hd; h2p.lo += Hd;
-  TcOut qo = run(Wap, Hd, h2p, Hd, 2);
+  emit(c2);
+  // ---- attention: q = W_a h2 (operand = second half of CATp[t]), fused score/softmax/context body
+  TcOut qo = emit_gemm(Wap, Hd, CATp, r0, Hd, Hd, dec_ws[2]);
   AttnFwdTc af;
   af.ctx = ctx; af.q = part_in(qo, Hd); af.alpha = ALPHA + (int64_t)t * B * S; af.cv = cat; af.ldcv = 2 * Hd;
   af.cvp = pack_out(CATp, r0, 0); af.q_out = Q + (int64_t)t * B * Hd; af.B = B; af.S = S; af.H = Hd;
-  prof_begin(1);
-  attn_fwd_tc(ctx_, af);
-  prof_end(1, (double)B * S * Hd * 4 + (double)B * (2.0 * Hd + S) * 4);
+  emit(af);
   // ---- a_t = tanh(W_c [cv ; h2])
-  TcOut uo = run(Wcp, Hd, sub_rows(CATp, r0, B), 2 * Hd, 3);
+  TcOut uo = emit_gemm(Wcp, Hd, CATp, r0, 0, 2 * Hd, dec_ws[3]);
   DecOutTc d;
   d.U = part_in(uo, Hd); d.a_out = A_all + (int64_t)t * B * Hd;
   d.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; d.ld_next = K1;
   d.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();
   d.B = B; d.H = Hd;
-  dec_out_tc(ctx_, d);
+  emit(d);
 }
 
 // per-timestep part of the decoder backward (model.lua:643-661) on tensor cores
 void Engine::decoder_backward_steps_tc() {
   const int B = b_, S = S_, T = T_;
-  const int terms = cfg.gemm_mode == 1 ? 1 : 3;
-  fill_zero(ctx_, dc1, (size_t)B * Hd * sizeof(float));
-  fill_zero(ctx_, dc2, (size_t)B * Hd * sizeof(float));
-  auto run = [&](const Pack& WT, int M, const Pack& X, int K, int slot) {
-    TcGemm g;
-    g.A = WT; g.B = X; g.M = M; g.N = B; g.K = K; g.ldc = M; g.transpose_out = true;
-    g.terms = terms; g.defer_reduce = true; g.ws = dec_ws[slot]; g.ws_floats = dec_ws_floats;
-    prof_begin(0);
-    TcOut o = gemm_tc(ctx_, g);
-    prof_end(0, 2.0 * M * (double)B * K);
-    return o;
-  };
+  if (!rec_) {
+    fill_zero(ctx_, dc1, (size_t)B * Hd * sizeof(float));
+    fill_zero(ctx_, dc2, (size_t)B * Hd * sizeof(float));
+  }
   TcOut dx1, dx2;   // carries of the previous (t+1) iteration; valid when !last
   for (int t = T - 1; t >= 0; t--) {
     const bool last = (t == T - 1);
@@ -141,18 +178,16 @@ void Engine::decoder_backward_steps_tc() {
     du.da_carry = (!last && cfg.input_feed) ? part_in(dx1, K1, 0) : PartIn();
     du.da_gen = dAgen + (int64_t)t * B * Hd; du.a = A_all + (int64_t)t * B * Hd;
     du.du = dU + (int64_t)t * B * Hd; du.pk = pack_out(dUp, 0, 0); du.B = B; du.H = Hd;
-    du_tc(ctx_, du);
+    emit(du);
     // d[cv ; h2] = du W_c
-    TcOut dcat = run(WcTp, 2 * Hd, dUp, Hd, 0);
+    TcOut dcat = emit_gemm(WcTp, 2 * Hd, dUp, 0, 0, Hd, dec_ws[0]);
     AttnBwdTc ab;
     ab.ctx = ctx; ab.alpha = ALPHA + (int64_t)t * B * S; ab.dcv = part_in(dcat, 2 * Hd, 0);
     ab.dcv_out = dCAT + (int64_t)t * B * 2 * Hd; ab.ld_dcv_out = 2 * Hd; ab.de = DE + (int64_t)t * B * S;
     ab.dq = dQ + (int64_t)t * B * Hd; ab.dqp = pack_out(dQp, 0, 0); ab.B = B; ab.S = S; ab.H = Hd;
-    prof_begin(1);
-    attn_bwd_tc(ctx_, ab);
-    prof_end(1, 2.0 * B * S * Hd * 4);
+    emit(ab);
     // dh2 += dq W_a
-    TcOut dh2q = run(WaTp, Hd, dQp, Hd, 1);
+    TcOut dh2q = emit_gemm(WaTp, Hd, dQp, 0, 0, Hd, dec_ws[1]);
     CellBwdTc b2;
     b2.dh_a = part_in(dcat, 2 * Hd, Hd);
     b2.dh_b = part_in(dh2q, Hd, 0);
@@ -160,9 +195,9 @@ void Engine::decoder_backward_steps_tc() {
     b2.dc = dc2; b2.c_prev = C2 + (int64_t)t * B * Hd; b2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
     b2.acts = ACT2 + (int64_t)t * B * 4 * Hd; b2.dG = dG2 + (int64_t)t * B * 4 * Hd; b2.pk = pack_out(dG2p, 0, 0);
     b2.B = B; b2.H = Hd;
-    cell_bwd_tc(ctx_, b2);
+    emit(b2);
     // [dh1 | dh2_prev] = dg2 [W_i2 | W_h2]      (slot 2 must outlive this iteration: read again at t-1)
-    dx2 = run(Wcat2Tp, 2 * Hd, dG2p, 4 * Hd, 2);
+    dx2 = emit_gemm(Wcat2Tp, 2 * Hd, dG2p, 0, 0, 4 * Hd, dec_ws[2]);
     CellBwdTc b1;
     b1.dh_a = part_in(dx2, 2 * Hd, 0);
     b1.dh_b = last ? PartIn() : part_in(dx1, K1, h1off);
@@ -170,12 +205,12 @@ void Engine::decoder_backward_steps_tc() {
     b1.dc = dc1; b1.c_prev = C1 + (int64_t)t * B * Hd; b1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
     b1.acts = ACT1 + (int64_t)t * B * 4 * Hd; b1.dG = dG1 + (int64_t)t * B * 4 * Hd; b1.pk = pack_out(dG1p, 0, 0);
     b1.B = B; b1.H = Hd;
-    cell_bwd_tc(ctx_, b1);
+    emit(b1);
     // [da_prev | dh1_prev] = dg1 [W_i1[:,E:] | W_h1]
-    dx1 = run(Wcat1Tp, K1, dG1p, 4 * Hd, 3);
+    dx1 = emit_gemm(Wcat1Tp, K1, dG1p, 0, 0, 4 * Hd, dec_ws[3]);
   }
   // hand d h1(0) to the encoder backward through the dense dX1 buffer (model.lua:666-667,680-681; quirk Q14)
-  part_to_dense(ctx_, part_in(dx1, K1, 0), dX1, K1, B, K1);
+  emit_to_dense(part_in(dx1, K1, 0), dX1, K1, B, K1);
 }
 
 }  // namespace aocr

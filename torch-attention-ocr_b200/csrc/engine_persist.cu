@@ -1,0 +1,51 @@
+// engine_persist.cu — builds, caches and launches the command lists of the persistent recurrence executor.
+// A program is recorded by running the ordinary step functions with `rec_` set (every emit() appends a command
+// instead of launching a kernel), so the per-kernel path and the persistent path share one description of the math.
+#include "engine.h"
+
+namespace aocr {
+
+void Engine::run_program(int kind, int nsteps, int variant) {
+  ProgKey key{kind, b_, S_, nsteps, variant};
+  auto it = programs_.find(key);
+  if (it == programs_.end()) {
+    PersistProgram prog;
+    int bn = b_ > 64 ? 128 : (b_ > 32 ? 64 : (b_ > 16 ? 32 : 16));
+    AOCR_CHECK(b_ <= 128, "persistent executor: per-GPU batch must be <= 128");
+    prog.bn = bn;
+    const bool enc = (kind == PK_ENC_FWD0 || kind == PK_ENC_FWD0 + 1 || kind == PK_ENC_BWD0 || kind == PK_ENC_BWD0 + 1);
+    int cap = persist_max_ctas(bn);
+    rec_max_ctas_ = enc ? (cap / 2 < 64 ? cap / 2 : 64) : (cap < 128 ? cap : 128);   // both encoder directions co-resident
+    prog.grid = 1;
+    rec_ = &prog;
+    try {
+      switch (kind) {
+        case PK_DEC_FWD: {
+          const int save = dec_steps_;
+          dec_steps_ = nsteps;
+          for (int t = 0; t < nsteps; t++) decoder_step_tc(t, tgt_tb + (int64_t)t * b_);
+          dec_steps_ = save;
+          break;
+        }
+        case PK_DEC_BWD: decoder_backward_steps_tc(); break;
+        case PK_ENC_FWD0: encoder_dir_forward(0); break;
+        case PK_ENC_FWD0 + 1: encoder_dir_forward(1); break;
+        case PK_ENC_BWD0: encoder_dir_backward(0); break;
+        case PK_ENC_BWD0 + 1: encoder_dir_backward(1); break;
+        default: throw InvalidError("unknown persistent program kind");
+      }
+    } catch (...) {
+      rec_ = nullptr;
+      throw;
+    }
+    rec_ = nullptr;
+    if (prog.grid < 16) prog.grid = 16;      // the bodies are grid-stride: a few more CTAs cost nothing
+    if (prog.grid > rec_max_ctas_) prog.grid = rec_max_ctas_;
+    it = programs_.emplace(key, std::move(prog)).first;
+  }
+  PersistProgram& prog = it->second;
+  if (!prog.uploaded) persist_upload(ctx_, prog);
+  persist_launch(ctx_, prog);
+}
+
+}  // namespace aocr

@@ -1,5 +1,7 @@
 // gemm_tc.cuh — host interface of the tcgen05/TMEM/TMA GEMM core (definitions in gemm_tc.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace aocr {
@@ -53,6 +55,8 @@ struct TcGemm {
 // where the result lives: value(i) = sum_{z < nz} base[z*stride + i], i indexed like C (ldc / transpose_out)
 struct TcOut { const float* base = nullptr; int nz = 1; int64_t stride = 0; };
 TcOut gemm_tc(Ctx& ctx, const TcGemm& g);
-bool gemm_tc_available();   // driver entry point for cuTensorMapEncodeTiled resolved
+bool gemm_tc_available();
+// cached 2-D tensor map of one bf16 plane [rows][kp] with a 64 x box_rows box, 128B swizzle (also used by persist.cu)
+const CUtensorMap& tc_map_2d(const __nv_bfloat16* ptr, int64_t rows, int64_t kp, int box_rows);   // driver entry point for cuTensorMapEncodeTiled resolved
 
 }  // namespace aocr

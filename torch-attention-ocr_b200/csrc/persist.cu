@@ -1,0 +1,296 @@
+// persist.cu — persistent recurrence executor (see persist.h).  One cooperative kernel, 256 threads per CTA, one CTA
+// per SM (197 KB of shared memory for the TMA ring): warp 0 = TMA producer, warp 1 = tcgen05 issuer and TMEM owner,
+// warps 2-5 = epilogue (TMEM -> split-K partials in global memory), all 8 warps = the fused cell / attention bodies.
+// mbarrier phases and the TMEM allocation persist across commands; a grid barrier (one global counter, acquire /
+// release, preceded by fence.proxy.async so the generic-proxy stores of a command are visible to the TMA loads of
+// the next one on every SM) replaces the kernel boundary between consecutive commands.
+#include "persist.h"
+
+#include "dec_bodies.cuh"
+#include "tc_ptx.cuh"
+
+namespace aocr {
+
+namespace {
+using namespace tcp;
+
+template <int BN> struct PCfg {
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kBPlane = BN * BK * 2;
+  static constexpr int kStageBytes = 2 * A_PLANE_BYTES + 2 * kBPlane;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned nblk, unsigned& epoch) {
+  asm volatile("fence.proxy.async;" ::: "memory");      // this thread's stores -> visible to the async proxy (TMA)
+  __syncthreads();
+  epoch++;
+  if (threadIdx.x == 0) {
+    __threadfence();                                    // cumulative over the CTA (bar.sync above): release
+    atomicAdd(ctr, 1u);
+    const unsigned target = epoch * nblk;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__device__ __forceinline__ const T& payload(const PCmd& c) { return *reinterpret_cast<const T*>(c.payload); }
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __restrict__ maps, unsigned* barrier) {
+  using C_ = PCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + C_::kStages * C_::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C_::kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * C_::kStages);
+  const uint32_t tmem_slot = bars + 8u * (2 * C_::kStages + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* scratch = reinterpret_cast<float*>(smem_raw + (base - raw));   // the (idle) TMA ring doubles as body scratch
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bid = blockIdx.x, nblk = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_::kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(C_::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  unsigned epoch = 0;
+  uint32_t it = 0;        // k-blocks this CTA has pushed through the ring so far (producer and issuer count alike)
+  uint32_t tiles = 0;     // GEMM tiles this CTA has finished (parity of the TMEM-full barrier)
+
+  for (int c = 0; c < ncmds; c++) {
+    const PCmd& cmd = cmds[c];
+    const int type = cmd.type;
+    if (type == P_GEMM) {
+      const PGemm g = payload<PGemm>(cmd);
+      const int ntiles = g.m_tiles * g.splits;
+      if (bid < ntiles) {
+        const int z = bid / g.m_tiles, mt = bid % g.m_tiles;
+        const int kb_begin = z * g.kb_per;
+        const int kb_end = min(g.num_kb, kb_begin + g.kb_per);
+        const int nkb = kb_end - kb_begin;
+        const int m0 = mt * BM;
+        if (warp == 0) {
+          if (lane == 0) {
+            const uint32_t tx = (uint32_t)(g.terms == 3 ? 2 : 1) * (A_PLANE_BYTES + C_::kBPlane);
+            const CUtensorMap* tAh = maps + g.map_a;
+            const CUtensorMap* tBh = maps + g.map_b;
+            for (int i = 0; i < nkb; i++) {
+              const uint32_t n = it + i;
+              const int s = n % C_::kStages;
+              const uint32_t ph = (n / C_::kStages) & 1u;
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              const uint32_t sa = base + s * C_::kStageBytes;
+              const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+              mbar_expect_tx(full_bar(s), tx);
+              const int kc = (kb_begin + i) * BK;
+              tma_load_2d(sa, tAh, full_bar(s), kc, m0);
+              tma_load_2d(sb, tBh, full_bar(s), g.b_k0 + kc, g.b_row0);
+              if (g.terms == 3) {
+                tma_load_2d(sa + A_PLANE_BYTES, tAh + 1, full_bar(s), kc, m0);
+                tma_load_2d(sb + C_::kBPlane, tBh + 1, full_bar(s), g.b_k0 + kc, g.b_row0);
+              }
+            }
+          }
+        } else if (warp == 1) {
+          const uint32_t idesc = make_idesc(BN, 0);
+          for (int i = 0; i < nkb; i++) {
+            const uint32_t n = it + i;
+            const int s = n % C_::kStages;
+            const uint32_t ph = (n / C_::kStages) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t sa = base + s * C_::kStageBytes;
+              const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+              const uint64_t dah = make_desc_kmajor_sw128(sa), dal = make_desc_kmajor_sw128(sa + A_PLANE_BYTES);
+              const uint64_t dbh = make_desc_kmajor_sw128(sb), dbl = make_desc_kmajor_sw128(sb + C_::kBPlane);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; k++) {
+                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                tc_mma(tmem_base, dah + adv, dbh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                if (g.terms == 3) {
+                  tc_mma(tmem_base, dah + adv, dbl + adv, idesc, 1u);
+                  tc_mma(tmem_base, dal + adv, dbh + adv, idesc, 1u);
+                }
+              }
+              tc_commit(empty_bar(s));
+              if (i == nkb - 1) tc_commit(tmem_full_bar);
+            }
+            __syncwarp();
+          }
+        } else if (warp < 6) {
+          const int q = warp & 3;
+          mbar_wait(tmem_full_bar, tiles & 1u);
+          tc_fence_after();
+          const int row = m0 + q * 32 + lane;                 // weight row = output column of the (batch x M) result
+          float* outp = g.ws + (long long)z * g.part_stride;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < g.M) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                const int n = c0 + j;
+                if (n < g.N) outp[(long long)n * g.ldc + row] = __uint_as_float(r[j]);   // coalesced over rows
+              }
+            }
+          }
+          tc_fence_before();
+        }
+        it += (uint32_t)nkb;
+        tiles += 1;
+      }
+    } else if (type == P_CELL_FWD) {
+      decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);
+    } else if (type == P_DEC_OUT) {
+      decb::dec_out_tc_body(payload<DecOutTc>(cmd), bid, nblk, scratch);
+    } else if (type == P_DU) {
+      decb::du_tc_body(payload<DuTc>(cmd), bid, nblk, scratch);
+    } else if (type == P_CELL_BWD) {
+      decb::cell_bwd_tc_body(payload<CellBwdTc>(cmd), bid, nblk, scratch);
+    } else if (type == P_ENC_CELL_FWD) {
+      decb::enc_cell_fwd_tc_body(payload<EncCellFwdTc>(cmd), bid, nblk, scratch);
+    } else if (type == P_ENC_CELL_BWD) {
+      decb::enc_cell_bwd_tc_body(payload<EncCellBwdTc>(cmd), bid, nblk, scratch);
+    } else if (type == P_TO_DENSE) {
+      const PToDense p = payload<PToDense>(cmd);
+      decb::part_to_dense_body(p.in, p.dst, p.ld, p.B, p.cols, bid, nblk, scratch);
+    } else if (type == P_ATTN_FWD) {
+      const AttnFwdTc p = payload<AttnFwdTc>(cmd);
+      for (int b = bid; b < p.B; b += nblk) {
+        decb::attn_fwd_tc_body(p.ctx, p.q, p.alpha, p.cv, p.ldcv, p.cvp, p.q_out, p.S, p.H, b, nblk, scratch);
+        __syncthreads();
+      }
+    } else if (type == P_ATTN_BWD) {
+      const AttnBwdTc p = payload<AttnBwdTc>(cmd);
+      for (int b = bid; b < p.B; b += nblk) {
+        decb::attn_bwd_tc_body(p.ctx, p.alpha, p.dcv, p.dcv_out, p.ld_dcv_out, p.de, p.dq, p.dqp, p.S, p.H, b, nblk,
+                               scratch);
+        __syncthreads();
+      }
+    }
+    grid_sync(barrier, (unsigned)nblk, epoch);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::kTmemCols) : "memory");
+  }
+}
+
+template <int BN>
+void launch_bn(Ctx& ctx, PersistProgram& prog) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AOCR_CUDA(cudaFuncSetAttribute(persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  const PCmd* cmds = prog.d_cmds;
+  int ncmds = (int)prog.cmds.size();
+  const CUtensorMap* maps = prog.d_maps;
+  unsigned* bar = prog.d_barrier;
+  void* args[] = {(void*)&cmds, (void*)&ncmds, (void*)&maps, (void*)&bar};
+  AOCR_CUDA(cudaMemsetAsync(prog.d_barrier, 0, sizeof(unsigned), ctx.st));
+  AOCR_CUDA(cudaLaunchCooperativeKernel((const void*)persist_kernel<BN>, dim3(prog.grid), dim3(256), args,
+                                        (size_t)PCfg<BN>::kSmemBytes, ctx.st));
+  ctx.launches++;
+}
+
+template <int BN>
+int max_ctas_bn() {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaFuncSetAttribute(persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel<BN>, 256, (size_t)PCfg<BN>::kSmemBytes);
+  return sms * per_sm;
+}
+
+}  // namespace
+
+PGemmPlan persist_plan_gemm(int M, int N, int K, int max_ctas, long long ws_floats) {
+  PGemmPlan p;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.num_kb = (int)(pad64(K) / BK);
+  p.part_stride = (((long long)(N - 1) * M + M) + 63) & ~63LL;
+  int splits = max_ctas / p.m_tiles;
+  if (splits > p.num_kb / 2) splits = p.num_kb / 2;
+  if (splits > 16) splits = 16;
+  if (splits < 1) splits = 1;
+  while (splits > 1 && (long long)splits * p.part_stride > ws_floats) splits--;
+  p.kb_per = (p.num_kb + splits - 1) / splits;
+  p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;
+  return p;
+}
+
+int persist_max_ctas(int bn) {
+  switch (bn) {
+    case 128: return max_ctas_bn<128>();
+    case 64: return max_ctas_bn<64>();
+    case 32: return max_ctas_bn<32>();
+    default: return max_ctas_bn<16>();
+  }
+}
+
+void persist_upload(Ctx& ctx, PersistProgram& prog) {
+  if (prog.uploaded) return;
+  AOCR_CHECK(!prog.cmds.empty(), "empty persistent program");
+  AOCR_CUDA(cudaMalloc(&prog.d_cmds, prog.cmds.size() * sizeof(PCmd)));
+  AOCR_CUDA(cudaMalloc(&prog.d_maps, (prog.maps.size() + 1) * sizeof(CUtensorMap)));
+  AOCR_CUDA(cudaMalloc(&prog.d_barrier, 256));
+  AOCR_CUDA(cudaMemcpy(prog.d_cmds, prog.cmds.data(), prog.cmds.size() * sizeof(PCmd), cudaMemcpyHostToDevice));
+  if (!prog.maps.empty())
+    AOCR_CUDA(cudaMemcpy(prog.d_maps, prog.maps.data(), prog.maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  prog.uploaded = true;
+}
+
+void persist_launch(Ctx& ctx, PersistProgram& prog) {
+  AOCR_CHECK(prog.uploaded, "persistent program not uploaded");
+  switch (prog.bn) {
+    case 128: launch_bn<128>(ctx, prog); break;
+    case 64: launch_bn<64>(ctx, prog); break;
+    case 32: launch_bn<32>(ctx, prog); break;
+    default: launch_bn<16>(ctx, prog); break;
+  }
+}
+
+void persist_free(PersistProgram& prog) {
+  if (prog.d_cmds) cudaFree(prog.d_cmds);
+  if (prog.d_maps) cudaFree(prog.d_maps);
+  if (prog.d_barrier) cudaFree(prog.d_barrier);
+  prog.d_cmds = nullptr; prog.d_maps = nullptr; prog.d_barrier = nullptr; prog.uploaded = false;
+}
+
+}  // namespace aocr

@@ -1,0 +1,69 @@
+// persist.h — the persistent recurrence executor: ONE cooperative kernel runs a whole recurrence (all timesteps of
+// the decoder forward, the decoder backward, or one encoder direction) as a command list.  Every command is either a
+// swap-AB tcgen05 GEMM (the CTA's tile of `weights x batch`, split-K partials) or one of the fused cell / attention /
+// output bodies of dec_bodies.cuh; a grid barrier separates consecutive commands.  Kernel boundaries (4-5 us each on
+// this part, ~9 per decoder step) disappear; TMEM, the mbarrier ring and the tensor-map table live for the whole
+// recurrence.  The command list is built once per (batch, S, T) shape on the host and cached on the device.
+#pragma once
+#include <vector>
+
+#include "gemm_tc.cuh"
+#include "kernels_dec.h"
+
+namespace aocr {
+
+enum PType {
+  P_GEMM = 0, P_CELL_FWD, P_DEC_OUT, P_DU, P_CELL_BWD, P_ATTN_FWD, P_ATTN_BWD, P_ENC_CELL_FWD, P_ENC_CELL_BWD, P_TO_DENSE
+};
+
+// swap-AB GEMM with the batch on the UMMA N side: partial z of out(n, m) at ws[z*part_stride + n*ldc + m]
+struct PGemm {
+  int map_a, map_b;        // index of the hi plane's tensor map in the table (lo plane = +1)
+  int m_tiles, splits, kb_per, num_kb;
+  int b_row0;              // first pack row of the activation operand (timestep * batch)
+  int b_k0;                // K offset (elements) inside the activation pack
+  int M, N, terms;
+  float* ws; long long part_stride; long long ldc;
+};
+struct PToDense { PartIn in; float* dst; long long ld; int B, cols; };
+
+struct alignas(16) PCmd {
+  int type;
+  int pad[3];
+  unsigned char payload[240];
+};
+
+struct PersistProgram {                 // host-side, then uploaded
+  std::vector<PCmd> cmds;
+  std::vector<CUtensorMap> maps;
+  int grid = 1;                         // CTAs (>= the largest number of GEMM tiles of any command)
+  int bn = 64;                          // UMMA N = batch rounded up to {16,32,64,128}
+  // device copies
+  PCmd* d_cmds = nullptr;
+  CUtensorMap* d_maps = nullptr;
+  unsigned* d_barrier = nullptr;
+  bool uploaded = false;
+
+  int add_map_pair(const CUtensorMap& hi, const CUtensorMap& lo) {
+    maps.push_back(hi); maps.push_back(lo);
+    return (int)maps.size() - 2;
+  }
+  template <typename T> void add(int type, const T& p) {
+    static_assert(sizeof(T) <= sizeof(PCmd::payload), "command payload too large");
+    PCmd c{};
+    c.type = type;
+    memcpy(c.payload, &p, sizeof(T));
+    cmds.push_back(c);
+  }
+};
+
+// plan of one swap-AB GEMM inside a program: split factor such that m_tiles * splits <= max_ctas
+struct PGemmPlan { int m_tiles, splits, kb_per, num_kb; long long part_stride; };
+PGemmPlan persist_plan_gemm(int M, int N, int K, int max_ctas, long long ws_floats);
+
+void persist_upload(Ctx& ctx, PersistProgram& prog);     // allocates + copies (once)
+void persist_launch(Ctx& ctx, PersistProgram& prog);     // cooperative launch on ctx.st
+void persist_free(PersistProgram& prog);
+int persist_max_ctas(int bn);                            // co-resident CTAs of the executor on this device
+
+}  // namespace aocr

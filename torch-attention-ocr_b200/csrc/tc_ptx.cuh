@@ -1,0 +1,103 @@
+// tc_ptx.cuh — inline-PTX wrappers for mbarrier / TMA / tcgen05 and the UMMA descriptors (sm_100a), shared by the
+// GEMM kernel (gemm_tc.cu) and the persistent recurrence executor (persist.cu).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace aocr {
+namespace tcp {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_PLANE_BYTES = BM * BK * 2;   // 16 KB
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// SM100 shared-memory matrix descriptor, K-major, 128-byte swizzle: start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 |
+// version 1 << 46 | SWIZZLE_128B (2) << 61      (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// MN-major operand (the contraction index is the OUTER, row index of the stored matrix), 128-byte swizzle:
+// a tile is a stack of [64 k-rows x 64 elements (128 B)] TMA boxes (8 KB each).  Canonical layout
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units (cute make_umma_desc<Major::MN>): SBO = 1024 B between
+// groups of 8 k-rows, LBO = 8192 B between consecutive 64-element blocks along M/N.
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (InstrDescriptor): D=f32, A=B=bf16, N>>3 at bit 17, M>>4 at bit 24, bits 15/16 = A/B MN-major
+__device__ __forceinline__ uint32_t make_idesc(int n, int mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+         (mn ? ((1u << 15) | (1u << 16)) : 0u);
+}
+
+
+}  // namespace tcp
+}  // namespace aocr
