@@ -349,7 +349,13 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     const long long r = e / cols, c = e % cols;
     const long long off = r * ldc + c;
     float v = 0.f;
-    for (int z = 0; z < nz; z++) v += ws[(long long)z * part_stride + off];
+    for (int z0 = 0; z0 < nz; z0 += 8) {     // 8 independent loads in flight, then add (fixed order)
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) t[j] = (z0 + j < nz) ? __ldcg(ws + (long long)(z0 + j) * part_stride + off) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j++) v += t[j];
+    }
     if (bias_r) v += bias_r[r];
     if (bias_c) v += bias_c[c];
     if (act == ACT_TANH) v = tanhf(v);
@@ -539,7 +545,7 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   if (ctx.tc_ws && tiles * 2 <= ctx.num_sms && p.num_kb >= 4) {
     splits = (int)(ctx.num_sms / tiles);
     if (splits > p.num_kb / 2) splits = p.num_kb / 2;
-    if (splits > 16) splits = 16;
+    if (splits > 8) splits = 8;     // consumers of deferred partials sum at most 8 (decb::kMaxSplits)
   }
   if (g.force_splits > 0 && ctx.tc_ws) splits = g.force_splits < p.num_kb ? g.force_splits : p.num_kb;
   float* wsbase = g.ws ? g.ws : ctx.tc_ws;

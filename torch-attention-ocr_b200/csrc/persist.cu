@@ -44,7 +44,8 @@ __device__ __forceinline__ const T& payload(const PCmd& c) { return *reinterpret
 
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
-persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __restrict__ maps, unsigned* barrier) {
+persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __restrict__ maps, unsigned* barrier,
+               unsigned long long* trace) {
   using C_ = PCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -83,6 +84,11 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
   for (int c = 0; c < ncmds; c++) {
     const PCmd& cmd = cmds[c];
     const int type = cmd.type;
+    if (trace && bid == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      trace[2 * c] = t;
+    }
     if (type == P_GEMM) {
       const PGemm g = payload<PGemm>(cmd);
       const int ntiles = g.m_tiles * g.splits;
@@ -199,6 +205,11 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         __syncthreads();
       }
     }
+    if (trace && bid == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      trace[2 * c + 1] = t;      // work of CTA 0 done; the barrier wait follows
+    }
     grid_sync(barrier, (unsigned)nblk, epoch);
   }
 
@@ -221,7 +232,8 @@ void launch_bn(Ctx& ctx, PersistProgram& prog) {
   int ncmds = (int)prog.cmds.size();
   const CUtensorMap* maps = prog.d_maps;
   unsigned* bar = prog.d_barrier;
-  void* args[] = {(void*)&cmds, (void*)&ncmds, (void*)&maps, (void*)&bar};
+  unsigned long long* trace = prog.d_trace;
+  void* args[] = {(void*)&cmds, (void*)&ncmds, (void*)&maps, (void*)&bar, (void*)&trace};
   AOCR_CUDA(cudaMemsetAsync(prog.d_barrier, 0, sizeof(unsigned), ctx.st));
   AOCR_CUDA(cudaLaunchCooperativeKernel((const void*)persist_kernel<BN>, dim3(prog.grid), dim3(256), args,
                                         (size_t)PCfg<BN>::kSmemBytes, ctx.st));
@@ -247,7 +259,7 @@ PGemmPlan persist_plan_gemm(int M, int N, int K, int max_ctas, long long ws_floa
   p.part_stride = (((long long)(N - 1) * M + M) + 63) & ~63LL;
   int splits = max_ctas / p.m_tiles;
   if (splits > p.num_kb / 2) splits = p.num_kb / 2;
-  if (splits > 16) splits = 16;
+  if (splits > 8) splits = 8;       // = decb::kMaxSplits (the consumers sum at most 8 partials)
   if (splits < 1) splits = 1;
   while (splits > 1 && (long long)splits * p.part_stride > ws_floats) splits--;
   p.kb_per = (p.num_kb + splits - 1) / splits;
@@ -270,6 +282,10 @@ void persist_upload(Ctx& ctx, PersistProgram& prog) {
   AOCR_CUDA(cudaMalloc(&prog.d_cmds, prog.cmds.size() * sizeof(PCmd)));
   AOCR_CUDA(cudaMalloc(&prog.d_maps, (prog.maps.size() + 1) * sizeof(CUtensorMap)));
   AOCR_CUDA(cudaMalloc(&prog.d_barrier, 256));
+  if (getenv("AOCR_PERSIST_TRACE")) {
+    AOCR_CUDA(cudaMalloc(&prog.d_trace, (prog.cmds.size() + 1) * 2 * sizeof(unsigned long long)));
+    AOCR_CUDA(cudaMemset(prog.d_trace, 0, (prog.cmds.size() + 1) * 2 * sizeof(unsigned long long)));
+  }
   AOCR_CUDA(cudaMemcpy(prog.d_cmds, prog.cmds.data(), prog.cmds.size() * sizeof(PCmd), cudaMemcpyHostToDevice));
   if (!prog.maps.empty())
     AOCR_CUDA(cudaMemcpy(prog.d_maps, prog.maps.data(), prog.maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
@@ -290,6 +306,19 @@ void persist_free(PersistProgram& prog) {
   if (prog.d_cmds) cudaFree(prog.d_cmds);
   if (prog.d_maps) cudaFree(prog.d_maps);
   if (prog.d_barrier) cudaFree(prog.d_barrier);
+  if (prog.d_trace) {   // AOCR_PERSIST_TRACE: per-command time of CTA 0 (work, then barrier wait), averaged by type
+    std::vector<unsigned long long> t(prog.cmds.size() * 2);
+    cudaMemcpy(t.data(), prog.d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    double work[16] = {0}, wait[16] = {0}; int cnt[16] = {0};
+    for (size_t c = 0; c + 1 < prog.cmds.size(); c++) {
+      int ty = prog.cmds[c].type & 15;
+      work[ty] += (double)(t[2 * c + 1] - t[2 * c]); wait[ty] += (double)(t[2 * c + 2] - t[2 * c + 1]); cnt[ty]++;
+    }
+    fprintf(stderr, "[persist trace] %zu cmds grid %d:", prog.cmds.size(), prog.grid);
+    for (int ty = 0; ty < 16; ty++) if (cnt[ty]) fprintf(stderr, " type%d n=%d work=%.2fus wait=%.2fus;", ty, cnt[ty], work[ty] / cnt[ty] / 1e3, wait[ty] / cnt[ty] / 1e3);
+    fprintf(stderr, "\n");
+    cudaFree(prog.d_trace); prog.d_trace = nullptr;
+  }
   prog.d_cmds = nullptr; prog.d_maps = nullptr; prog.d_barrier = nullptr; prog.uploaded = false;
 }
 

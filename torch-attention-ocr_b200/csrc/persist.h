@@ -42,6 +42,7 @@ struct PersistProgram {                 // host-side, then uploaded
   PCmd* d_cmds = nullptr;
   CUtensorMap* d_maps = nullptr;
   unsigned* d_barrier = nullptr;
+  unsigned long long* d_trace = nullptr;
   bool uploaded = false;
 
   int add_map_pair(const CUtensorMap& hi, const CUtensorMap& lo) {
