@@ -313,11 +313,12 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ dz, const float* __restrict__ z,
                                                            const float* __restrict__ mean, const float* __restrict__ var,
                                                            const float* __restrict__ gamma, const float* __restrict__ s1,
-                                                           const float* __restrict__ s2, int64_t R, int C, int train) {
+                                                           const float* __restrict__ s2, int64_t R, int64_t Rglobal, int C,
+                                                           int train) {
   pdl_launch_dependents();
   pdl_wait();
-  const int64_t total = R * C;
-  const float invR = 1.0f / (float)R;
+  const int64_t total = R * C;                 // local rows
+  const float invR = 1.0f / (float)Rglobal;    // statistics are over the global batch (data parallelism)
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
     float inv = rsqrtf(var[c] + BN_EPS);
@@ -450,7 +451,7 @@ void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, cons
     else { sync.fn(sync.user, dgamma, C); sync.fn(sync.user, dbeta, C); }
   }
   launch_pdl(ctx, bn_bwd_apply_kernel, dim3(grid_for(R * C, 256, ctx.num_sms)), dim3(256), 0, dz, z, mean, var, gamma, dbeta, dgamma,
-                                                                           R * sync.world, C, train);
+                                                                           R, R * sync.world, C, train);
   AOCR_CUDA(cudaGetLastError());
   if (sync.world > 1) {   // the gradient all-reduce will sum these again over ranks: pre-divide
     scale_vec(ctx, dgamma, C, 1.0f / (float)sync.world);
