@@ -61,7 +61,6 @@ void Engine::encoder_forward_steps_tc() {
   const size_t slot_bytes = (size_t)B * He * sizeof(__nv_bfloat16);
   fill_zero(ctx_, HencP[0].hi, slot_bytes); fill_zero(ctx_, HencP[0].lo, slot_bytes);
   fill_zero(ctx_, HencP[1].hi + (int64_t)S * B * He, slot_bytes); fill_zero(ctx_, HencP[1].lo + (int64_t)S * B * He, slot_bytes);
-  prof_begin(2);
   fork_to(2);
   for (int d = 0; d < 2; d++) {
     use_lane(d == 0 ? 0 : 2);
@@ -70,7 +69,6 @@ void Engine::encoder_forward_steps_tc() {
   }
   use_lane(0);
   join_from(2);
-  prof_end(2, 2.0 * 2 * S * (double)B * He * 4 * He);
 }
 
 void Engine::encoder_backward_steps_tc() {

@@ -45,7 +45,16 @@ void Engine::run_program(int kind, int nsteps, int variant) {
   }
   PersistProgram& prog = it->second;
   if (!prog.uploaded) persist_upload(ctx_, prog);
+  double flops = 0.0;
+  if (prof_on)
+    for (const PCmd& c : prog.cmds)
+      if (c.type == P_GEMM) {
+        const PGemm* g = reinterpret_cast<const PGemm*>(c.payload);
+        flops += 2.0 * g->M * (double)g->N * (double)g->num_kb * 64.0;
+      }
+  prof_begin(2);
   persist_launch(ctx_, prog);
+  prof_end(2, flops);
 }
 
 }  // namespace aocr
