@@ -41,9 +41,10 @@ def load_peaks():
     return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
-def load_traffic():
+def load_traffic(kind="gemm"):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)"""
-    p = os.path.join(ROOT, "profiles", "r01_tc_gemm_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01_persist_kernel_ncu_full.json" if kind == "persist"
+                     else "r01_tc_gemm_traffic.json")
     if os.path.exists(p):
         return json.load(open(p)).get("dram_bytes_per_launch")
     return None
@@ -278,7 +279,7 @@ def main():
                      "persist_kernel (persistent recurrence executor: decoder fwd/bwd + encoder directions, "
                      "tcgen05 GEMM tiles + fused cell/attention bodies + grid barriers; lanes overlap, shares can sum > 1)")
         roof = dict(recur if rec_ms >= gemm_ms else conv)      # the dominant kernel class of the step
-        roof["traffic"] = load_traffic()
+        roof["traffic"] = load_traffic("persist" if rec_ms >= gemm_ms else "gemm")
         roof["other_class"] = conv if rec_ms >= gemm_ms else recur
         roof["note"] = ("achieved counts every MAC once; the default bf16x3 mode issues 3 MMAs per MAC (DESIGN.md 4), "
                         "and the per-timestep GEMMs have N = batch = 64: the class is latency-bound, not tensor-bound")
