@@ -64,7 +64,7 @@ __device__ __forceinline__ void cell_fwd_tc_body(CellFwdTc p, int bid, int nblk,
   for (int64_t e = (int64_t)bid * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
     const int u = (int)(e % H);
     const int64_t b = e / H;
-    const float* ar = p.addrows + (p.rowsel ? (int64_t)(p.rowsel[b] - 1) * p.addld : 0) + u;
+    const float* ar = p.addrows + (p.rowsel ? (int64_t)(__ldcg(p.rowsel + b) - 1) * p.addld : 0) + u;
     const float i_ = sigmoidf_(part_load(p.G, b, u) + ar[0]);
     const float f_ = sigmoidf_(part_load(p.G, b, H + u) + ar[H]);
     const float o_ = sigmoidf_(part_load(p.G, b, 2 * H + u) + ar[2 * H]);
@@ -355,6 +355,78 @@ __device__ __forceinline__ void part_to_dense_body(PartIn in, float* dst, int64_
   }
 }
 
+
+// ---- generator (Linear(H,V) + log-softmax [+ NLL / dlogits]) for the rows r = bid, bid+nblk, ... ; 8 warps per row
+__device__ __forceinline__ float warp_max_(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void generator_body(const GenTc& p, int bid, int nblk, float* sm) {
+  float* zs = sm;                                   // V <= 64 logits
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  const int nv = p.H / 128, V = p.V, H = p.H;
+  for (int64_t r = bid; r < p.R; r += nblk) {
+    float4 av[ATT_MAXV];
+#pragma unroll
+    for (int i = 0; i < ATT_MAXV; i++)
+      av[i] = (i < nv) ? __ldcg(reinterpret_cast<const float4*>(p.a + r * H + lane * 4 + 128 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = warp; v < V; v += nw) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < ATT_MAXV; i++) {
+        if (i < nv) {
+          float4 w = *reinterpret_cast<const float4*>(p.W + (int64_t)v * H + lane * 4 + 128 * i);
+          dot += w.x * av[i].x + w.y * av[i].y + w.z * av[i].z + w.w * av[i].w;
+        }
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) zs[v] = dot + p.bias[v];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const float z0 = lane < V ? zs[lane] : -INFINITY;
+      const float z1 = lane + 32 < V ? zs[lane + 32] : -INFINITY;
+      const float mx = warp_max_(fmaxf(z0, z1));
+      float se = (lane < V ? expf(z0 - mx) : 0.f) + (lane + 32 < V ? expf(z1 - mx) : 0.f);
+      se = warp_sum(se);
+      const float lse = mx + logf(se);
+      const int yy = p.y ? p.y[r] - 1 : -1;
+      const float w = (p.y && yy != 0) ? 1.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int v = lane + 32 * j;
+        if (v < V) {
+          const float lp = (j == 0 ? z0 : z1) - lse;
+          p.logp[r * V + v] = lp;
+          if (p.dz) p.dz[r * V + v] = (expf(lp) - (v == yy ? 1.f : 0.f)) * w * p.inv_bn;
+          if (p.rowloss && v == yy) p.rowloss[r] = -w * lp;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+// sticky-PAD edit, argmax, score accumulate, next token (model.lua:402,448-458); one thread per batch row
+__device__ __forceinline__ void greedy_select_body(const GreedyTc& p, int bid, int nblk, float* sm) {
+  for (int b = bid * blockDim.x + threadIdx.x; b < p.B; b += nblk * blockDim.x) {
+    float* lp = p.logp + (int64_t)b * p.V;
+    float first = __ldcg(lp);
+    if (p.t > 0) {
+      const int prev = __ldcg(p.tok + b);
+      if (prev == 1 || prev == 3) { first = 0.f; lp[0] = 0.f; }
+    }
+    float best = first;
+    int bi = 0;
+    for (int v = 1; v < p.V; v++) {
+      const float x = __ldcg(lp + v);
+      if (x > best) { best = x; bi = v; }
+    }
+    p.score[b] = (p.t == 0 ? 0.0 : __ldcg(p.score + b)) + (double)best;
+    p.tok[b] = bi + 1;
+    p.labels[(int64_t)b * p.ldl + p.t] = bi + 1;
+  }
+}
 
 }  // namespace decb
 }  // namespace aocr

@@ -108,7 +108,7 @@ class Engine {
   void emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols);
   void encoder_dir_forward(int d);
   void encoder_dir_backward(int d);
-  enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4 };
+  enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4, PK_DEC_GREEDY = 6 };
   struct ProgKey { int kind, b, S, nsteps, variant; bool operator<(const ProgKey& o) const {
     return std::tie(kind, b, S, nsteps, variant) < std::tie(o.kind, o.b, o.S, o.nsteps, o.variant); } };
   std::map<ProgKey, PersistProgram> programs_;

@@ -470,12 +470,16 @@ void Engine::decode_enqueue() {
   // greedy pass
   AOCR_CUDA(cudaMemcpyAsync(tok, tgt_tb, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx_.st));  // GO row
   decoder_init();
-  for (int t = 0; t < Ld; t++) {
-    decoder_step(t, tok);
-    float* lp = logp[1] + (int64_t)t * B * V;
-    generator_fwd(ctx_, A_all + (int64_t)t * B * Hd, d_params + L.wo, d_params + L.bo, nullptr, lp, nullptr, nullptr, B,
-                  Hd, V, 1.0f);
-    greedy_select(ctx_, lp, tok, score, labels, Ld, t, B, V);
+  if (persist_on_ && cfg.gemm_mode != 2) {
+    run_program(PK_DEC_GREEDY, Ld, 0);
+  } else {
+    for (int t = 0; t < Ld; t++) {
+      decoder_step(t, tok);
+      float* lp = logp[1] + (int64_t)t * B * V;
+      generator_fwd(ctx_, A_all + (int64_t)t * B * Hd, d_params + L.wo, d_params + L.bo, nullptr, lp, nullptr, nullptr, B,
+                    Hd, V, 1.0f);
+      greedy_select(ctx_, lp, tok, score, labels, Ld, t, B, V);
+    }
   }
   // gold pass: teacher forced with the padded targets (model.lua:589-627)
   decoder_init();

@@ -27,6 +27,23 @@ void Engine::run_program(int kind, int nsteps, int variant) {
           dec_steps_ = save;
           break;
         }
+        case PK_DEC_GREEDY: {   // greedy pass: the argmax of step t feeds the embedding lookup of step t+1 (device-side)
+          const int save = dec_steps_;
+          dec_steps_ = nsteps;
+          for (int t = 0; t < nsteps; t++) {
+            decoder_step_tc(t, tok);
+            GenTc gp;
+            gp.a = A_all + (int64_t)t * b_ * Hd; gp.W = d_params + L.wo; gp.bias = d_params + L.bo; gp.y = nullptr;
+            gp.logp = logp[1] + (int64_t)t * b_ * V; gp.dz = nullptr; gp.rowloss = nullptr;
+            gp.R = b_; gp.H = Hd; gp.V = V; gp.inv_bn = 1.0f;
+            prog.add(P_GENERATOR, gp);
+            GreedyTc gs;
+            gs.logp = gp.logp; gs.tok = tok; gs.score = score; gs.labels = labels; gs.ldl = Tmax; gs.t = t; gs.B = b_; gs.V = V;
+            prog.add(P_GREEDY, gs);
+          }
+          dec_steps_ = save;
+          break;
+        }
         case PK_DEC_BWD: decoder_backward_steps_tc(); break;
         case PK_ENC_FWD0: encoder_dir_forward(0); break;
         case PK_ENC_FWD0 + 1: encoder_dir_forward(1); break;

@@ -52,6 +52,12 @@ struct AttnBwdTc {
   int B, S, H;
 };
 void attn_bwd_tc(Ctx&, const AttnBwdTc&);
+// generator + greedy selection as executor commands (greedy decode, model.lua:393-404,446-459)
+struct GenTc {
+  const float* a; const float* W; const float* bias; const int32_t* y; float* logp; float* dz; float* rowloss;
+  int R, H, V; float inv_bn;
+};
+struct GreedyTc { float* logp; int32_t* tok; double* score; int32_t* labels; long long ldl; int t, B, V; };
 inline size_t attn_smem_bytes(int S, int H) { return (size_t)(((S + 3) & ~3) + 16 + 8 * H) * sizeof(float); }
 
 }  // namespace aocr

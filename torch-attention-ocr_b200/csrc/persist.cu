@@ -103,6 +103,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
             const uint32_t tx = (uint32_t)(g.terms == 3 ? 2 : 1) * (A_PLANE_BYTES + C_::kBPlane);
             const CUtensorMap* tAh = maps + g.map_a;
             const CUtensorMap* tBh = maps + g.map_b;
+            const uint64_t pol_w = l2_policy_evict_last_frac();   // weights: re-read every timestep
             for (int i = 0; i < nkb; i++) {
               const uint32_t n = it + i;
               const int s = n % C_::kStages;
@@ -112,10 +113,10 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
               const uint32_t sb = sa + 2 * A_PLANE_BYTES;
               mbar_expect_tx(full_bar(s), tx);
               const int kc = (kb_begin + i) * BK;
-              tma_load_2d(sa, tAh, full_bar(s), kc, m0);
+              tma_load_2d_hint(sa, tAh, full_bar(s), kc, m0, pol_w);
               tma_load_2d(sb, tBh, full_bar(s), g.b_k0 + kc, g.b_row0);
               if (g.terms == 3) {
-                tma_load_2d(sa + A_PLANE_BYTES, tAh + 1, full_bar(s), kc, m0);
+                tma_load_2d_hint(sa + A_PLANE_BYTES, tAh + 1, full_bar(s), kc, m0, pol_w);
                 tma_load_2d(sb + C_::kBPlane, tBh + 1, full_bar(s), g.b_k0 + kc, g.b_row0);
               }
             }
@@ -191,6 +192,10 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
     } else if (type == P_TO_DENSE) {
       const PToDense p = payload<PToDense>(cmd);
       decb::part_to_dense_body(p.in, p.dst, p.ld, p.B, p.cols, bid, nblk, scratch);
+    } else if (type == P_GENERATOR) {
+      decb::generator_body(payload<GenTc>(cmd), bid, nblk, scratch);
+    } else if (type == P_GREEDY) {
+      decb::greedy_select_body(payload<GreedyTc>(cmd), bid, nblk, scratch);
     } else if (type == P_ATTN_FWD) {
       const AttnFwdTc p = payload<AttnFwdTc>(cmd);
       for (int b = bid; b < p.B; b += nblk) {

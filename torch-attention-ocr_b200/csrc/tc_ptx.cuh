@@ -45,6 +45,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, with an L2 cache-policy operand (createpolicy): used to keep a fraction of the streamed recurrent weights
+// resident in L2 across timesteps instead of LRU-thrashing a working set slightly larger than the cache
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last_frac() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.60;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
