@@ -17,6 +17,11 @@ for i in range(n):
 if os.environ.get("STEP_DECODE"):
     h.decode_greedy_staged(sync=True)
     print("decode done", flush=True)
+if os.environ.get("STEP_PROF"):      # AOCR_PROF_DUMP=1 prints every profiled call (class, time, work)
+    h.prof_enable(True)
+    h.train_step_staged(0.1, sync=True)
+    print("profiled step:", [h.prof_read(c) for c in range(3)], flush=True)
+    h.prof_enable(False)
 import time
 h.synchronize()
 for i in range(3):

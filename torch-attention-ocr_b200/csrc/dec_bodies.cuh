@@ -1,7 +1,7 @@
 // dec_bodies.cuh — device bodies of the fused recurrence kernels (cell / attention / output), shared by the
 // stand-alone kernels (kernels_dec.cu) and by the persistent recurrence executor (persist.cu).
 // Each body is written for a 256-thread CTA; `bid` / `nblk` are the CTA's index and the number of CTAs sharing the
-// op, `sm` is a scratch region of shared memory (attention: ((S+3)&~3) + 16 + 8*H floats).
+// op, `sm` is a scratch region of shared memory (attention: ((S+3)&~3) + 16 + 9*H floats).
 #pragma once
 #include "kernels_dec.h"
 
@@ -81,36 +81,6 @@ __device__ __forceinline__ void cell_fwd_tc_body(CellFwdTc p, int bid, int nblk,
   }
 }
 
-// a = tanh(u): the decoder output / next step's input feed
-__device__ __forceinline__ void dec_out_tc_body(DecOutTc p, int bid, int nblk, float* sm) {
-  const int H = p.H;
-  const int64_t total = (int64_t)p.B * H;
-  for (int64_t e = (int64_t)bid * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
-    const int u = (int)(e % H);
-    const int64_t b = e / H;
-    const float a = tanhf(part_load(p.U, b, u));
-    p.a_out[e] = a;
-    if (p.x_next) p.x_next[b * p.ld_next + u] = a;
-    pack_store(p.pk_next, b, u, a);
-  }
-}
-
-// du = (da_carry + da_gen) * (1 - a^2)
-__device__ __forceinline__ void du_tc_body(DuTc p, int bid, int nblk, float* sm) {
-  const int H = p.H;
-  const int64_t total = (int64_t)p.B * H;
-  for (int64_t e = (int64_t)bid * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
-    const int u = (int)(e % H);
-    const int64_t b = e / H;
-    float g = p.da_gen[e];
-    if (p.da_carry.p) g += part_load(p.da_carry, b, u);
-    const float av = p.a[e];
-    const float d = g * (1.f - av * av);
-    p.du[e] = d;
-    pack_store(p.pk, b, u, d);
-  }
-}
-
 __device__ __forceinline__ void cell_bwd_tc_body(CellBwdTc p, int bid, int nblk, float* sm) {
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
@@ -143,38 +113,47 @@ __device__ __forceinline__ void cell_bwd_tc_body(CellBwdTc p, int bid, int nblk,
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_MAXV = 8;
 
-__device__ __forceinline__ void attn_fwd_tc_body(const float* __restrict__ ctx, PartIn q,
-                                                          float* __restrict__ alpha, float* __restrict__ cv, int64_t ldcv,
-                                                          PackOut cvp, float* __restrict__ q_out, int S, int H, int bid, int nblk, float* sm) {
+// attention + output projection of batch row b (see AttnOutTc)
+__device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, float* sm) {
+  const int S = p.S, H = p.H;
   float* es = sm;
   float* wm = es + ((S + 3) & ~3);
   float* wl = wm + ATT_WARPS;
   float* accs = wl + ATT_WARPS;
-  const int b = bid, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int nv = H / 128;
-  const float* cb = ctx + (int64_t)b * S * H;
+  const float* cb = p.ctx + (int64_t)b * S * H;
+  const float* wb = p.ctxwc + (int64_t)b * S * H;
+  float* qs = accs + ATT_WARPS * H;               // the summed query, shared by the 8 warps
+  // split-K partials of [q | v] are summed ONCE per CTA (4 consecutive columns per thread), not once per warp
+  const int e4 = threadIdx.x * 4;
+  float4 vpre = make_float4(0.f, 0.f, 0.f, 0.f);  // W_c2 h2 for the 4 outputs this thread finishes
+  if (e4 < H) {
+    const float4 q4 = part_load4(p.g3, b, e4);
+    vpre = part_load4(p.g3, b, H + e4);
+    *reinterpret_cast<float4*>(qs + e4) = q4;
+    if (p.q_out) *reinterpret_cast<float4*>(p.q_out + (int64_t)b * H + e4) = q4;   // needed again by the backward
+  }
+  __syncthreads();
   float4 qv[ATT_MAXV], acc[ATT_MAXV];
 #pragma unroll
   for (int i = 0; i < ATT_MAXV; i++) {
     acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    qv[i] = (i < nv) ? part_load4(q, b, lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (q_out && warp == 0) {   // the summed query is needed again by the backward (D_ctx product)
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++)
-      if (i < nv) *reinterpret_cast<float4*>(q_out + (int64_t)b * H + lane * 4 + 128 * i) = qv[i];
+    qv[i] = (i < nv) ? *reinterpret_cast<const float4*>(qs + lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float m = -INFINITY, l = 0.f;
   for (int s = warp; s < S; s += ATT_WARPS) {
-    float4 row[ATT_MAXV];
-    float dot = 0.f;
+    float4 row[ATT_MAXV], vrow[ATT_MAXV];
 #pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++) {
+    for (int i = 0; i < ATT_MAXV; i++)
       if (i < nv) {
         row[i] = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
-        dot += row[i].x * qv[i].x + row[i].y * qv[i].y + row[i].z * qv[i].z + row[i].w * qv[i].w;
+        vrow[i] = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)s * H + lane * 4 + 128 * i));
       }
-    }
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < ATT_MAXV; i++)
+      if (i < nv) dot += row[i].x * qv[i].x + row[i].y * qv[i].y + row[i].z * qv[i].z + row[i].w * qv[i].w;
     dot = warp_sum(dot);
     if (lane == 0) es[s] = dot;
     const float mn = fmaxf(m, dot);
@@ -184,10 +163,10 @@ __device__ __forceinline__ void attn_fwd_tc_body(const float* __restrict__ ctx, 
 #pragma unroll
     for (int i = 0; i < ATT_MAXV; i++) {
       if (i < nv) {
-        acc[i].x = acc[i].x * sc + pe * row[i].x;
-        acc[i].y = acc[i].y * sc + pe * row[i].y;
-        acc[i].z = acc[i].z * sc + pe * row[i].z;
-        acc[i].w = acc[i].w * sc + pe * row[i].w;
+        acc[i].x = acc[i].x * sc + pe * vrow[i].x;
+        acc[i].y = acc[i].y * sc + pe * vrow[i].y;
+        acc[i].z = acc[i].z * sc + pe * vrow[i].z;
+        acc[i].w = acc[i].w * sc + pe * vrow[i].w;
       }
     }
     m = mn;
@@ -210,41 +189,58 @@ __device__ __forceinline__ void attn_fwd_tc_body(const float* __restrict__ ctx, 
     }
   }
   __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float s = 0.f;
+  if (e4 < H) {
+    float4 u = vpre;
 #pragma unroll
-    for (int w = 0; w < ATT_WARPS; w++) s += accs[w * H + h];
-    cv[(int64_t)b * ldcv + h] = s;
-    pack_store(cvp, b, h, s);
+    for (int w = 0; w < ATT_WARPS; w++) {
+      const float4 t = *reinterpret_cast<const float4*>(accs + w * H + e4);
+      u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
+    }
+    const float4 a = make_float4(tanhf(u.x), tanhf(u.y), tanhf(u.z), tanhf(u.w));
+    *reinterpret_cast<float4*>(p.a_out + (int64_t)b * H + e4) = a;
+    if (p.x_next) *reinterpret_cast<float4*>(p.x_next + (int64_t)b * p.ld_next + e4) = a;
+    pack_store4(p.pk_next, b, e4, a);
   }
-  for (int s = threadIdx.x; s < S; s += blockDim.x) alpha[(int64_t)b * S + s] = expf(es[s] - M) / L;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) p.alpha[(int64_t)b * S + s] = expf(es[s] - M) / L;
 }
 
-__device__ __forceinline__ void attn_bwd_tc_body(const float* __restrict__ ctx, const float* __restrict__ alpha,
-                                                          PartIn dcv, float* __restrict__ dcv_out, int64_t ld_dcv_out,
-                                                          float* __restrict__ de, float* __restrict__ dq, PackOut dqp,
-                                                          int S, int H, int bid, int nblk, float* sm) {
+// backward of attention + output projection for batch row b (see AttnDuTc)
+__device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float* sm) {
+  const int S = p.S, H = p.H;
   float* das = sm;
   float* red = das + ((S + 3) & ~3);
-  float* accs = red + 4;
-  const int b = bid, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  float* accs = red + 16;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int nv = H / 128;
-  const float* cb = ctx + (int64_t)b * S * H;
+  const float* cb = p.ctx + (int64_t)b * S * H;
+  const float* wb = p.ctxwc + (int64_t)b * S * H;
+  const float* alpha = p.alpha + (int64_t)b * S;
+  float* gs = accs + ATT_WARPS * H;               // du, shared by the 8 warps
+  const int e4 = threadIdx.x * 4;
+  if (e4 < H) {   // du once per CTA: kept for the time-batched weight gradients + first half of the next GEMM's operand
+    const int64_t e = (int64_t)b * H + e4;
+    float4 g = __ldcg(reinterpret_cast<const float4*>(p.da_gen + e));
+    if (p.da_carry.p) {
+      const float4 c = part_load4(p.da_carry, b, e4);
+      g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w;
+    }
+    const float4 av = __ldcg(reinterpret_cast<const float4*>(p.a + e));
+    g.x *= 1.f - av.x * av.x; g.y *= 1.f - av.y * av.y; g.z *= 1.f - av.z * av.z; g.w *= 1.f - av.w * av.w;
+    *reinterpret_cast<float4*>(gs + e4) = g;
+    *reinterpret_cast<float4*>(p.du_out + e) = g;
+    pack_store4(p.pk, b, e4, g);
+  }
+  __syncthreads();
   float4 gv[ATT_MAXV];
 #pragma unroll
   for (int i = 0; i < ATT_MAXV; i++)
-    gv[i] = (i < nv) ? part_load4(dcv, b, lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (warp == 0) {   // keep the summed d(context vector) for the time-batched D_ctx product
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++)
-      if (i < nv) *reinterpret_cast<float4*>(dcv_out + (int64_t)b * ld_dcv_out + lane * 4 + 128 * i) = gv[i];
-  }
+    gv[i] = (i < nv) ? *reinterpret_cast<const float4*>(gs + lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = warp; s < S; s += ATT_WARPS) {
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < ATT_MAXV; i++) {
       if (i < nv) {
-        float4 r = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
+        const float4 r = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)s * H + lane * 4 + 128 * i));
         dot += r.x * gv[i].x + r.y * gv[i].y + r.z * gv[i].z + r.w * gv[i].w;
       }
     }
@@ -254,22 +250,22 @@ __device__ __forceinline__ void attn_bwd_tc_body(const float* __restrict__ ctx, 
   __syncthreads();
   if (warp == 0) {
     float s_ = 0.f;
-    for (int s = lane; s < S; s += 32) s_ += alpha[(int64_t)b * S + s] * das[s];
+    for (int s = lane; s < S; s += 32) s_ += alpha[s] * das[s];
     s_ = warp_sum(s_);
     if (lane == 0) red[0] = s_;
   }
   __syncthreads();
   const float tot = red[0];
-  for (int s = threadIdx.x; s < S; s += blockDim.x) de[(int64_t)b * S + s] = alpha[(int64_t)b * S + s] * (das[s] - tot);
+  for (int s = threadIdx.x; s < S; s += blockDim.x) p.de[(int64_t)b * S + s] = alpha[s] * (das[s] - tot);
   float4 acc[ATT_MAXV];
 #pragma unroll
   for (int i = 0; i < ATT_MAXV; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = warp; s < S; s += ATT_WARPS) {
-    const float w = alpha[(int64_t)b * S + s] * (das[s] - tot);
+    const float w = alpha[s] * (das[s] - tot);
 #pragma unroll
     for (int i = 0; i < ATT_MAXV; i++) {
       if (i < nv) {
-        float4 r = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
+        const float4 r = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
         acc[i].x = fmaf(w, r.x, acc[i].x); acc[i].y = fmaf(w, r.y, acc[i].y);
         acc[i].z = fmaf(w, r.z, acc[i].z); acc[i].w = fmaf(w, r.w, acc[i].w);
       }
@@ -279,12 +275,15 @@ __device__ __forceinline__ void attn_bwd_tc_body(const float* __restrict__ ctx, 
   for (int i = 0; i < ATT_MAXV; i++)
     if (i < nv) *reinterpret_cast<float4*>(accs + warp * H + lane * 4 + 128 * i) = acc[i];
   __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float s = 0.f;
+  if (e4 < H) {
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < ATT_WARPS; w++) s += accs[w * H + h];
-    dq[(int64_t)b * H + h] = s;
-    pack_store(dqp, b, h, s);
+    for (int w = 0; w < ATT_WARPS; w++) {
+      const float4 t = *reinterpret_cast<const float4*>(accs + w * H + e4);
+      u.x += t.x; u.y += t.y; u.z += t.z; u.w += t.w;
+    }
+    *reinterpret_cast<float4*>(p.dq + (int64_t)b * H + e4) = u;
+    pack_store4(p.pk, b, H + e4, u);
   }
 }
 

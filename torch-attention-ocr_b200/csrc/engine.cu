@@ -159,11 +159,11 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     // tensor-core decoder path (engine_dec_tc.cu)
     const int64_t Hd_ = 2 * c.encoder_num_hidden, K1_ = c.input_feed ? 2 * Hd_ : Hd_, Tm = c.max_decoder_l;
     Wcat1p = alloc_pack(4 * Hd_, K1_); Wcat2p = alloc_pack(4 * Hd_, 2 * Hd_);
-    Wap = alloc_pack(Hd_, Hd_); Wcp = alloc_pack(Hd_, 2 * Hd_);
+    W3p = alloc_pack(2 * Hd_, Hd_);
     Wcat1Tp = alloc_pack(K1_, 4 * Hd_); Wcat2Tp = alloc_pack(2 * Hd_, 4 * Hd_);
-    WaTp = alloc_pack(Hd_, Hd_); WcTp = alloc_pack(2 * Hd_, Hd_);
-    X1p = alloc_pack(Tm * B, K1_); X2p = alloc_pack(Tm * B, 2 * Hd_); CATp = alloc_pack(Tm * B, 2 * Hd_);
-    dUp = alloc_pack(B, Hd_); dQp = alloc_pack(B, Hd_); dG2p = alloc_pack(B, 4 * Hd_); dG1p = alloc_pack(B, 4 * Hd_);
+    W3Tp = alloc_pack(Hd_, 2 * Hd_);
+    X1p = alloc_pack(Tm * B, K1_); X2p = alloc_pack(Tm * B, 2 * Hd_); H2p = alloc_pack(Tm * B, Hd_);
+    dUQp = alloc_pack(B, 2 * Hd_); dG2p = alloc_pack(B, 4 * Hd_); dG1p = alloc_pack(B, 4 * Hd_);
     dec_ws_floats = (int64_t)16 * B * 4 * Hd_ + 1024;
     for (int i = 0; i < 4; i++) dec_ws[i] = alloc<float>(dec_ws_floats);
     // tensor-core encoder recurrence (engine_enc_tc.cu)
@@ -209,6 +209,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   dZ = alloc<float>(T * B * V); rowloss = alloc<float>(T * B); dAgen = alloc<float>(T * B * Hd);
   dU = alloc<float>(T * B * Hd); dCAT = alloc<float>(T * B * 2 * Hd); DE = alloc<float>(T * B * S);
   dQ = alloc<float>(T * B * Hd); dH2q = alloc<float>(B * Hd);
+  CtxWc = alloc<float>(B * S * Hd); dCtxWc = alloc<float>(B * S * Hd);
   dG2 = alloc<float>(T * B * 4 * Hd); dG1 = alloc<float>(T * B * 4 * Hd);
   dX2 = alloc<float>(B * 2 * Hd); dX1 = alloc<float>(B * K1);
   dc1 = alloc<float>(B * Hd); dc2 = alloc<float>(B * Hd); dP = alloc<float>((int64_t)V * 4 * Hd);
@@ -396,6 +397,9 @@ void Engine::prof_collect() {
     if (prof_recs_[i].second < 0) continue;
     float ms = 0.f;
     AOCR_CUDA(cudaEventElapsedTime(&ms, prof_pool_[2 * i], prof_pool_[2 * i + 1]));
+    if (prof_dump_)
+      fprintf(stderr, "[aocr prof] #%zu class %d  %.1f us  %.3f GFLOP(or GB)  -> %.1f T/s\n", i, prof_recs_[i].first, ms * 1e3,
+              prof_recs_[i].second * 1e-9, prof_recs_[i].second / (ms * 1e-3) * 1e-12);
     prof_ms[prof_recs_[i].first] += ms;
     prof_launches[prof_recs_[i].first] += 1;
     prof_work[prof_recs_[i].first] += prof_recs_[i].second;

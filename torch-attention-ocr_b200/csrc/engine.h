@@ -94,6 +94,7 @@ class Engine {
   void encoder_forward();
   void encoder_backward();
   void decoder_init();
+  void attention_precompute();
   void decoder_step(int t, const int32_t* tok);
   void decoder_backward();
   void decoder_step_simt(int t, const int32_t* tok);
@@ -103,8 +104,8 @@ class Engine {
   void build_decoder_packs();
   // emitters: launch a piece of a recurrence as its own kernel, or record it into a persistent program
   TcOut emit_gemm(const Pack& W, int M, const Pack& X, int64_t row0, int64_t k0, int K, float* ws);
-  void emit(const CellFwdTc& p); void emit(const DecOutTc& p); void emit(const DuTc& p); void emit(const CellBwdTc& p);
-  void emit(const EncCellFwdTc& p); void emit(const EncCellBwdTc& p); void emit(const AttnFwdTc& p); void emit(const AttnBwdTc& p);
+  void emit(const CellFwdTc& p); void emit(const CellBwdTc& p);
+  void emit(const EncCellFwdTc& p); void emit(const EncCellBwdTc& p); void emit(const AttnOutTc& p); void emit(const AttnDuTc& p);
   void emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols);
   void encoder_dir_forward(int d);
   void encoder_dir_backward(int d);
@@ -157,6 +158,7 @@ class Engine {
   std::vector<cudaEvent_t> prof_pool_;
   std::vector<std::pair<int, double>> prof_recs_;
   size_t prof_used_ = 0;
+  bool prof_dump_ = getenv("AOCR_PROF_DUMP") != nullptr;   // print every profiled call (class, time, work)
   std::vector<size_t> prof_open_;
 
   int device_;
@@ -165,8 +167,8 @@ class Engine {
   int64_t weights_version_ = 0;
   Pack scratch_[2];
   // tensor-core decoder path: concatenated weight packs, per-step operand packs, split-K partial regions
-  Pack Wcat1p, Wcat2p, Wap, Wcp, Wcat1Tp, Wcat2Tp, WaTp, WcTp;
-  Pack X1p, X2p, CATp, dUp, dQp, dG2p, dG1p;
+  Pack Wcat1p, Wcat2p, W3p, Wcat1Tp, Wcat2Tp, W3Tp;   // W3 = [W_a ; W_c[:, H:]] (rows), W3T = its transpose
+  Pack X1p, X2p, H2p, dUQp, dG2p, dG1p;
   Pack Whp[2], WhTp[2], HencP[2], dGeP[2];
   float* dec_ws[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t dec_ws_floats = 0;
@@ -200,7 +202,7 @@ class Engine {
         *Gs = nullptr;
   float *logp[3] = {}, *dZ = nullptr, *rowloss = nullptr, *dAgen = nullptr, *dU = nullptr, *dCAT = nullptr,
         *DE = nullptr, *dQ = nullptr, *dH2q = nullptr, *dG2 = nullptr, *dG1 = nullptr, *dX2 = nullptr, *dX1 = nullptr,
-        *dc1 = nullptr, *dc2 = nullptr, *dP = nullptr;
+        *dc1 = nullptr, *dc2 = nullptr, *dP = nullptr, *CtxWc = nullptr, *dCtxWc = nullptr;
   int32_t *tok = nullptr, *labels = nullptr;
   double *score = nullptr, *d_loss = nullptr, *d_sumsq = nullptr, *d_sq_partial = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

@@ -215,6 +215,15 @@ void Engine::decoder_backward() {
   } else {
     decoder_backward_steps_simt();
   }
+  const bool tc = cfg.gemm_mode != 2;
+  if (tc) {   // dctxwc[b,s,:] = sum_t alpha_t[b,s] du_t[b,:]: feeds both D_ctx (lane 0) and dW_c[:, :H] (lane 1)
+    g = Gemm();
+    g.M = S; g.N = Hd; g.K = T; g.batch = B;
+    g.A = ALPHA; g.sam = 1; g.sak = (int64_t)B * S; g.bsa = S;
+    g.B = dU; g.sbk = (int64_t)B * Hd; g.sbn = 1; g.bsb = Hd;
+    g.C = dCtxWc; g.ldc = Hd; g.bsc = (int64_t)S * Hd;
+    gemm(g);
+  }
   // the time-batched parameter gradients below depend only on the saved per-step tensors: lane 1, concurrently
   // with D_ctx + the encoder/CNN backward that continue on lane 0
   fork_to(1);
@@ -228,7 +237,19 @@ void Engine::decoder_backward() {
     w.C = dW; w.ldc = ldw;
     gemm(w);
   };
-  wgrad(dU, Hd, CAT, 2 * Hd, 2 * Hd, d_grads + L.wc, 2 * Hd);
+  if (!tc) {
+    wgrad(dU, Hd, CAT, 2 * Hd, 2 * Hd, d_grads + L.wc, 2 * Hd);
+  } else {
+    // the tensor-core path never forms cv_t (engine_dec_tc.cu): dW_c[:, H:] = dU^T H2, and dW_c[:, :H] from dctxwc
+    // (dW_c1 = sum_t du_t^T cv_t re-associated over source positions)
+    wgrad(dU, Hd, CAT + Hd, 2 * Hd, Hd, d_grads + L.wc + Hd, 2 * Hd);
+    g = Gemm();                                           // dW_c[:, :H] = dctxwc^T ctx   (K = B*S)
+    g.M = Hd; g.N = Hd; g.K = B * S;
+    g.A = dCtxWc; g.sam = 1; g.sak = Hd;
+    g.B = ctx; g.sbk = Hd; g.sbn = 1;
+    g.C = d_grads + L.wc; g.ldc = 2 * Hd;
+    gemm(g);
+  }
   wgrad(dQ, Hd, CAT + Hd, 2 * Hd, Hd, d_grads + L.wa, Hd);
   wgrad(dG2, 4 * Hd, X2, 2 * Hd, Hd, d_grads + L.l2_wi, Hd);
   wgrad(dG2, 4 * Hd, X2 + Hd, 2 * Hd, Hd, d_grads + L.l2_wh, Hd);
@@ -264,14 +285,24 @@ void Engine::decoder_backward() {
   // D_ctx[b] = sum_t alpha_t[b]^T dcv_t[b] + de_t[b]^T q_t[b]   (replaces the per-step RMW of model.lua:652-653)
   g = Gemm();
   g.M = S; g.N = Hd; g.K = T; g.batch = B;
-  g.A = ALPHA; g.sam = 1; g.sak = (int64_t)B * S; g.bsa = S;
-  g.B = dCAT; g.sbk = (int64_t)B * 2 * Hd; g.sbn = 1; g.bsb = 2 * Hd;
+  g.A = DE; g.sam = 1; g.sak = (int64_t)B * S; g.bsa = S;
+  g.B = Q; g.sbk = (int64_t)B * Hd; g.sbn = 1; g.bsb = Hd;
   g.C = Dctx; g.ldc = Hd; g.bsc = (int64_t)S * Hd;
   gemm(g);
-  g.A = DE;
-  g.B = Q; g.sbk = (int64_t)B * Hd; g.bsb = Hd;
-  g.accumulate = 1;
-  gemm(g);
+  if (!tc) {
+    g.A = ALPHA;
+    g.B = dCAT; g.sbk = (int64_t)B * 2 * Hd; g.bsb = 2 * Hd;
+    g.accumulate = 1;
+    gemm(g);
+  } else {
+    // sum_t alpha^T dcv_t = (sum_t alpha^T du_t) W_c[:, :H] = dctxwc W_c1
+    g = Gemm();
+    g.M = B * S; g.N = Hd; g.K = Hd;
+    g.A = dCtxWc; g.sam = Hd; g.sak = 1;
+    g.B = d_params + L.wc; g.sbk = 2 * Hd; g.sbn = 1;
+    g.C = Dctx; g.ldc = Hd; g.accumulate = 1;
+    gemm(g);
+  }
   taps_["dctx"] = {Dctx, (int64_t)B * S * Hd};
 }
 
@@ -313,6 +344,7 @@ void Engine::forward_backward_enqueue() {
   cnn_forward(true);
   phase_mark("cnn_fwd");
   encoder_forward();
+  attention_precompute();
   phase_mark("enc_fwd");
   decoder_init();
   dec_steps_ = T;
@@ -466,6 +498,7 @@ void Engine::decode_enqueue() {
   gather_tokens(ctx_, tev_bt, tev_tb, B, T, Ld, 1);
   cnn_forward(false);
   encoder_forward();
+  attention_precompute();
   dec_steps_ = Ld;
   // greedy pass
   AOCR_CUDA(cudaMemcpyAsync(tok, tgt_tb, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx_.st));  // GO row

@@ -1,7 +1,8 @@
-// engine_dec_tc.cu — the decoder schedule on tensor cores (gemm_mode 0/1).  Per timestep: four tcgen05 GEMMs
-// (layer-1 gates, layer-2 gates, attention query, output projection), each followed by ONE memory-bound
-// body that sums the GEMM's split-K partials, applies the cell / attention / tanh math and writes the next
-// GEMM's operand as bf16 planes.  Weights are concatenated along K ([W_i | W_h]) so a cell needs one GEMM,
+// engine_dec_tc.cu — the decoder schedule on tensor cores (gemm_mode 0/1).  Per timestep: three tcgen05 GEMMs
+// (layer-1 gates, layer-2 gates, attention query + h2 half of the output projection), each followed by ONE
+// memory-bound body that sums the GEMM's split-K partials, applies the cell / attention+output math and writes
+// the next GEMM's operand as bf16 planes.  The context half of the output projection is time-independent per
+// source position and is precomputed once per batch (attention_precompute).  Weights are concatenated along K ([W_i | W_h]) so a cell needs one GEMM,
 // and the batch rides the UMMA N dimension (swap-AB) so the 128-row M tile is filled by weight rows.
 // The same step functions either LAUNCH each piece as its own kernel or RECORD it into the command list of the
 // persistent recurrence executor (persist.cu), which then runs the whole recurrence as one cooperative kernel.
@@ -63,21 +64,19 @@ TcOut Engine::emit_gemm(const Pack& W, int M, const Pack& X, int64_t row0, int64
   return o;
 }
 void Engine::emit(const CellFwdTc& p) { if (rec_) rec_->add(P_CELL_FWD, p); else cell_fwd_tc(ctx_, p); }
-void Engine::emit(const DecOutTc& p) { if (rec_) rec_->add(P_DEC_OUT, p); else dec_out_tc(ctx_, p); }
-void Engine::emit(const DuTc& p) { if (rec_) rec_->add(P_DU, p); else du_tc(ctx_, p); }
 void Engine::emit(const CellBwdTc& p) { if (rec_) rec_->add(P_CELL_BWD, p); else cell_bwd_tc(ctx_, p); }
 void Engine::emit(const EncCellFwdTc& p) { if (rec_) rec_->add(P_ENC_CELL_FWD, p); else enc_cell_fwd_tc(ctx_, p); }
 void Engine::emit(const EncCellBwdTc& p) { if (rec_) rec_->add(P_ENC_CELL_BWD, p); else enc_cell_bwd_tc(ctx_, p); }
-void Engine::emit(const AttnFwdTc& p) {
-  if (rec_) { rec_->add(P_ATTN_FWD, p); return; }
+void Engine::emit(const AttnOutTc& p) {
+  if (rec_) { rec_->add(P_ATTN_OUT, p); return; }
   prof_begin(1);
-  attn_fwd_tc(ctx_, p);
-  prof_end(1, (double)p.B * p.S * p.H * 4 + (double)p.B * (2.0 * p.H + p.S) * 4);
+  attn_out_tc(ctx_, p);
+  prof_end(1, 2.0 * p.B * p.S * p.H * 4 + (double)p.B * (3.0 * p.H + p.S) * 4);
 }
-void Engine::emit(const AttnBwdTc& p) {
-  if (rec_) { rec_->add(P_ATTN_BWD, p); return; }
+void Engine::emit(const AttnDuTc& p) {
+  if (rec_) { rec_->add(P_ATTN_DU, p); return; }
   prof_begin(1);
-  attn_bwd_tc(ctx_, p);
+  attn_du_tc(ctx_, p);
   prof_end(1, 2.0 * p.B * p.S * p.H * 4);
 }
 void Engine::emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols) {
@@ -100,21 +99,33 @@ void Engine::build_decoder_packs() {
   split_to_pack(ctx_, P + L.l1_wh, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat1p, h1off), Hd);
   split_to_pack(ctx_, P + L.l2_wi, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat2p, 0), Hd);
   split_to_pack(ctx_, P + L.l2_wh, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat2p, Hd), Hd);
-  split_to_pack(ctx_, P + L.wa, Hd, Hd, Hd, 1, Wap);
-  split_to_pack(ctx_, P + L.wc, Hd, 2 * Hd, 2 * Hd, 1, Wcp);
+  split_to_pack(ctx_, P + L.wa, Hd, Hd, Hd, 1, sub_rows(W3p, 0, Hd));                 // rows 0..H-1   : W_a
+  split_to_pack(ctx_, P + L.wc + Hd, Hd, Hd, 2 * Hd, 1, sub_rows(W3p, Hd, Hd));        // rows H..2H-1  : W_c[:, H:]
   // backward packs: rows = input units, K = output units (transposes)
   if (cfg.input_feed) split_to_pack(ctx_, P + L.l1_wi + E, Hd, 4 * Hd, 1, in1, sub_rows(Wcat1Tp, 0, Hd));
   split_to_pack(ctx_, P + L.l1_wh, Hd, 4 * Hd, 1, Hd, sub_rows(Wcat1Tp, h1off, Hd));
   split_to_pack(ctx_, P + L.l2_wi, Hd, 4 * Hd, 1, Hd, sub_rows(Wcat2Tp, 0, Hd));
   split_to_pack(ctx_, P + L.l2_wh, Hd, 4 * Hd, 1, Hd, sub_rows(Wcat2Tp, Hd, Hd));
-  split_to_pack(ctx_, P + L.wa, Hd, Hd, 1, Hd, WaTp);
-  split_to_pack(ctx_, P + L.wc, 2 * Hd, Hd, 1, 2 * Hd, WcTp);
+  split_to_pack(ctx_, P + L.wc + Hd, Hd, Hd, 1, 2 * Hd, sub_cols(W3Tp, 0), Hd);        // K 0..H-1  : W_c[:, H:]^T (du)
+  split_to_pack(ctx_, P + L.wa, Hd, Hd, 1, Hd, sub_cols(W3Tp, Hd), Hd);                // K H..2H-1 : W_a^T        (dq)
   dec_packs_version_ = weights_version_;
 }
 
-// One decoder step.  Saved fp32 state (for backward) has the layout of the SIMT path:
-//   X1[t] = [a_{t-1} | h1_{t-1}]   X2[t] = [h1_t | h2_{t-1}]   CAT[t] = [cv_t | h2_t]   A_all[t] = a_t
-// and X1p / X2p / CATp mirror them as bf16 planes (written by the producing bodies, never by a conversion pass).
+// Time-independent half of the output projection: ctxwc[b,s,:] = W_c[:, :H] ctx[b,s,:]  (see AttnOutTc)
+void Engine::attention_precompute() {
+  if (cfg.gemm_mode == 2) return;
+  Gemm g;
+  g.M = b_ * S_; g.N = Hd; g.K = Hd;
+  g.A = ctx; g.sam = Hd; g.sak = 1;
+  g.B = d_params + L.wc; g.sbk = 1; g.sbn = 2 * Hd;
+  g.C = CtxWc; g.ldc = Hd;
+  gemm(g);
+}
+
+// One decoder step.  Saved fp32 state (for backward) has the layout of the SIMT path, minus the context vector:
+//   X1[t] = [a_{t-1} | h1_{t-1}]   X2[t] = [h1_t | h2_{t-1}]   CAT[t] = [ - | h2_t]   A_all[t] = a_t   Q[t] = W_a h2_t
+// and X1p / X2p / H2p mirror them as bf16 planes (written by the producing bodies, never by a conversion pass).
+// Three GEMMs + three bodies per step: gates1 -> cell1 -> gates2 -> cell2 -> [q ; v] = [W_a ; W_c2] h2 -> attention+output.
 void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   const int B = b_, S = S_;
   const int nsteps = dec_steps_;
@@ -143,27 +154,22 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   c2.acts = ACT2 + (int64_t)t * B * 4 * Hd;
   c2.h_out0 = cat + Hd; c2.ld0 = 2 * Hd;
   c2.h_out1 = has_next ? x2 + (int64_t)B * 2 * Hd + Hd : nullptr; c2.ld1 = 2 * Hd;
-  c2.pk0 = pack_out(CATp, r0, Hd);
+  c2.pk0 = pack_out(H2p, r0, 0);
   c2.pk1 = has_next ? pack_out(X2p, r1, Hd) : PackOut();
   c2.B = B; c2.H = Hd;
   emit(c2);
-  // ---- attention: q = W_a h2 (operand = second half of CATp[t]), fused score/softmax/context body
-  TcOut qo = emit_gemm(Wap, Hd, CATp, r0, Hd, Hd, dec_ws[2]);
-  AttnFwdTc af;
-  af.ctx = ctx; af.q = part_in(qo, Hd); af.alpha = ALPHA + (int64_t)t * B * S; af.cv = cat; af.ldcv = 2 * Hd;
-  af.cvp = pack_out(CATp, r0, 0); af.q_out = Q + (int64_t)t * B * Hd; af.B = B; af.S = S; af.H = Hd;
-  emit(af);
-  // ---- a_t = tanh(W_c [cv ; h2])
-  TcOut uo = emit_gemm(Wcp, Hd, CATp, r0, 0, 2 * Hd, dec_ws[3]);
-  DecOutTc d;
-  d.U = part_in(uo, Hd); d.a_out = A_all + (int64_t)t * B * Hd;
-  d.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; d.ld_next = K1;
-  d.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();
-  d.B = B; d.H = Hd;
-  emit(d);
+  // ---- [q ; v] = [W_a ; W_c2] h2, then scores / softmax / alpha-weighted ctxwc + v / tanh in one body
+  TcOut g3 = emit_gemm(W3p, 2 * Hd, H2p, r0, 0, Hd, dec_ws[2]);
+  AttnOutTc ao;
+  ao.ctx = ctx; ao.ctxwc = CtxWc; ao.g3 = part_in(g3, 2 * Hd);
+  ao.alpha = ALPHA + (int64_t)t * B * S; ao.q_out = Q + (int64_t)t * B * Hd; ao.a_out = A_all + (int64_t)t * B * Hd;
+  ao.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; ao.ld_next = K1;
+  ao.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();
+  ao.B = B; ao.S = S; ao.H = Hd;
+  emit(ao);
 }
 
-// per-timestep part of the decoder backward (model.lua:643-661) on tensor cores
+// per-timestep part of the decoder backward (model.lua:643-661) on tensor cores: three bodies + three GEMMs per step
 void Engine::decoder_backward_steps_tc() {
   const int B = b_, S = S_, T = T_;
   if (!rec_) {
@@ -173,25 +179,20 @@ void Engine::decoder_backward_steps_tc() {
   TcOut dx1, dx2;   // carries of the previous (t+1) iteration; valid when !last
   for (int t = T - 1; t >= 0; t--) {
     const bool last = (t == T - 1);
-    // du = (da_prev + W_o^T dz) * (1 - a^2)
-    DuTc du;
-    du.da_carry = (!last && cfg.input_feed) ? part_in(dx1, K1, 0) : PartIn();
-    du.da_gen = dAgen + (int64_t)t * B * Hd; du.a = A_all + (int64_t)t * B * Hd;
-    du.du = dU + (int64_t)t * B * Hd; du.pk = pack_out(dUp, 0, 0); du.B = B; du.H = Hd;
-    emit(du);
-    // d[cv ; h2] = du W_c
-    TcOut dcat = emit_gemm(WcTp, 2 * Hd, dUp, 0, 0, Hd, dec_ws[0]);
-    AttnBwdTc ab;
-    ab.ctx = ctx; ab.alpha = ALPHA + (int64_t)t * B * S; ab.dcv = part_in(dcat, 2 * Hd, 0);
-    ab.dcv_out = dCAT + (int64_t)t * B * 2 * Hd; ab.ld_dcv_out = 2 * Hd; ab.de = DE + (int64_t)t * B * S;
-    ab.dq = dQ + (int64_t)t * B * Hd; ab.dqp = pack_out(dQp, 0, 0); ab.B = B; ab.S = S; ab.H = Hd;
-    emit(ab);
-    // dh2 += dq W_a
-    TcOut dh2q = emit_gemm(WaTp, Hd, dQp, 0, 0, Hd, dec_ws[1]);
+    // du = (da_prev + W_o^T dz) (1 - a^2); attention backward -> [du | dq]
+    AttnDuTc ad;
+    ad.ctx = ctx; ad.ctxwc = CtxWc; ad.alpha = ALPHA + (int64_t)t * B * S;
+    ad.da_carry = (!last && cfg.input_feed) ? part_in(dx1, K1, 0) : PartIn();
+    ad.da_gen = dAgen + (int64_t)t * B * Hd; ad.a = A_all + (int64_t)t * B * Hd;
+    ad.du_out = dU + (int64_t)t * B * Hd; ad.de = DE + (int64_t)t * B * S; ad.dq = dQ + (int64_t)t * B * Hd;
+    ad.pk = pack_out(dUQp, 0, 0); ad.B = B; ad.S = S; ad.H = Hd;
+    emit(ad);
+    // dh2 (through the output projection and the query) = [du | dq] [W_c2 ; W_a]
+    TcOut dh2 = emit_gemm(W3Tp, Hd, dUQp, 0, 0, 2 * Hd, dec_ws[1]);
     CellBwdTc b2;
-    b2.dh_a = part_in(dcat, 2 * Hd, Hd);
-    b2.dh_b = part_in(dh2q, Hd, 0);
-    b2.dh_c = last ? PartIn() : part_in(dx2, 2 * Hd, Hd);
+    b2.dh_a = part_in(dh2, Hd, 0);
+    b2.dh_b = last ? PartIn() : part_in(dx2, 2 * Hd, Hd);
+    b2.dh_c = PartIn();
     b2.dc = dc2; b2.c_prev = C2 + (int64_t)t * B * Hd; b2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
     b2.acts = ACT2 + (int64_t)t * B * 4 * Hd; b2.dG = dG2 + (int64_t)t * B * 4 * Hd; b2.pk = pack_out(dG2p, 0, 0);
     b2.B = B; b2.H = Hd;

@@ -21,24 +21,21 @@ inline int grid_for(int64_t total, int threads, int num_sms) {
     decb::NAME##_body(p, (int)blockIdx.x, (int)gridDim.x, nullptr);                \
   }
 AOCR_WRAP(cell_fwd_tc, CellFwdTc)
-AOCR_WRAP(dec_out_tc, DecOutTc)
-AOCR_WRAP(du_tc, DuTc)
 AOCR_WRAP(cell_bwd_tc, CellBwdTc)
 AOCR_WRAP(enc_cell_fwd_tc, EncCellFwdTc)
 AOCR_WRAP(enc_cell_bwd_tc, EncCellBwdTc)
 
-__global__ void __launch_bounds__(256) attn_fwd_tc_kernel(AttnFwdTc p) {
+__global__ void __launch_bounds__(256) attn_out_tc_kernel(AttnOutTc p) {
   extern __shared__ float sm[];
   pdl_launch_dependents();
   pdl_wait();
-  decb::attn_fwd_tc_body(p.ctx, p.q, p.alpha, p.cv, p.ldcv, p.cvp, p.q_out, p.S, p.H, (int)blockIdx.x, (int)gridDim.x, sm);
+  decb::attn_out_tc_body(p, (int)blockIdx.x, sm);
 }
-__global__ void __launch_bounds__(256) attn_bwd_tc_kernel(AttnBwdTc p) {
+__global__ void __launch_bounds__(256) attn_du_tc_kernel(AttnDuTc p) {
   extern __shared__ float sm[];
   pdl_launch_dependents();
   pdl_wait();
-  decb::attn_bwd_tc_body(p.ctx, p.alpha, p.dcv, p.dcv_out, p.ld_dcv_out, p.de, p.dq, p.dqp, p.S, p.H, (int)blockIdx.x,
-                         (int)gridDim.x, sm);
+  decb::attn_du_tc_body(p, (int)blockIdx.x, sm);
 }
 __global__ void part_to_dense_kernel(PartIn in, float* dst, int64_t ld, int B, int cols) {
   pdl_launch_dependents();
@@ -58,19 +55,18 @@ void part_to_dense(Ctx& ctx, const PartIn& in, float* dst, int64_t ld, int B, in
     AOCR_CUDA(cudaGetLastError());                                                                           \
   }
 AOCR_LAUNCH_EW(cell_fwd_tc, CellFwdTc, (int64_t)p.B * p.H)
-AOCR_LAUNCH_EW(dec_out_tc, DecOutTc, (int64_t)p.B * p.H)
-AOCR_LAUNCH_EW(du_tc, DuTc, (int64_t)p.B * p.H)
 AOCR_LAUNCH_EW(cell_bwd_tc, CellBwdTc, (int64_t)p.B * p.H)
 AOCR_LAUNCH_EW(enc_cell_fwd_tc, EncCellFwdTc, (int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He)
 AOCR_LAUNCH_EW(enc_cell_bwd_tc, EncCellBwdTc, (int64_t)(p.d_only < 0 ? 2 : 1) * p.B * p.He)
 
-void attn_fwd_tc(Ctx& ctx, const AttnFwdTc& p) {
+void attn_out_tc(Ctx& ctx, const AttnOutTc& p) {
   AOCR_CHECK(p.H % 128 == 0 && p.H <= 1024, "attention kernel needs decoder hidden size in {128,...,1024}");
-  launch_pdl(ctx, attn_fwd_tc_kernel, dim3(p.B), dim3(256), attn_smem_bytes(p.S, p.H), p);
+  launch_pdl(ctx, attn_out_tc_kernel, dim3(p.B), dim3(256), attn_smem_bytes(p.S, p.H), p);
   AOCR_CUDA(cudaGetLastError());
 }
-void attn_bwd_tc(Ctx& ctx, const AttnBwdTc& p) {
-  launch_pdl(ctx, attn_bwd_tc_kernel, dim3(p.B), dim3(256), attn_smem_bytes(p.S, p.H), p);
+void attn_du_tc(Ctx& ctx, const AttnDuTc& p) {
+  AOCR_CHECK(p.H % 128 == 0 && p.H <= 1024, "attention kernel needs decoder hidden size in {128,...,1024}");
+  launch_pdl(ctx, attn_du_tc_kernel, dim3(p.B), dim3(256), attn_smem_bytes(p.S, p.H), p);
   AOCR_CUDA(cudaGetLastError());
 }
 

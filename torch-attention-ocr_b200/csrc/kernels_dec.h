@@ -19,16 +19,6 @@ struct CellFwdTc {
 };
 void cell_fwd_tc(Ctx&, const CellFwdTc&);
 
-struct DecOutTc {
-  PartIn U; float* a_out; float* x_next; int64_t ld_next; PackOut pk_next; int B, H;
-};
-void dec_out_tc(Ctx&, const DecOutTc&);
-
-struct DuTc {
-  PartIn da_carry; const float* da_gen; const float* a; float* du; PackOut pk; int B, H;
-};
-void du_tc(Ctx&, const DuTc&);
-
 struct CellBwdTc {
   PartIn dh_a, dh_b, dh_c;                    // summed; p == nullptr: absent
   float* dc; const float* c_prev; const float* c_new; const float* acts;
@@ -40,25 +30,37 @@ void cell_bwd_tc(Ctx&, const CellBwdTc&);
 // dst[b*ld + j] = value(b, j): materialise a split result (used once per step for the encoder seeds)
 void part_to_dense(Ctx&, const PartIn& in, float* dst, int64_t ld, int B, int cols);
 
-struct AttnFwdTc {
-  const float* ctx; PartIn q; float* alpha; float* cv; int64_t ldcv; PackOut cvp;
-  float* q_out;        // dense copy of the summed query (needed by the backward), may be null
+// Attention + decoder output of one step in ONE body.  The output projection W_c [cv ; h2] is split as
+//   W_c1 cv + W_c2 h2 = sum_s alpha_s (W_c1 ctx_s) + W_c2 h2,
+// with ctxwc = ctx W_c1^T precomputed once per batch (time-independent) and [q ; v] = [W_a ; W_c2] h2 from one GEMM:
+// scores, softmax, the alpha-weighted sum of ctxwc rows, + v, tanh.  (model.lua:553-568 / LSTM.lua:124-162 math,
+// re-associated; removes one GEMM and one pointwise pass per step.)
+struct AttnOutTc {
+  const float* ctx; const float* ctxwc;       // (B, S, H) each
+  PartIn g3;                                  // (B, 2H): [q | v] split-K partials
+  float* alpha; float* q_out;                 // (B, S), (B, H) saved for backward
+  float* a_out;                               // (B, H) a_t
+  float* x_next; int64_t ld_next; PackOut pk_next;   // input feed of step t+1 (may be null)
   int B, S, H;
 };
-void attn_fwd_tc(Ctx&, const AttnFwdTc&);
-struct AttnBwdTc {
-  const float* ctx; const float* alpha; PartIn dcv; float* dcv_out; int64_t ld_dcv_out;
-  float* de; float* dq; PackOut dqp;
+void attn_out_tc(Ctx&, const AttnOutTc&);
+// Backward of the same: du = (da_gen + da_carry) (1 - a^2);  d alpha_s = ctxwc_s . du;  de = softmax backward;
+// dq = sum_s de_s ctx_s.  Writes [du | dq] as the operand of the [W_c2 ; W_a]^T GEMM.
+struct AttnDuTc {
+  const float* ctx; const float* ctxwc; const float* alpha;
+  PartIn da_carry; const float* da_gen; const float* a;
+  float* du_out; float* de; float* dq;
+  PackOut pk;                                 // (B, 2H): du at column 0, dq at column H
   int B, S, H;
 };
-void attn_bwd_tc(Ctx&, const AttnBwdTc&);
+void attn_du_tc(Ctx&, const AttnDuTc&);
 // generator + greedy selection as executor commands (greedy decode, model.lua:393-404,446-459)
 struct GenTc {
   const float* a; const float* W; const float* bias; const int32_t* y; float* logp; float* dz; float* rowloss;
   int R, H, V; float inv_bn;
 };
 struct GreedyTc { float* logp; int32_t* tok; double* score; int32_t* labels; long long ldl; int t, B, V; };
-inline size_t attn_smem_bytes(int S, int H) { return (size_t)(((S + 3) & ~3) + 16 + 8 * H) * sizeof(float); }
+inline size_t attn_smem_bytes(int S, int H) { return (size_t)(((S + 3) & ~3) + 16 + 9 * H) * sizeof(float); }
 
 }  // namespace aocr
 

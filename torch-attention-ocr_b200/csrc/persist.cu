@@ -179,10 +179,6 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       }
     } else if (type == P_CELL_FWD) {
       decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_DEC_OUT) {
-      decb::dec_out_tc_body(payload<DecOutTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_DU) {
-      decb::du_tc_body(payload<DuTc>(cmd), bid, nblk, scratch);
     } else if (type == P_CELL_BWD) {
       decb::cell_bwd_tc_body(payload<CellBwdTc>(cmd), bid, nblk, scratch);
     } else if (type == P_ENC_CELL_FWD) {
@@ -196,17 +192,16 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       decb::generator_body(payload<GenTc>(cmd), bid, nblk, scratch);
     } else if (type == P_GREEDY) {
       decb::greedy_select_body(payload<GreedyTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_ATTN_FWD) {
-      const AttnFwdTc p = payload<AttnFwdTc>(cmd);
+    } else if (type == P_ATTN_OUT) {
+      const AttnOutTc p = payload<AttnOutTc>(cmd);
       for (int b = bid; b < p.B; b += nblk) {
-        decb::attn_fwd_tc_body(p.ctx, p.q, p.alpha, p.cv, p.ldcv, p.cvp, p.q_out, p.S, p.H, b, nblk, scratch);
+        decb::attn_out_tc_body(p, b, scratch);
         __syncthreads();
       }
-    } else if (type == P_ATTN_BWD) {
-      const AttnBwdTc p = payload<AttnBwdTc>(cmd);
+    } else if (type == P_ATTN_DU) {
+      const AttnDuTc p = payload<AttnDuTc>(cmd);
       for (int b = bid; b < p.B; b += nblk) {
-        decb::attn_bwd_tc_body(p.ctx, p.alpha, p.dcv, p.dcv_out, p.ld_dcv_out, p.de, p.dq, p.dqp, p.S, p.H, b, nblk,
-                               scratch);
+        decb::attn_du_tc_body(p, b, scratch);
         __syncthreads();
       }
     }

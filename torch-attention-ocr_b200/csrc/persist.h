@@ -13,7 +13,7 @@
 namespace aocr {
 
 enum PType {
-  P_GEMM = 0, P_CELL_FWD, P_DEC_OUT, P_DU, P_CELL_BWD, P_ATTN_FWD, P_ATTN_BWD, P_ENC_CELL_FWD, P_ENC_CELL_BWD, P_TO_DENSE, P_GENERATOR, P_GREEDY
+  P_GEMM = 0, P_CELL_FWD, P_CELL_BWD, P_ATTN_OUT, P_ATTN_DU, P_ENC_CELL_FWD, P_ENC_CELL_BWD, P_TO_DENSE, P_GENERATOR, P_GREEDY
 };
 
 // swap-AB GEMM with the batch on the UMMA N side: partial z of out(n, m) at ws[z*part_stride + n*ldc + m]
