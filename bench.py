@@ -170,8 +170,17 @@ def main():
     stream = torch.cuda.ExternalStream(h.stream(), device=local)
     if world > 1:
         from aocr import dist as aocr_dist
-        aocr_dist.attach(h, local)      # NCCL exchange hook: SyncBN statistics + 3 overlapped gradient buckets
+        # exchange = SyncBN statistics + 3 overlapped gradient buckets; native NCCL inside the library (graph-captured),
+        # AOCR_DP_HOOK=1 selects the torch.distributed hook flavour instead
+        if os.environ.get("AOCR_DP_HOOK"):
+            aocr_dist.attach(h, local)
+        else:
+            aocr_dist.attach_native(h, local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def trace(msg):
+        if os.environ.get("AOCR_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
     def step_resident():
         h.train_step_staged(lr, sync=False)     # dp: the engine calls the exchange hook at its bucket boundaries
@@ -186,7 +195,9 @@ def main():
     h.stage_batch(batch["images"], batch["targets"], batch["targets_eval"])
     for _ in range(warmup):
         step_resident()
+    trace("warmup enqueued")
     barrier()
+    trace("warmup done")
     sampler = ClockSampler(local)
     sampler.start()
     l0 = h.launch_count()
@@ -199,7 +210,9 @@ def main():
         step_resident()
         with torch.cuda.stream(stream):
             ev[i][1].record(stream)
+    trace("timed steps enqueued")
     barrier()
+    trace("timed steps done")
     launches = h.launch_count() - l0
     ms_resident = sum(a.elapsed_time(b) for a, b in ev) / steps
     loss = h.read_loss()
@@ -220,6 +233,7 @@ def main():
         step_e2e()
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    trace("e2e done")
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -243,6 +257,7 @@ def main():
         model.step(hb, True)
     barrier()
     ms_dec_e2e = (time.perf_counter() - t0) * 1e3 / nd
+    trace("decode done")
 
     # ---- per-kernel-class timing for the roofline: CUDA events recorded on the engine stream around every call of
     # the class during extra (untimed) steps; no host sync inside the step

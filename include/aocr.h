@@ -118,6 +118,12 @@ int aocr_stream(aocr_handle* h, void** cuda_stream);       /* cudaStream_t the e
  * The host runtime implements it with NCCL (aocr/dist.py: torch.distributed). */
 typedef void (*aocr_allreduce_fn)(void* user, void* dev_ptr, int64_t n_floats, int kind);
 int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user);
+/* Native exchange: the library issues the same three kinds as NCCL all-reduces itself (libnccl.so.2 bound at run
+ * time), on its own streams, so a data-parallel step is captured into the whole-step CUDA graph.  Rank 0 calls
+ * aocr_dp_unique_id (128 bytes = ncclUniqueId), the host ships it to every rank, every rank of the handle's
+ * dp_world calls aocr_dp_init (collective).  Takes precedence over a hook.  No reference counterpart. */
+int aocr_dp_unique_id(void* out128);
+int aocr_dp_init(aocr_handle* h, const void* id128);
 int aocr_synchronize(aocr_handle* h);
 /* number of kernel launches the library has issued on this handle (bench `gpu_launches`) */
 int64_t aocr_launch_count(const aocr_handle* h);

@@ -63,6 +63,8 @@ _SYMBOLS = {
     "aocr_set_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "aocr_synchronize": (C.c_int, [C.c_void_p]),
     "aocr_launch_count": (C.c_int64, [C.c_void_p]),
+    "aocr_dp_unique_id": (C.c_int, [C.c_void_p]),
+    "aocr_dp_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aocr_prof_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "aocr_prof_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_double)]),
@@ -117,6 +119,14 @@ class Lib:
         if cls._inst is None:
             cls._inst = Lib()
         return cls._inst
+
+    def dp_unique_id(self) -> bytes:
+        """128-byte NCCL unique id (call on rank 0, ship to every rank, then Handle.dp_init on all of them)"""
+        buf = C.create_string_buffer(128)
+        rc = self.dll.aocr_dp_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError("aocr_dp_unique_id failed: NCCL (libnccl.so.2) not loadable")
+        return buf.raw
 
 
 def _ptr(a):
@@ -284,6 +294,12 @@ class Handle:
 
     def launch_count(self):
         return int(self.lib.dll.aocr_launch_count(self.h))
+
+    def dp_init(self, unique_id: bytes):
+        """native NCCL exchange (collective over the handle's dp_world); `unique_id` from Lib.dp_unique_id() of rank 0"""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.lib.dll.aocr_dp_init(self.h, buf))
 
     def prof_enable(self, on=True):
         self._ck(self.lib.dll.aocr_prof_enable(self.h, 1 if on else 0))

@@ -1,5 +1,8 @@
-"""Data-parallel plumbing for libaocr: one process per GPU, torch.distributed (NCCL over NVLink) does the
-collectives, the engine says WHEN through its exchange hook (include/aocr.h: aocr_set_allreduce).
+"""Data-parallel plumbing for libaocr: one process per GPU.  Two flavours of the same exchange:
+  * attach_native (default on GPUs): the library issues the NCCL all-reduces itself (include/aocr.h: aocr_dp_init);
+    torch.distributed only bootstraps the NCCL unique id;
+  * attach / GradSync: torch.distributed does the collectives, the engine says WHEN through its exchange hook
+    (aocr_set_allreduce) — the flavour the CPU (gloo) tests exercise, and the seam for a custom exchange.
 
 The reference is single-device; training shards the batch over ranks.  To reproduce the
 single-device reference at the GLOBAL batch the engine (i) scales the loss by 1/global_batch, (ii) sums the
@@ -76,6 +79,22 @@ def attach(handle, device_index, group=None, overlap=True):
     handle.set_allreduce(gs.cb)
     handle._grad_sync = gs                        # lifetime: as long as the handle
     return gs
+
+
+def attach_native(handle, device_index, group=None):
+    """Native exchange: the library itself issues the NCCL all-reduces (no Python in the step, data-parallel steps are
+    graph-captured).  torch.distributed only ships rank 0's NCCL unique id to the other ranks of `group`."""
+    import torch
+    import torch.distributed as dist
+    from .capi import Lib
+    rank = dist.get_rank(group)
+    uid = Lib.get().dp_unique_id() if rank == 0 else bytes(128)
+    dev = torch.device("cuda", device_index) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    handle.dp_init(bytes(t.cpu().tolist()))
+    return handle
 
 
 def shard(batch, rank, world):

@@ -176,6 +176,21 @@ int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user) {
   h->eng->ar_fn = fn; h->eng->ar_user = user;
   AOCR_API_END(h)
 }
+int aocr_dp_unique_id(void* out128) {
+  try {
+    if (!out128) return AOCR_ERR_INVALID;
+    aocr::dp_unique_id(out128);
+    return AOCR_OK;
+  } catch (...) {
+    return AOCR_ERR_CUDA;
+  }
+}
+int aocr_dp_init(aocr_handle* h, const void* id128) {
+  AOCR_API_BEGIN(h)
+  AOCR_CHECK(id128 != nullptr, "null unique id");
+  h->eng->dp_init(id128);
+  AOCR_API_END(h)
+}
 int aocr_stream(aocr_handle* h, void** cuda_stream) {
   AOCR_API_BEGIN(h)
   if (cuda_stream) *cuda_stream = (void*)h->eng->ctx_.st;

@@ -222,6 +222,10 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   use_lane(0);
   if (ctx_.st) cudaStreamSynchronize(ctx_.st);
+  // captured graphs hold references on the NCCL communicator (persistent plans): they must go first, or
+  // ncclCommDestroy waits for them forever
+  for (auto& kv : graphs_) if (kv.second.exec) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
+  dp_shutdown();
   for (int i = 1; i < 3; i++)
     if (lanes_on_ && lanes_[i].st) { cudaStreamSynchronize(lanes_[i].st); cudaStreamDestroy(lanes_[i].st); }
   for (int i = 0; i < 8; i++) if (lane_ev_[i]) cudaEventDestroy(lane_ev_[i]);
@@ -229,7 +233,6 @@ Engine::~Engine() {
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
-  for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (auto& kv : programs_) persist_free(kv.second);
   if (ctx_.st) cudaStreamDestroy(ctx_.st);
 }

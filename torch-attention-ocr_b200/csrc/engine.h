@@ -67,6 +67,10 @@ class Engine {
   // 1 = gradient bucket that may run concurrently with later kernels, 2 = join all outstanding buckets
   aocr_allreduce_fn ar_fn = nullptr;
   void* ar_user = nullptr;
+  // native flavour of the same exchange (engine_nccl.cu): NCCL bound at run time, collectives on the engine's own streams
+  void dp_init(const void* id128);
+  void dp_shutdown();
+  bool dp_native() const { return nccl_comm_ != nullptr; }
   StatSync stat_sync();
   void grad_bucket(int first_group, int last_group);
   void grad_join();
@@ -162,6 +166,15 @@ class Engine {
   std::vector<size_t> prof_open_;
 
   int device_;
+  void* nccl_comm_ = nullptr;
+  cudaStream_t comm_st_ = nullptr;
+  cudaEvent_t comm_ev_[4] = {};
+  int comm_ev_next_ = 0;
+  bool comm_pending_ = false;
+  void dp_allreduce(float* buf, int64_t n, int kind);
+ public:
+  void exchange(float* buf, int64_t n, int kind);
+ private:
   struct WeightPack { Pack pack; int64_t version; };
   std::map<std::tuple<const float*, int64_t, int64_t, int64_t, int64_t>, WeightPack> wcache_;
   int64_t weights_version_ = 0;
@@ -207,5 +220,7 @@ class Engine {
   double *score = nullptr, *d_loss = nullptr, *d_sumsq = nullptr, *d_sq_partial = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 };
+
+void dp_unique_id(void* out128);
 
 }  // namespace aocr

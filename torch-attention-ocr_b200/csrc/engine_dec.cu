@@ -308,13 +308,17 @@ void Engine::decoder_backward() {
 
 // ---- data-parallel hooks (no reference counterpart) ------------------------------------------
 static void stat_sync_tramp(void* user, float* buf, int64_t n) {
-  Engine* e = static_cast<Engine*>(user);
-  e->ar_fn(e->ar_user, buf, n, 0);
+  static_cast<Engine*>(user)->exchange(buf, n, 0);
+}
+// one exchange point: the native NCCL path when aocr_dp_init was called, else the host hook
+void Engine::exchange(float* buf, int64_t n, int kind) {
+  if (nccl_comm_) { dp_allreduce(buf, n, kind); return; }
+  AOCR_CHECK(ar_fn != nullptr, "dp_world > 1 needs aocr_dp_init or aocr_set_allreduce before a training step");
+  ar_fn(ar_user, buf, n, kind);
 }
 StatSync Engine::stat_sync() {
   StatSync s;
   if (cfg.dp_world > 1) {
-    AOCR_CHECK(ar_fn != nullptr, "dp_world > 1 needs aocr_set_allreduce before a training step");
     s.fn = stat_sync_tramp; s.user = this; s.world = cfg.dp_world;
   }
   return s;
@@ -322,13 +326,12 @@ StatSync Engine::stat_sync() {
 // groups are laid out [proj | decoder | enc_fw | enc_bw | cnn] = the order in which backward completes them
 void Engine::grad_bucket(int first_group, int last_group) {
   if (cfg.dp_world <= 1) return;
-  AOCR_CHECK(ar_fn != nullptr, "dp_world > 1 needs aocr_set_allreduce before a training step");
   const int64_t off = L.goff[first_group];
   const int64_t end = L.goff[last_group] + L.gphys[last_group];
-  ar_fn(ar_user, d_grads + off, end - off, 1);
+  exchange(d_grads + off, end - off, 1);
 }
 void Engine::grad_join() {
-  if (cfg.dp_world > 1) ar_fn(ar_user, nullptr, 0, 2);
+  if (cfg.dp_world > 1) exchange(nullptr, 0, 2);
 }
 
 // feval, train branch (model.lua:284-316,537-569,634-695)
@@ -416,10 +419,10 @@ void Engine::sgd_enqueue(double lr, double clip) {
 // A step is a fixed sequence of ~700 dependent launches whose per-launch latency (4-5 us on this part), not their
 // work, bounds the step at batch 64.  The second time a (shape, lr) key is seen the sequence is stream-captured and
 // instantiated; from then on one cudaGraphLaunch replays it.  Eager first (fills the weight-pack / tensor-map
-// caches: no allocation may happen during capture).  Not used under data parallelism (the exchange hook calls
-// into the host runtime) nor while profiling.
+// caches: no allocation may happen during capture).  Data-parallel steps are captured too when the exchange is the
+// native NCCL one (engine_nccl.cu); with a host hook (aocr_set_allreduce) they stay eager.  Never while profiling.
 void Engine::train_step_enqueue(double lr, double clip) {
-  const bool eligible = graphs_on_ && cfg.dp_world <= 1 && !prof_on && !phases_on_;
+  const bool eligible = graphs_on_ && (cfg.dp_world <= 1 || dp_native()) && !prof_on && !phases_on_;
   if (!eligible) {
     forward_backward_enqueue();
     sgd_enqueue(lr, clip);
