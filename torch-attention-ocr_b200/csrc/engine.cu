@@ -543,6 +543,7 @@ void Engine::cnn_backward() {
     }
     dcur = gB;
     // next iteration writes dz into gA again and reads dcur=gB: fine (distinct buffers)
+    if (l == 4 && cnn_bucket_split_ >= 0) grad_range(cnn_bucket_split_, L.goff[G_CNN] + L.gphys[G_CNN]);
   }
   const int nblk = 256;
   conv1_bwd(ctx_, x0, act[1], pidx[1], dcur, d_grads + L.conv_w[0], d_grads + L.conv_b[0], partial, nblk, B, W_);

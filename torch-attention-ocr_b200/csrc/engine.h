@@ -73,6 +73,7 @@ class Engine {
   bool dp_native() const { return nccl_comm_ != nullptr; }
   StatSync stat_sync();
   void grad_bucket(int first_group, int last_group);
+  void grad_range(int64_t off, int64_t end);
   void grad_join();
   void mark_weights_dirty() { weights_dirty_ = true; weights_version_++; }
 
@@ -166,11 +167,13 @@ class Engine {
   std::vector<size_t> prof_open_;
 
   int device_;
-  void* nccl_comm_ = nullptr;
+  void* nccl_comm_ = nullptr;        // gradient buckets (communication stream)
+  void* nccl_comm_stat_ = nullptr;   // batch-norm statistics (engine stream)
   cudaStream_t comm_st_ = nullptr;
   cudaEvent_t comm_ev_[4] = {};
   int comm_ev_next_ = 0;
   bool comm_pending_ = false;
+  int64_t cnn_bucket_split_ = -1;    // >= 0: cnn_backward issues [split, end of cnn group) as soon as conv5 is done
   void dp_allreduce(float* buf, int64_t n, int kind);
  public:
   void exchange(float* buf, int64_t n, int kind);

@@ -326,9 +326,10 @@ StatSync Engine::stat_sync() {
 // groups are laid out [proj | decoder | enc_fw | enc_bw | cnn] = the order in which backward completes them
 void Engine::grad_bucket(int first_group, int last_group) {
   if (cfg.dp_world <= 1) return;
-  const int64_t off = L.goff[first_group];
-  const int64_t end = L.goff[last_group] + L.gphys[last_group];
-  exchange(d_grads + off, end - off, 1);
+  grad_range(L.goff[first_group], L.goff[last_group] + L.gphys[last_group]);
+}
+void Engine::grad_range(int64_t off, int64_t end) {
+  if (cfg.dp_world > 1 && end > off) exchange(d_grads + off, end - off, 1);
 }
 void Engine::grad_join() {
   if (cfg.dp_world > 1) exchange(nullptr, 0, 2);
@@ -361,15 +362,22 @@ void Engine::forward_backward_enqueue() {
   encoder_backward();
   phase_mark("enc_bwd");
   taps_["dsrc"] = {dsrc, (int64_t)S_ * B * 512};
-  if (cfg.dp_world > 1) {
-    join_from(1);                  // decoder weight gradients (lane 1) are complete
-    grad_bucket(G_PROJ, G_DEC);    // [proj | decoder] all-reduce overlaps the CNN backward
+  // Gradient buckets in the order backward completes them (the flat buffer is laid out in that order).  Native
+  // exchange: a bucket is issued from the lane that finishes it (the communication stream waits on that lane only),
+  // so lane 0 never waits for the time-batched weight gradients of lane 1; the CNN bucket is split so that only the
+  // small conv1-4 tail is exposed after the last kernel.  Hook flavour: the host runtime orders on lane 0's stream.
+  const bool dp = cfg.dp_world > 1, native = dp && dp_native();
+  if (dp) {
+    if (native) { use_lane(1); grad_bucket(G_PROJ, G_DEC); use_lane(0); }
+    else { join_from(1); grad_bucket(G_PROJ, G_DEC); }
   }
+  cnn_bucket_split_ = native ? L.conv_w[4] : -1;      // conv5..conv7 (+BN) complete after the conv5 iteration
+  if (native) { use_lane(1); grad_bucket(G_ENC_FW, G_ENC_BW); use_lane(0); }   // all encoder gradients are lane-1 work
   cnn_backward();
   phase_mark("cnn_bwd");
   join_from(1);                    // encoder (and decoder) weight gradients
-  grad_bucket(G_ENC_FW, G_ENC_BW);
-  grad_bucket(G_CNN, G_CNN);
+  if (dp && !native) { grad_bucket(G_ENC_FW, G_ENC_BW); grad_bucket(G_CNN, G_CNN); }
+  if (native) grad_range(L.goff[G_CNN], cnn_bucket_split_);
   grad_join();
   phase_report();
   have_grads_ = true;
