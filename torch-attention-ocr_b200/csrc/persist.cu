@@ -27,14 +27,14 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned nblk, unsigned
   __syncthreads();
   epoch++;
   if (threadIdx.x == 0) {
-    __threadfence();                                    // cumulative over the CTA (bar.sync above): release
-    atomicAdd(ctr, 1u);
+    // arrive: a release reduction (no return value, so no round trip before the polling starts); the release is
+    // cumulative over the CTA's writes ordered before it by the bar.sync above
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
     const unsigned target = epoch * nblk;
     unsigned v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     } while (v < target);
-    __threadfence();
   }
   __syncthreads();
 }
