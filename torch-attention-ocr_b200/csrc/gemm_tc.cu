@@ -251,18 +251,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (nb + j < p.N) bias[j] = p.bias_n[nb + j];
         }
       }
+      float v[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        const int n = nb + j;
-        if (n < p.N) {
-          float v = __uint_as_float(r[j]);
-          if (!plain) {
-            v += bm + bias[j];
-            if (p.act == ACT_TANH) v = tanhf(v);
-            v += old[j];
+        v[j] = __uint_as_float(r[j]);
+        if (!plain) {
+          v[j] += bm + bias[j];
+          if (p.act == ACT_TANH) v[j] = tanhf(v[j]);
+          v[j] += old[j];
+        }
+      }
+      if (p.dbg & 2) continue;
+      if (!p.transpose_out && nb + 16 <= p.N && (p.ldc & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(outp + row * p.ldc + nb) & 15) == 0) {
+        // this thread owns 16 consecutive columns of one output row: four 16-byte stores
+        float4* dst = reinterpret_cast<float4*>(outp + row * p.ldc + nb);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int n = nb + j;
+          if (n < p.N) {
+            float* dst = p.transpose_out ? outp + (long long)n * p.ldc + row : outp + row * p.ldc + n;
+            *dst = v[j];
           }
-          float* dst = p.transpose_out ? outp + (long long)n * p.ldc + row : outp + row * p.ldc + n;
-          if (!(p.dbg & 2)) *dst = v;
         }
       }
     }
