@@ -136,6 +136,10 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   zb[7] = alloc<float>(B * S * 512);
   src = alloc<float>(S * B * 512);
   act[7] = src;
+  if (cfg.gemm_mode != 2) {
+    const int64_t n_act[7] = {0, B * 16 * W1 * 64, B * 8 * W2 * 128, B * 8 * W2 * 256, B * 4 * W2 * 256, B * 4 * W2 * 512, B * 2 * W2 * 512};
+    for (int l = 1; l <= 6; l++) actp_[l] = alloc_pack(1, n_act[l]);
+  }
   const int bnc[3] = {256, 512, 512};
   for (int i = 0; i < 3; i++) {
     bn_mean[i] = alloc<float>(bnc[i]); bn_var[i] = alloc<float>(bnc[i]);
@@ -451,7 +455,9 @@ void Engine::prep_weights() {
 void Engine::cnn_forward(bool train) {
   cnn_train_ = train;
   const int B = b_;
-  conv1_fwd(ctx_, x0, d_params + L.conv_w[0], d_params + L.conv_b[0], act[1], pidx[1], B, W_);
+  const bool tc = cfg.gemm_mode != 2;
+  conv1_fwd(ctx_, x0, d_params + L.conv_w[0], d_params + L.conv_b[0], act[1], pidx[1], B, W_, tc ? actp_[1].hi : nullptr,
+            tc ? actp_[1].lo : nullptr);
   for (int l = 1; l < 7; l++) {
     const ConvSpec& c = kConv[l];
     int Hin, Win, Hout, Wout;
@@ -461,7 +467,7 @@ void Engine::cnn_forward(bool train) {
     if (cfg.gemm_mode != 2) {
       // implicit GEMM: the NHWC activation is the A operand (4-D tensor map, halo by TMA zero fill); no im2col
       conv_tc(act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, d_params + L.conv_w[l], c.cout, zb[l + 1],
-              d_params + L.conv_b[l]);
+              d_params + L.conv_b[l], &actp_[l]);
     } else {
       im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
       Gemm g;
@@ -482,10 +488,14 @@ void Engine::cnn_forward(bool train) {
         mean = bn_rmean[c.bn]; var = bn_rvar[c.bn];
       }
       const bool last = (l == 6);
+      // the next convolution's operand planes come straight from this kernel (the last layer feeds the encoder)
+      __nv_bfloat16* ph = (tc && !last) ? actp_[l + 1].hi : nullptr;
+      __nv_bfloat16* pl = (tc && !last) ? actp_[l + 1].lo : nullptr;
       bn_relu_fwd(ctx_, zb[l + 1], mean, var, d_params + L.bn_g[c.bn], d_params + L.bn_b[c.bn], act[l + 1], rows, c.cout,
-                  last ? S_ : 0, last ? B : 0);
+                  last ? S_ : 0, last ? B : 0, ph, pl);
     } else {
-      relu_pool_fwd(ctx_, zb[l + 1], act[l + 1], pidx[l + 1], B, Hout, Wout, c.cout, c.pool_kw);
+      relu_pool_fwd(ctx_, zb[l + 1], act[l + 1], pidx[l + 1], B, Hout, Wout, c.cout, c.pool_kw, tc ? actp_[l + 1].hi : nullptr,
+                    tc ? actp_[l + 1].lo : nullptr);
     }
   }
   taps_["cnn_out"] = {src, (int64_t)S_ * B * 512};
@@ -502,21 +512,26 @@ void Engine::cnn_backward() {
     const int64_t rows = (int64_t)B * Hout * Wout;
     const int Kc = c.k * c.k * c.cin;
     float* dz = gA;
+    // dz as bf16 planes, written by the kernel that produces dz: shared by the weight- and the data-gradient GEMM
+    const bool tc = cfg.gemm_mode != 2;
+    Pack dzp;
+    dzp.rows = rows; dzp.kp = c.cout; dzp.hi = tc ? scratch_[0].hi : nullptr; dzp.lo = tc ? scratch_[0].lo : nullptr;
+    if (tc) AOCR_CHECK(rows * c.cout <= scratch_elems_, "dz larger than the scratch pack");
     if (c.bn >= 0) {
       const bool last = (l == 6);
       const float* mean = cnn_train_ ? bn_mean[c.bn] : bn_rmean[c.bn];
       const float* var = cnn_train_ ? bn_var[c.bn] : bn_rvar[c.bn];
       bn_relu_bwd(ctx_, dcur, act[l + 1], zb[l + 1], mean, var, d_params + L.bn_g[c.bn], dz, d_grads + L.bn_g[c.bn],
                   d_grads + L.bn_b[c.bn], partial, rows, c.cout, last ? S_ : 0, last ? B : 0, cnn_train_ ? 1 : 0,
-                  cnn_train_ ? stat_sync() : StatSync());
+                  cnn_train_ ? stat_sync() : StatSync(), dzp.hi, dzp.lo);
     } else {
-      relu_pool_bwd(ctx_, dcur, act[l + 1], pidx[l + 1], dz, B, Hout, Wout, c.cout, c.pool_kw);
+      relu_pool_bwd(ctx_, dcur, act[l + 1], pidx[l + 1], dz, B, Hout, Wout, c.cout, c.pool_kw, dzp.hi, dzp.lo);
     }
     // bias grad
     col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);
     // weight grad: dW[co][tap,ci] = sum_rows dz[row][co] * col[row][tap,ci]
     if (cfg.gemm_mode != 2) {
-      conv_wgrad_tc(dz, act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, c.cout, d_grads + L.conv_w[l]);
+      conv_wgrad_tc(dz, act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, c.cout, d_grads + L.conv_w[l], &dzp, &actp_[l]);
     } else {
       im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
       Gemm gw;
@@ -529,7 +544,7 @@ void Engine::cnn_backward() {
     // data grad: correlation of dz with flipped, in/out-swapped weights, padding k-1-pad
     const int padd = c.k - 1 - c.pad;
     if (cfg.gemm_mode != 2) {
-      conv_tc(dz, B, Hout, Wout, c.cout, c.k, padd, Hin, Win, wt[l], c.cin, gB, nullptr);
+      conv_tc(dz, B, Hout, Wout, c.cout, c.k, padd, Hin, Win, wt[l], c.cin, gB, nullptr, &dzp);
     } else {
       im2col(ctx_, dz, col, B, Hout, Wout, c.cout, c.k, padd);
       const int Kd = c.k * c.k * c.cout;

@@ -125,9 +125,9 @@ class Engine {
   void encoder_forward_steps_tc();
   void encoder_backward_steps_tc();
   void conv_wgrad_tc(const float* dz, const float* x, int N, int H, int W, int Cin, int k, int pad, int Ho, int Wo,
-                     int Cout, float* dW);
+                     int Cout, float* dW, const Pack* zpack = nullptr, const Pack* xpack = nullptr);
   void conv_tc(const float* x, int N, int H, int W, int C, int k, int pad, int Ho, int Wo, const float* Wk, int Cout,
-               float* out, const float* bias);
+               float* out, const float* bias, const Pack* xpack = nullptr);
   void conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const;
   Pack alloc_pack(int64_t rows, int64_t kp);
   bool is_param(const float* p) const;
@@ -185,6 +185,7 @@ class Engine {
   // tensor-core decoder path: concatenated weight packs, per-step operand packs, split-K partial regions
   Pack Wcat1p, Wcat2p, W3p, Wcat1Tp, Wcat2Tp, W3Tp;   // W3 = [W_a ; W_c[:, H:]] (rows), W3T = its transpose
   Pack X1p, X2p, H2p, dUQp, dG2p, dG1p;
+  Pack actp_[8];   // act[l] (input of conv l+1) as bf16 planes, written by the producing kernel; reused by the weight gradient
   Pack Whp[2], WhTp[2], HencP[2], dGeP[2];
   float* dec_ws[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t dec_ws_floats = 0;

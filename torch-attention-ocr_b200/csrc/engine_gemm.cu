@@ -87,14 +87,19 @@ void Engine::gemm(const Gemm& g, int cls) {
 // Used for the forward convolutions (x = activation, Wk = parameters) and for the data gradient (x = dz,
 // Wk = flipped / in-out-swapped weights, pad = k-1-pad).  Only the small NHWC activation is converted to bf16 planes.
 void Engine::conv_tc(const float* x, int N, int H, int W, int C, int k, int pad, int Ho, int Wo, const float* Wk, int Cout,
-                     float* out, const float* bias) {
+                     float* out, const float* bias, const Pack* xpack) {
   const int64_t rows_in = (int64_t)N * H * W;
   const int Kc = k * k * C;
   prof_begin(0);
   Pack xp;
-  xp.rows = rows_in; xp.kp = C; xp.hi = scratch_[0].hi; xp.lo = scratch_[0].lo;
-  AOCR_CHECK(C % 64 == 0 && rows_in * C <= scratch_elems_, "conv_tc: channel count must be a multiple of 64");
-  split_to_pack(ctx_, x, rows_in, C, C, 1, xp);
+  AOCR_CHECK(C % 64 == 0, "conv_tc: channel count must be a multiple of 64");
+  if (xpack) {          // the producer of x already wrote it as bf16 planes
+    xp = *xpack; xp.rows = rows_in; xp.kp = C;
+  } else {
+    xp.rows = rows_in; xp.kp = C; xp.hi = scratch_[0].hi; xp.lo = scratch_[0].lo;
+    AOCR_CHECK(rows_in * C <= scratch_elems_, "conv_tc: activation larger than the scratch pack");
+    split_to_pack(ctx_, x, rows_in, C, C, 1, xp);
+  }
   Pack wp = operand_pack(Wk, Cout, Kc, Kc, 1, 1);
   ConvView v;
   v.N = N; v.H = H; v.W = W; v.C = C; v.k = k; v.pad = pad; v.Ho = Ho; v.Wo = Wo;
@@ -111,15 +116,15 @@ void Engine::conv_tc(const float* x, int N, int H, int W, int C, int k, int pad,
 // sum over output pixels of dz[pix][co] * x[pix + tap][ci].  Both operands are the NHWC tensors as stored; the
 // filter tap is a shift of the TMA box origin of x (zero fill = padding).  No im2col, no transposes.
 void Engine::conv_wgrad_tc(const float* dz, const float* x, int N, int H, int W, int Cin, int k, int pad, int Ho, int Wo,
-                           int Cout, float* dW) {
+                           int Cout, float* dW, const Pack* zpack, const Pack* xpack) {
   const int64_t rows_out = (int64_t)N * Ho * Wo, rows_in = (int64_t)N * H * W;
   prof_begin(0);
   Pack zp, xp;
   zp.rows = rows_out; zp.kp = Cout; zp.hi = scratch_[0].hi; zp.lo = scratch_[0].lo;
   xp.rows = rows_in; xp.kp = Cin; xp.hi = scratch_[1].hi; xp.lo = scratch_[1].lo;
   AOCR_CHECK(rows_out * Cout <= scratch_elems_ && rows_in * Cin <= scratch_elems_, "conv wgrad operand exceeds scratch");
-  split_to_pack(ctx_, dz, rows_out, Cout, Cout, 1, zp);
-  split_to_pack(ctx_, x, rows_in, Cin, Cin, 1, xp);
+  if (zpack) { zp.hi = zpack->hi; zp.lo = zpack->lo; } else split_to_pack(ctx_, dz, rows_out, Cout, Cout, 1, zp);
+  if (xpack) { xp.hi = xpack->hi; xp.lo = xpack->lo; } else split_to_pack(ctx_, x, rows_in, Cin, Cin, 1, xp);
   ConvView v;
   v.N = N; v.H = H; v.W = W; v.C = Cin; v.k = k; v.pad = pad; v.Ho = Ho; v.Wo = Wo;
   TcGemm t;

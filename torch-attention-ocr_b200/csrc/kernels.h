@@ -6,16 +6,18 @@ namespace aocr {
 
 // ---------------- CNN (reference: src/model/cnn.lua:9-45) -------------------------------------
 // K1+K2: (x-128)/128 -> conv1 3x3 p1 (1->64) + bias + ReLU + maxpool 2x2.  x (B,32,W) -> a1 (B,16,W/2,64) NHWC
+// (phi, plo), where given: the output also as bf16 (hi, lo) operand planes for the next tensor-core contraction
 void conv1_fwd(Ctx&, const float* x, const float* w /*[64][9]*/, const float* bias, float* a1, uint8_t* idx,
-               int B, int W);
+               int B, int W, __nv_bfloat16* phi = nullptr, __nv_bfloat16* plo = nullptr);
 // dW1 (64x9), db1 from d a1 routed through the pool argmax / ReLU mask.  Deterministic two-stage reduction.
 void conv1_bwd(Ctx&, const float* x, const float* a1, const uint8_t* idx, const float* da1, float* dw, float* db,
                float* partial /* [nblk][640] scratch */, int nblk, int B, int W);
 // ReLU + maxpool (KH x KW in {2x2, 2x1}), floor mode.  z (B,H,Wi,C) -> a (B,H/2,Wi/KW,C) + argmax index.
-void relu_pool_fwd(Ctx&, const float* z, float* a, uint8_t* idx, int B, int H, int Wi, int C, int kw);
+void relu_pool_fwd(Ctx&, const float* z, float* a, uint8_t* idx, int B, int H, int Wi, int C, int kw,
+                   __nv_bfloat16* phi = nullptr, __nv_bfloat16* plo = nullptr);
 // dz (full, zero-filled) from da through argmax + (a>0)
 void relu_pool_bwd(Ctx&, const float* da, const float* a, const uint8_t* idx, float* dz, int B, int H, int Wi, int C,
-                   int kw);
+                   int kw, __nv_bfloat16* phi = nullptr, __nv_bfloat16* plo = nullptr);
 // im2col of an NHWC activation: a (B,H,Wi,C) -> col (B*Ho*Wo, k*k*C), tap-major / channel-fastest.
 // flip=1 reads taps mirrored (used for the data gradient, where `a` is dz and the GEMM weight is W^T).
 void im2col(Ctx&, const float* a, float* col, int B, int H, int Wi, int C, int k, int pad);
@@ -29,12 +31,13 @@ void bn_stats(Ctx&, const float* z, int64_t R, int C, float* mean, float* var /*
 void bn_update_running(Ctx&, const float* mean, const float* var, float* rmean, float* rvar, int C, int64_t R);
 // y = relu(gamma*(z-mean)/sqrt(var+eps)+beta).  If tm_S>0 rows (n,s) are written time-major to row s*tm_B+n.
 void bn_relu_fwd(Ctx&, const float* z, const float* mean, const float* var, const float* gamma, const float* beta,
-                 float* a, int64_t R, int C, int tm_S, int tm_B);
+                 float* a, int64_t R, int C, int tm_S, int tm_B, __nv_bfloat16* phi = nullptr, __nv_bfloat16* plo = nullptr);
 // BN backward.  step 1: dy = da*(a>0) written to dz; sums s1=sum(dy), s2=sum(dy*xhat) via col reductions;
 // step 2: dz = gamma*inv*(dy - s1/R - xhat*s2/R) (train) or gamma*inv*dy (eval stats).  dgamma=s2, dbeta=s1.
 void bn_relu_bwd(Ctx&, const float* da, const float* a, const float* z, const float* mean, const float* var,
                  const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial, int64_t R, int C,
-                 int tm_S, int tm_B, int train, const StatSync& sync);
+                 int tm_S, int tm_B, int train, const StatSync& sync, __nv_bfloat16* phi = nullptr,
+                 __nv_bfloat16* plo = nullptr);
 
 // ---------------- LSTM cells (reference: src/model/LSTM.lua:79-105) ---------------------------
 // One encoder step for both directions: g = xg[t] + h_prev W_h^T ; cell.  Layouts in DESIGN.md §4.

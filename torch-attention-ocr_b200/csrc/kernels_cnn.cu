@@ -12,9 +12,30 @@ constexpr float BN_EPS = 1e-5f;
 // ------------------------------------------------------------------ conv1
 // thread = one pooled output element (n, ph, pw, c); the 4x4 input patch is shared by the 64 channel
 // threads (L1 broadcast), weights live in smem.
+// optional bf16 (hi, lo) operand planes written next to an fp32 activation (same linear index: kp == C)
+__device__ __forceinline__ void split_store1(__nv_bfloat16* phi, __nv_bfloat16* plo, int64_t i, float v) {
+  if (!phi) return;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  phi[i] = h;
+  plo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void split_store4(__nv_bfloat16* phi, __nv_bfloat16* plo, int64_t i, float4 v) {
+  if (!phi) return;
+  __nv_bfloat16 h[4], l[4];
+  const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    h[k] = __float2bfloat16_rn(x[k]);
+    l[k] = __float2bfloat16_rn(x[k] - __bfloat162float(h[k]));
+  }
+  *reinterpret_cast<uint2*>(phi + i) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(plo + i) = *reinterpret_cast<uint2*>(l);
+}
+
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ a1,
-                                                        uint8_t* __restrict__ idx, int B, int W) {
+                                                        uint8_t* __restrict__ idx, int B, int W, __nv_bfloat16* __restrict__ phi,
+                                                        __nv_bfloat16* __restrict__ plo) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float ws[64 * 9];
@@ -59,6 +80,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
       }
     a1[e] = best;
     idx[e] = (uint8_t)bi;
+    split_store1(phi, plo, e, best);
   }
 }
 
@@ -126,7 +148,8 @@ __global__ void conv1_bwd_final_kernel(const float* __restrict__ partial, int nb
 // ------------------------------------------------------------------ ReLU + max-pool
 template <int KW>
 __global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restrict__ z, float* __restrict__ a,
-                                                            uint8_t* __restrict__ idx, int B, int H, int Wi, int C) {
+                                                            uint8_t* __restrict__ idx, int B, int H, int Wi, int C,
+                                                            __nv_bfloat16* __restrict__ phi, __nv_bfloat16* __restrict__ plo) {
   pdl_launch_dependents();
   pdl_wait();
   const int Ho = H / 2, Wo = Wi / KW;
@@ -149,6 +172,7 @@ __global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restr
       }
     a[e] = best;
     idx[e] = (uint8_t)bi;
+    split_store1(phi, plo, e, best);
   }
 }
 
@@ -157,7 +181,8 @@ __global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restr
 template <int KW>
 __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a,
                                                             const uint8_t* __restrict__ idx, float* __restrict__ dz,
-                                                            int B, int H, int Wi, int C) {
+                                                            int B, int H, int Wi, int C, __nv_bfloat16* __restrict__ phi,
+                                                            __nv_bfloat16* __restrict__ plo) {
   pdl_launch_dependents();
   pdl_wait();
   const int Ho = H / 2, Wo = Wi / KW;
@@ -176,6 +201,7 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restr
       if (idx[o] == bi && a[o] > 0.f) v = da[o];
     }
     dz[e] = v;
+    split_store1(phi, plo, e, v);
   }
 }
 
@@ -262,7 +288,8 @@ __global__ void bn_update_running_kernel(const float* __restrict__ mean, const f
 __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
                                                           const float* __restrict__ var, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ a, int64_t R,
-                                                          int C, int tm_S, int tm_B) {
+                                                          int C, int tm_S, int tm_B, __nv_bfloat16* __restrict__ phi,
+                                                          __nv_bfloat16* __restrict__ plo) {
   pdl_launch_dependents();
   pdl_wait();
   const int C4 = C / 4;
@@ -283,6 +310,7 @@ __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restric
     int64_t ro = r;
     if (tm_S > 0) ro = (r % tm_S) * tm_B + r / tm_S;
     *reinterpret_cast<float4*>(a + ro * C + c) = o;
+    split_store4(phi, plo, ro * C + c, o);
   }
 }
 
@@ -314,7 +342,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
                                                            const float* __restrict__ mean, const float* __restrict__ var,
                                                            const float* __restrict__ gamma, const float* __restrict__ s1,
                                                            const float* __restrict__ s2, int64_t R, int64_t Rglobal, int C,
-                                                           int train) {
+                                                           int train, __nv_bfloat16* __restrict__ phi,
+                                                           __nv_bfloat16* __restrict__ plo) {
   pdl_launch_dependents();
   pdl_wait();
   const int64_t total = R * C;                 // local rows
@@ -331,6 +360,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* __restrict__ d
       o = gamma[c] * inv * dy;
     }
     dz[e] = o;
+    split_store1(phi, plo, e, o);
   }
 }
 
@@ -363,9 +393,10 @@ void col_reduce(Ctx& ctx, const float* z, const float* z2, const float* mean, co
 
 }  // namespace
 
-void conv1_fwd(Ctx& ctx, const float* x, const float* w, const float* bias, float* a1, uint8_t* idx, int B, int W) {
+void conv1_fwd(Ctx& ctx, const float* x, const float* w, const float* bias, float* a1, uint8_t* idx, int B, int W,
+               __nv_bfloat16* phi, __nv_bfloat16* plo) {
   int64_t total = (int64_t)B * 16 * (W / 2) * 64;
-  launch_pdl(ctx, conv1_fwd_kernel, dim3(grid_for(total, 256, ctx.num_sms)), dim3(256), 0, x, w, bias, a1, idx, B, W);
+  launch_pdl(ctx, conv1_fwd_kernel, dim3(grid_for(total, 256, ctx.num_sms)), dim3(256), 0, x, w, bias, a1, idx, B, W, phi, plo);
   AOCR_CUDA(cudaGetLastError());
 }
 
@@ -379,20 +410,21 @@ void conv1_bwd(Ctx& ctx, const float* x, const float* a1, const uint8_t* idx, co
   AOCR_CUDA(cudaGetLastError());
 }
 
-void relu_pool_fwd(Ctx& ctx, const float* z, float* a, uint8_t* idx, int B, int H, int Wi, int C, int kw) {
+void relu_pool_fwd(Ctx& ctx, const float* z, float* a, uint8_t* idx, int B, int H, int Wi, int C, int kw,
+                   __nv_bfloat16* phi, __nv_bfloat16* plo) {
   int64_t total = (int64_t)B * (H / 2) * (Wi / kw) * C;
   int g = grid_for(total, 256, ctx.num_sms);
-  if (kw == 2) relu_pool_fwd_kernel<2><<<g, 256, 0, ctx.st>>>(z, a, idx, B, H, Wi, C);
-  else relu_pool_fwd_kernel<1><<<g, 256, 0, ctx.st>>>(z, a, idx, B, H, Wi, C);
+  if (kw == 2) relu_pool_fwd_kernel<2><<<g, 256, 0, ctx.st>>>(z, a, idx, B, H, Wi, C, phi, plo);
+  else relu_pool_fwd_kernel<1><<<g, 256, 0, ctx.st>>>(z, a, idx, B, H, Wi, C, phi, plo);
   AOCR_LAUNCH_CHECK(ctx);
 }
 
 void relu_pool_bwd(Ctx& ctx, const float* da, const float* a, const uint8_t* idx, float* dz, int B, int H, int Wi, int C,
-                   int kw) {
+                   int kw, __nv_bfloat16* phi, __nv_bfloat16* plo) {
   int64_t total = (int64_t)B * H * Wi * C;
   int g = grid_for(total, 256, ctx.num_sms);
-  if (kw == 2) relu_pool_bwd_kernel<2><<<g, 256, 0, ctx.st>>>(da, a, idx, dz, B, H, Wi, C);
-  else relu_pool_bwd_kernel<1><<<g, 256, 0, ctx.st>>>(da, a, idx, dz, B, H, Wi, C);
+  if (kw == 2) relu_pool_bwd_kernel<2><<<g, 256, 0, ctx.st>>>(da, a, idx, dz, B, H, Wi, C, phi, plo);
+  else relu_pool_bwd_kernel<1><<<g, 256, 0, ctx.st>>>(da, a, idx, dz, B, H, Wi, C, phi, plo);
   AOCR_LAUNCH_CHECK(ctx);
 }
 
@@ -432,15 +464,15 @@ void bn_update_running(Ctx& ctx, const float* mean, const float* var, float* rme
 }
 
 void bn_relu_fwd(Ctx& ctx, const float* z, const float* mean, const float* var, const float* gamma, const float* beta,
-                 float* a, int64_t R, int C, int tm_S, int tm_B) {
+                 float* a, int64_t R, int C, int tm_S, int tm_B, __nv_bfloat16* phi, __nv_bfloat16* plo) {
   launch_pdl(ctx, bn_relu_fwd_kernel, dim3(grid_for(R * (C / 4), 256, ctx.num_sms)), dim3(256), 0, z, mean, var, gamma, beta, a, R, C,
-                                                                                 tm_S, tm_B);
+                                                                                 tm_S, tm_B, phi, plo);
   AOCR_CUDA(cudaGetLastError());
 }
 
 void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, const float* mean, const float* var,
                  const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial, int64_t R, int C, int tm_S,
-                 int tm_B, int train, const StatSync& sync) {
+                 int tm_B, int train, const StatSync& sync, __nv_bfloat16* phi, __nv_bfloat16* plo) {
   launch_pdl(ctx, relu_mask_kernel, dim3(grid_for(R * (C / 4), 256, ctx.num_sms)), dim3(256), 0, da, a, dz, R, C, tm_S, tm_B);
   AOCR_CUDA(cudaGetLastError());
   // dbeta = s1 ; dgamma = s2 (each BN parameter receives gradient exactly once per step)
@@ -451,7 +483,7 @@ void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, cons
     else { sync.fn(sync.user, dgamma, C); sync.fn(sync.user, dbeta, C); }
   }
   launch_pdl(ctx, bn_bwd_apply_kernel, dim3(grid_for(R * C, 256, ctx.num_sms)), dim3(256), 0, dz, z, mean, var, gamma, dbeta, dgamma,
-                                                                           R, R * sync.world, C, train);
+                                                                           R, R * sync.world, C, train, phi, plo);
   AOCR_CUDA(cudaGetLastError());
   if (sync.world > 1) {   // the gradient all-reduce will sum these again over ranks: pre-divide
     scale_vec(ctx, dgamma, C, 1.0f / (float)sync.world);
