@@ -414,12 +414,13 @@ void Engine::group_norms(double* pn, double* gn) {
 // optim.sgd_list, default branch (optim_sgd.lua:49-52,90): per group clip to `clip`, p -= lr*g.  No host sync.
 void Engine::sgd_enqueue(double lr, double clip) {
   AOCR_CHECK(have_grads_, "no gradients yet: call aocr_forward_backward first");
+  SgdGroups G;
   for (int g = 0; g < 5; g++) {
-    int nb = sq_blocks(L.gphys[g]);
-    sumsq_partial(ctx_, d_grads + L.goff[g], L.gphys[g], d_sq_partial + g * 1024, nb);
-    sumsq_final(ctx_, d_sq_partial + g * 1024, nb, d_sumsq + g);
-    sgd_apply(ctx_, d_params + L.goff[g], d_grads + L.goff[g], L.gphys[g], d_sumsq + g, lr, clip);
+    G.off[g] = L.goff[g]; G.n[g] = L.gphys[g];
+    int64_t nb = L.gphys[g] / 16384 + 1;          // ~16k floats per block and pass
+    G.nb[g] = (int)(nb < 1024 ? nb : 1024);
   }
+  sgd_groups(ctx_, d_params, d_grads, G, d_sq_partial, d_sumsq, lr, clip);
   mark_weights_dirty();
 }
 

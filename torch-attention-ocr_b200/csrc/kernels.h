@@ -116,6 +116,10 @@ void sumsq_partial(Ctx&, const float* v, int64_t n, double* partial, int nblk); 
 void sumsq_final(Ctx&, const double* partial, int nblk, double* out);
 // p -= lr * scale * g with scale = (norm>clip ? clip/norm : 1), norm = sqrt(*sumsq)
 void sgd_apply(Ctx&, float* p, float* g, int64_t n, const double* sumsq, double lr, double clip);
+// the three steps above for all 5 parameter groups in 3 launches; nb[g] <= 1024 blocks work on group g (fixed
+// assignment: deterministic), partial is [5][1024] doubles, sumsq [5]
+struct SgdGroups { int64_t off[5]; int64_t n[5]; int nb[5]; };
+void sgd_groups(Ctx&, float* params, float* grads, const SgdGroups& G, double* partial, double* sumsq, double lr, double clip);
 void scale_vec(Ctx&, float* v, int64_t n, float s);
 void axpy_vec(Ctx&, float* y, const float* x, int64_t n, float a);
 

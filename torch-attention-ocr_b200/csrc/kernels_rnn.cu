@@ -562,7 +562,92 @@ __global__ void __launch_bounds__(256) sgd_apply_kernel(float* __restrict__ p, f
   }
 }
 
+// ---- the same for all parameter groups at once (3 launches per update instead of 15) ----------------------------
+__device__ __forceinline__ int group_of_block(const SgdGroups& G, int blk, int& local) {
+  int g = 0, first = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (g == i && blk >= first + G.nb[i]) { first += G.nb[i]; g = i + 1; }
+  }
+  local = blk - first;
+  return g;
+}
+__global__ void __launch_bounds__(256) sumsq_groups_kernel(const float* __restrict__ base, SgdGroups G,
+                                                           double* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[8];
+  int local;
+  const int g = group_of_block(G, blockIdx.x, local);
+  const float4* v = reinterpret_cast<const float4*>(base + G.off[g]);
+  const int64_t n4 = G.n[g] / 4;           // group extents are padded to 64 floats
+  double s = 0.0;
+  for (int64_t e = (int64_t)local * blockDim.x + threadIdx.x; e < n4; e += (int64_t)G.nb[g] * blockDim.x) {
+    const float4 x = v[e];
+    s += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += red[w];
+    partial[g * 1024 + local] = t;
+  }
+}
+__global__ void __launch_bounds__(256) sumsq_final_groups_kernel(const double* __restrict__ partial, SgdGroups G,
+                                                                 double* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double red[256];
+  const int g = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < G.nb[g]; i += 256) s += partial[g * 1024 + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[g] = red[0];
+}
+__global__ void __launch_bounds__(256) sgd_apply_groups_kernel(float* __restrict__ pbase, float* __restrict__ gbase, SgdGroups G,
+                                                               const double* __restrict__ sumsq, double lr, double clip) {
+  pdl_launch_dependents();
+  pdl_wait();
+  int local;
+  const int g = group_of_block(G, blockIdx.x, local);
+  const double norm = sqrt(sumsq[g]);
+  const float scale = norm > clip ? (float)(clip / norm) : 1.0f;   // optim_sgd.lua:50-52
+  const float flr = (float)lr;
+  float4* p = reinterpret_cast<float4*>(pbase + G.off[g]);
+  float4* gr = reinterpret_cast<float4*>(gbase + G.off[g]);
+  const int64_t n4 = G.n[g] / 4;
+  for (int64_t e = (int64_t)local * blockDim.x + threadIdx.x; e < n4; e += (int64_t)G.nb[g] * blockDim.x) {
+    float4 gv = gr[e];
+    float4 pv = p[e];
+    gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
+    gr[e] = gv;                      // the reference clips dfdy in place
+    pv.x -= flr * gv.x; pv.y -= flr * gv.y; pv.z -= flr * gv.z; pv.w -= flr * gv.w;   // optim_sgd.lua:90
+    p[e] = pv;
+  }
+}
+
 }  // namespace
+
+void sgd_groups(Ctx& ctx, float* params, float* grads, const SgdGroups& G, double* partial, double* sumsq, double lr,
+                double clip) {
+  int total = 0;
+  for (int g = 0; g < 5; g++) total += G.nb[g];
+  launch_pdl(ctx, sumsq_groups_kernel, dim3(total), dim3(256), 0, (const float*)grads, G, partial);
+  AOCR_CUDA(cudaGetLastError());
+  launch_pdl(ctx, sumsq_final_groups_kernel, dim3(5), dim3(256), 0, (const double*)partial, G, sumsq);
+  AOCR_CUDA(cudaGetLastError());
+  launch_pdl(ctx, sgd_apply_groups_kernel, dim3(total), dim3(256), 0, params, grads, G, (const double*)sumsq, lr, clip);
+  AOCR_CUDA(cudaGetLastError());
+}
 
 void enc_step_fwd(Ctx& ctx, const EncStep& p) {
   dim3 grid(p.He / 8, 2, cdiv(p.B, 32));
