@@ -122,8 +122,9 @@ __device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, floa
   float* accs = wl + ATT_WARPS;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int nv = H / 128;
-  const float* cb = p.ctx + (int64_t)b * S * H;
-  const float* wb = p.ctxwc + (int64_t)b * S * H;
+  const int bsrc = p.ctx_rows > 0 ? b % p.ctx_rows : b;
+  const float* cb = p.ctx + (int64_t)bsrc * S * H;
+  const float* wb = p.ctxwc + (int64_t)bsrc * S * H;
   float* qs = accs + ATT_WARPS * H;               // the summed query, shared by the 8 warps
   // split-K partials of [q | v] are summed ONCE per CTA (4 consecutive columns per thread), not once per warp
   const int e4 = threadIdx.x * 4;
@@ -390,16 +391,20 @@ __device__ __forceinline__ void generator_body(const GenTc& p, int bid, int nblk
       float se = (lane < V ? expf(z0 - mx) : 0.f) + (lane + 32 < V ? expf(z1 - mx) : 0.f);
       se = warp_sum(se);
       const float lse = mx + logf(se);
-      const int yy = p.y ? p.y[r] - 1 : -1;
-      const float w = (p.y && yy != 0) ? 1.f : 0.f;
+      const bool second = p.split > 0 && r >= p.split;           // teacher-forced half of a dual pass
+      const int64_t ro = second ? r - p.split : r;
+      const bool has_y = p.y && (p.split == 0 || second);
+      const int yy = has_y ? p.y[ro] - 1 : -1;
+      const float w = (has_y && yy != 0) ? 1.f : 0.f;
+      float* lpo = second ? p.logp2 : p.logp;
 #pragma unroll
       for (int j = 0; j < 2; j++) {
         const int v = lane + 32 * j;
         if (v < V) {
           const float lp = (j == 0 ? z0 : z1) - lse;
-          p.logp[r * V + v] = lp;
+          lpo[ro * V + v] = lp;
           if (p.dz) p.dz[r * V + v] = (expf(lp) - (v == yy ? 1.f : 0.f)) * w * p.inv_bn;
-          if (p.rowloss && v == yy) p.rowloss[r] = -w * lp;
+          if (p.rowloss && has_y && v == yy) p.rowloss[ro] = -w * lp;
         }
       }
     }
@@ -422,7 +427,7 @@ __device__ __forceinline__ void greedy_select_body(const GreedyTc& p, int bid, i
       if (x > best) { best = x; bi = v; }
     }
     p.score[b] = (p.t == 0 ? 0.0 : __ldcg(p.score + b)) + (double)best;
-    p.tok[b] = bi + 1;
+    p.tok_out[b] = bi + 1;
     p.labels[(int64_t)b * p.ldl + p.t] = bi + 1;
   }
 }

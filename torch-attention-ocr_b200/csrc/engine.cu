@@ -111,6 +111,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (const char* e = getenv("AOCR_PHASES")) phases_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_GRAPHS")) graphs_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_PERSIST")) persist_on_ = atoi(e) != 0;
+  if (const char* e = getenv("AOCR_DUAL")) dual_on_ = atoi(e) != 0;
   if (c.batch_size > 128 || c.gemm_mode == 2) persist_on_ = false;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));
@@ -166,9 +167,10 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     W3p = alloc_pack(2 * Hd_, Hd_);
     Wcat1Tp = alloc_pack(K1_, 4 * Hd_); Wcat2Tp = alloc_pack(2 * Hd_, 4 * Hd_);
     W3Tp = alloc_pack(Hd_, 2 * Hd_);
-    X1p = alloc_pack(Tm * B, K1_); X2p = alloc_pack(Tm * B, 2 * Hd_); H2p = alloc_pack(Tm * B, Hd_);
+    // decoder forward state holds 2B rows: greedy decode runs its greedy and its gold pass as ONE batch of 2B
+    X1p = alloc_pack(Tm * 2 * B, K1_); X2p = alloc_pack(Tm * 2 * B, 2 * Hd_); H2p = alloc_pack(Tm * 2 * B, Hd_);
     dUQp = alloc_pack(B, 2 * Hd_); dG2p = alloc_pack(B, 4 * Hd_); dG1p = alloc_pack(B, 4 * Hd_);
-    dec_ws_floats = (int64_t)16 * B * 4 * Hd_ + 1024;
+    dec_ws_floats = (int64_t)16 * 2 * B * 4 * Hd_ + 1024;
     for (int i = 0; i < 4; i++) dec_ws[i] = alloc<float>(dec_ws_floats);
     // tensor-core encoder recurrence (engine_enc_tc.cu)
     const int64_t He_ = c.encoder_num_hidden;
@@ -203,10 +205,11 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   enc_dh = alloc<float>(2 * B * He); enc_dc = alloc<float>(2 * B * He);
   dsrc = alloc<float>(S * B * 512);
 
-  X1 = alloc<float>(T * B * K1);  C1 = alloc<float>((T + 1) * B * Hd); ACT1 = alloc<float>(T * B * 4 * Hd);
-  X2 = alloc<float>(T * B * 2 * Hd); C2 = alloc<float>((T + 1) * B * Hd); ACT2 = alloc<float>(T * B * 4 * Hd);
-  CAT = alloc<float>(T * B * 2 * Hd); Q = alloc<float>(T * B * Hd); ALPHA = alloc<float>(T * B * S);
-  A_all = alloc<float>(T * B * Hd);
+  const int64_t B2 = 2 * B;   // see the dual decode pass (engine_dec.cu: decode_enqueue)
+  X1 = alloc<float>(T * B2 * K1);  C1 = alloc<float>((T + 1) * B2 * Hd); ACT1 = alloc<float>(T * B2 * 4 * Hd);
+  X2 = alloc<float>(T * B2 * 2 * Hd); C2 = alloc<float>((T + 1) * B2 * Hd); ACT2 = alloc<float>(T * B2 * 4 * Hd);
+  CAT = alloc<float>(T * B2 * 2 * Hd); Q = alloc<float>(T * B2 * Hd); ALPHA = alloc<float>(T * B2 * S);
+  A_all = alloc<float>(T * B2 * Hd); tokseq = alloc<int32_t>((T + 1) * B2);
   Ptab = alloc<float>((int64_t)V * 4 * Hd); bsum1 = alloc<float>(4 * Hd); bsum2 = alloc<float>(4 * Hd);
   Gs = alloc<float>(B * 4 * Hd);
   for (int i = 0; i < 3; i++) logp[i] = alloc<float>(T * B * V);

@@ -98,7 +98,7 @@ class Engine {
   void cnn_backward();
   void encoder_forward();
   void encoder_backward();
-  void decoder_init();
+  void decoder_init(int reps = 1);
   void attention_precompute();
   void decoder_step(int t, const int32_t* tok);
   void decoder_backward();
@@ -114,12 +114,14 @@ class Engine {
   void emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols);
   void encoder_dir_forward(int d);
   void encoder_dir_backward(int d);
-  enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4, PK_DEC_GREEDY = 6 };
+  enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4, PK_DEC_GREEDY = 6, PK_DEC_DUAL = 7 };
+  int dual_rows_ = 0;   // > 0 while the dual decode pass is recorded / initialised: the number of real batch rows
   struct ProgKey { int kind, b, S, nsteps, variant; bool operator<(const ProgKey& o) const {
     return std::tie(kind, b, S, nsteps, variant) < std::tie(o.kind, o.b, o.S, o.nsteps, o.variant); } };
   std::map<ProgKey, PersistProgram> programs_;
   PersistProgram* rec_ = nullptr;
   int rec_max_ctas_ = 128;
+  bool dual_on_ = true;         // AOCR_DUAL=0: greedy and gold decode passes one after the other
   bool persist_on_ = true;      // AOCR_PERSIST=0: per-kernel chains instead of the persistent executor
   void run_program(int kind, int nsteps, int variant);
   void encoder_forward_steps_tc();
@@ -220,7 +222,7 @@ class Engine {
   float *logp[3] = {}, *dZ = nullptr, *rowloss = nullptr, *dAgen = nullptr, *dU = nullptr, *dCAT = nullptr,
         *DE = nullptr, *dQ = nullptr, *dH2q = nullptr, *dG2 = nullptr, *dG1 = nullptr, *dX2 = nullptr, *dX1 = nullptr,
         *dc1 = nullptr, *dc2 = nullptr, *dP = nullptr, *CtxWc = nullptr, *dCtxWc = nullptr;
-  int32_t *tok = nullptr, *labels = nullptr;
+  int32_t *tok = nullptr, *labels = nullptr, *tokseq = nullptr;
   double *score = nullptr, *d_loss = nullptr, *d_sumsq = nullptr, *d_sq_partial = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 };

@@ -11,25 +11,28 @@ namespace aocr {
 // model.lua:539-552 / 360-372 / 589-602.  Quirk Q14: with -input_feed the reference's
 // "zero layers >= 2" loop indexes the state list without the input-feed offset and so zeroes h1(0); the
 // decoder starts from c1(0) = [c_fw(S); c_bw(1)], h1(0) = 0.  Without input feed h1(0) = [h_fw(S); h_bw(1)].
-void Engine::decoder_init() {
+void Engine::decoder_init(int reps) {
   const int B = b_, S = S_;
   const int64_t slot = (int64_t)B * He;
   const float* cfw = Cenc + ((int64_t)0 * (S + 1) + S) * slot;
   const float* cbw = Cenc + ((int64_t)1 * (S + 1) + 0) * slot;
-  concat_enc_finals(ctx_, cfw, cbw, C1, Hd, B, He);
-  fill_zero(ctx_, X1, (size_t)B * K1 * sizeof(float));
-  if (!cfg.input_feed) {
-    const float* hfw = Henc + ((int64_t)0 * (S + 1) + S) * slot;
-    const float* hbw = Henc + ((int64_t)1 * (S + 1) + 0) * slot;
-    concat_enc_finals(ctx_, hfw, hbw, X1, K1, B, He);
+  const int64_t BR = (int64_t)B * reps;            // reps = 2: the dual decode pass, rows [B, 2B) start from the same state
+  fill_zero(ctx_, X1, (size_t)BR * K1 * sizeof(float));
+  for (int r = 0; r < reps; r++) {
+    concat_enc_finals(ctx_, cfw, cbw, C1 + (int64_t)r * B * Hd, Hd, B, He);
+    if (!cfg.input_feed) {
+      const float* hfw = Henc + ((int64_t)0 * (S + 1) + S) * slot;
+      const float* hbw = Henc + ((int64_t)1 * (S + 1) + 0) * slot;
+      concat_enc_finals(ctx_, hfw, hbw, X1 + (int64_t)r * B * K1, K1, B, He);
+    }
   }
-  fill_zero(ctx_, C2, (size_t)B * Hd * sizeof(float));
-  fill_zero(ctx_, X2, (size_t)B * 2 * Hd * sizeof(float));
+  fill_zero(ctx_, C2, (size_t)BR * Hd * sizeof(float));
+  fill_zero(ctx_, X2, (size_t)BR * 2 * Hd * sizeof(float));
   if (cfg.gemm_mode != 2) {   // the same initial state as bf16 operand planes for the first step's GEMMs
-    Pack x1_0 = X1p; x1_0.rows = B;
-    split_to_pack(ctx_, X1, B, K1, K1, 1, x1_0);
-    fill_zero(ctx_, X2p.hi, (size_t)B * 2 * Hd * sizeof(__nv_bfloat16));
-    fill_zero(ctx_, X2p.lo, (size_t)B * 2 * Hd * sizeof(__nv_bfloat16));
+    Pack x1_0 = X1p; x1_0.rows = BR;
+    split_to_pack(ctx_, X1, BR, K1, K1, 1, x1_0);
+    fill_zero(ctx_, X2p.hi, (size_t)BR * 2 * Hd * sizeof(__nv_bfloat16));
+    fill_zero(ctx_, X2p.lo, (size_t)BR * 2 * Hd * sizeof(__nv_bfloat16));
   }
 }
 
@@ -512,6 +515,28 @@ void Engine::decode_enqueue() {
   encoder_forward();
   attention_precompute();
   dec_steps_ = Ld;
+  if (persist_on_ && cfg.gemm_mode != 2 && 2 * B <= 128 && dual_on_) {
+    // Dual pass: the greedy pass and the teacher-forced gold pass are independent recurrences over the same encoder
+    // state, and a decoder step is bound by streaming the weights, not by the batch: run them as ONE batch of 2B rows
+    // (rows [0,B) greedy, rows [B,2B) gold) and halve the number of sequential steps (model.lua:360-404 + 589-627).
+    const int B2 = 2 * B;
+    AOCR_CUDA(cudaMemcpyAsync(tokseq, tgt_tb, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx_.st));  // GO row
+    AOCR_CUDA(cudaMemcpy2DAsync(tokseq + B, (size_t)B2 * sizeof(int32_t), tgt_tb, (size_t)B * sizeof(int32_t),
+                                (size_t)B * sizeof(int32_t), (size_t)Ld, cudaMemcpyDeviceToDevice, ctx_.st));
+    decoder_init(2);
+    dual_rows_ = B;
+    b_ = B2;
+    try {
+      run_program(PK_DEC_DUAL, Ld, 0);
+    } catch (...) {
+      b_ = B; dual_rows_ = 0;
+      throw;
+    }
+    b_ = B; dual_rows_ = 0;
+    reduce_sum_double(ctx_, rowloss, (int64_t)Ld * B, d_loss);
+    last_logp_rows_[1] = last_logp_rows_[2] = Ld * B;
+    return;
+  }
   // greedy pass
   AOCR_CUDA(cudaMemcpyAsync(tok, tgt_tb, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx_.st));  // GO row
   decoder_init();

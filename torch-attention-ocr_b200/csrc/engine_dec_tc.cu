@@ -165,7 +165,7 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   ao.alpha = ALPHA + (int64_t)t * B * S; ao.q_out = Q + (int64_t)t * B * Hd; ao.a_out = A_all + (int64_t)t * B * Hd;
   ao.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; ao.ld_next = K1;
   ao.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();
-  ao.B = B; ao.S = S; ao.H = Hd;
+  ao.B = B; ao.S = S; ao.H = Hd; ao.ctx_rows = dual_rows_;
   emit(ao);
 }
 

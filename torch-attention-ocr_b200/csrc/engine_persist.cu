@@ -38,7 +38,26 @@ void Engine::run_program(int kind, int nsteps, int variant) {
             gp.R = b_; gp.H = Hd; gp.V = V; gp.inv_bn = 1.0f;
             prog.add(P_GENERATOR, gp);
             GreedyTc gs;
-            gs.logp = gp.logp; gs.tok = tok; gs.score = score; gs.labels = labels; gs.ldl = Tmax; gs.t = t; gs.B = b_; gs.V = V;
+            gs.logp = gp.logp; gs.tok = tok; gs.tok_out = tok; gs.score = score; gs.labels = labels; gs.ldl = Tmax; gs.t = t; gs.B = b_; gs.V = V;
+            prog.add(P_GREEDY, gs);
+          }
+          dec_steps_ = save;
+          break;
+        }
+        case PK_DEC_DUAL: {     // b_ = 2B here: rows [0,B) greedy (argmax feedback), rows [B,2B) teacher forced
+          const int save = dec_steps_, Bh = dual_rows_;
+          dec_steps_ = nsteps;
+          for (int t = 0; t < nsteps; t++) {
+            decoder_step_tc(t, tokseq + (int64_t)t * b_);
+            GenTc gp;
+            gp.a = A_all + (int64_t)t * b_ * Hd; gp.W = d_params + L.wo; gp.bias = d_params + L.bo;
+            gp.y = tev_tb + (int64_t)t * Bh; gp.logp = logp[1] + (int64_t)t * Bh * V; gp.logp2 = logp[2] + (int64_t)t * Bh * V;
+            gp.dz = nullptr; gp.rowloss = rowloss + (int64_t)t * Bh; gp.split = Bh;
+            gp.R = b_; gp.H = Hd; gp.V = V; gp.inv_bn = 1.0f;
+            prog.add(P_GENERATOR, gp);
+            GreedyTc gs;
+            gs.logp = gp.logp; gs.tok = tokseq + (int64_t)t * b_; gs.tok_out = tokseq + (int64_t)(t + 1) * b_;
+            gs.score = score; gs.labels = labels; gs.ldl = Tmax; gs.t = t; gs.B = Bh; gs.V = V;
             prog.add(P_GREEDY, gs);
           }
           dec_steps_ = save;

@@ -42,6 +42,7 @@ struct AttnOutTc {
   float* a_out;                               // (B, H) a_t
   float* x_next; int64_t ld_next; PackOut pk_next;   // input feed of step t+1 (may be null)
   int B, S, H;
+  int ctx_rows = 0;                           // > 0: batch row b attends over source b % ctx_rows (dual pass)
 };
 void attn_out_tc(Ctx&, const AttnOutTc&);
 // Backward of the same: du = (da_gen + da_carry) (1 - a^2);  d alpha_s = ctxwc_s . du;  de = softmax backward;
@@ -58,8 +59,12 @@ void attn_du_tc(Ctx&, const AttnDuTc&);
 struct GenTc {
   const float* a; const float* W; const float* bias; const int32_t* y; float* logp; float* dz; float* rowloss;
   int R, H, V; float inv_bn;
+  // dual pass (greedy rows [0, split) + teacher-forced rows [split, R) in one batch): rows >= split write their
+  // log-probs to logp2 and take y / rowloss at index r - split; rows < split have no target.  split = 0: off.
+  int split = 0; float* logp2 = nullptr;
 };
-struct GreedyTc { float* logp; int32_t* tok; double* score; int32_t* labels; long long ldl; int t, B, V; };
+// tok: token chosen at step t-1 (read for the sticky-PAD rule); tok_out: where the token of step t goes (may alias tok)
+struct GreedyTc { float* logp; const int32_t* tok; int32_t* tok_out; double* score; int32_t* labels; long long ldl; int t, B, V; };
 inline size_t attn_smem_bytes(int S, int H) { return (size_t)(((S + 3) & ~3) + 16 + 9 * H) * sizeof(float); }
 
 }  // namespace aocr

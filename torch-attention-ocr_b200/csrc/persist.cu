@@ -4,6 +4,8 @@
 // mbarrier phases and the TMEM allocation persist across commands; a grid barrier (one global counter, acquire /
 // release, preceded by fence.proxy.async so the generic-proxy stores of a command are visible to the TMA loads of
 // the next one on every SM) replaces the kernel boundary between consecutive commands.
+#include <algorithm>
+
 #include "persist.h"
 
 #include "dec_bodies.cuh"
@@ -84,10 +86,10 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
   for (int c = 0; c < ncmds; c++) {
     const PCmd& cmd = cmds[c];
     const int type = cmd.type;
-    if (trace && bid == 0 && threadIdx.x == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      trace[2 * c] = t;
+    unsigned long long t_begin = 0;
+    if (trace && threadIdx.x == 0) {
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
+      if (bid == 0) trace[2 * c] = t_begin;
     }
     if (type == P_GEMM) {
       const PGemm g = payload<PGemm>(cmd);
@@ -205,10 +207,14 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         __syncthreads();
       }
     }
-    if (trace && bid == 0 && threadIdx.x == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      trace[2 * c + 1] = t;      // work of CTA 0 done; the barrier wait follows
+    if (trace) {
+      __syncthreads();           // (tracing only) the whole CTA is done with the command
+      if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (bid == 0) trace[2 * c + 1] = t;      // work of CTA 0 done; the barrier wait follows
+        trace[2 * (ncmds + 1) + (size_t)c * nblk + bid] = t - t_begin;
+      }
     }
     grid_sync(barrier, (unsigned)nblk, epoch);
   }
@@ -283,8 +289,9 @@ void persist_upload(Ctx& ctx, PersistProgram& prog) {
   AOCR_CUDA(cudaMalloc(&prog.d_maps, (prog.maps.size() + 1) * sizeof(CUtensorMap)));
   AOCR_CUDA(cudaMalloc(&prog.d_barrier, 256));
   if (getenv("AOCR_PERSIST_TRACE")) {
-    AOCR_CUDA(cudaMalloc(&prog.d_trace, (prog.cmds.size() + 1) * 2 * sizeof(unsigned long long)));
-    AOCR_CUDA(cudaMemset(prog.d_trace, 0, (prog.cmds.size() + 1) * 2 * sizeof(unsigned long long)));
+    const size_t nt = (prog.cmds.size() + 1) * 2 + prog.cmds.size() * (size_t)prog.grid;
+    AOCR_CUDA(cudaMalloc(&prog.d_trace, nt * sizeof(unsigned long long)));
+    AOCR_CUDA(cudaMemset(prog.d_trace, 0, nt * sizeof(unsigned long long)));
   }
   AOCR_CUDA(cudaMemcpy(prog.d_cmds, prog.cmds.data(), prog.cmds.size() * sizeof(PCmd), cudaMemcpyHostToDevice));
   if (!prog.maps.empty())
@@ -307,15 +314,29 @@ void persist_free(PersistProgram& prog) {
   if (prog.d_maps) cudaFree(prog.d_maps);
   if (prog.d_barrier) cudaFree(prog.d_barrier);
   if (prog.d_trace) {   // AOCR_PERSIST_TRACE: per-command time of CTA 0 (work, then barrier wait), averaged by type
-    std::vector<unsigned long long> t(prog.cmds.size() * 2);
+    const size_t nc = prog.cmds.size(), ng = (size_t)prog.grid;
+    std::vector<unsigned long long> t((nc + 1) * 2 + nc * ng);
     cudaMemcpy(t.data(), prog.d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    double work[16] = {0}, wait[16] = {0}; int cnt[16] = {0};
-    for (size_t c = 0; c + 1 < prog.cmds.size(); c++) {
+    double work[16] = {0}, wait[16] = {0}, wmax[16] = {0}, wmed[16] = {0}; int cnt[16] = {0};
+    std::vector<int> slow(16 * ng, 0);
+    for (size_t c = 0; c + 1 < nc; c++) {
       int ty = prog.cmds[c].type & 15;
       work[ty] += (double)(t[2 * c + 1] - t[2 * c]); wait[ty] += (double)(t[2 * c + 2] - t[2 * c + 1]); cnt[ty]++;
+      std::vector<unsigned long long> w(t.begin() + (nc + 1) * 2 + c * ng, t.begin() + (nc + 1) * 2 + (c + 1) * ng);
+      size_t am = 0;
+      for (size_t i = 0; i < ng; i++) if (w[i] > w[am]) am = i;
+      slow[ty * ng + am]++;
+      wmax[ty] += (double)w[am];
+      std::sort(w.begin(), w.end());
+      wmed[ty] += (double)w[ng / 2];
     }
-    fprintf(stderr, "[persist trace] %zu cmds grid %d:", prog.cmds.size(), prog.grid);
-    for (int ty = 0; ty < 16; ty++) if (cnt[ty]) fprintf(stderr, " type%d n=%d work=%.2fus wait=%.2fus;", ty, cnt[ty], work[ty] / cnt[ty] / 1e3, wait[ty] / cnt[ty] / 1e3);
+    fprintf(stderr, "[persist trace] %zu cmds grid %d:", nc, prog.grid);
+    for (int ty = 0; ty < 16; ty++) if (cnt[ty]) {
+      size_t top = 0;
+      for (size_t i = 0; i < ng; i++) if (slow[ty * ng + i] > slow[ty * ng + top]) top = i;
+      fprintf(stderr, " type%d n=%d cta0 work=%.2fus wait=%.2fus | all CTAs: median %.2fus max %.2fus (slowest most often: CTA %zu, %d times);",
+              ty, cnt[ty], work[ty] / cnt[ty] / 1e3, wait[ty] / cnt[ty] / 1e3, wmed[ty] / cnt[ty] / 1e3, wmax[ty] / cnt[ty] / 1e3, top, slow[ty * ng + top]);
+    }
     fprintf(stderr, "\n");
     cudaFree(prog.d_trace); prog.d_trace = nullptr;
   }
