@@ -112,6 +112,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (const char* e = getenv("AOCR_GRAPHS")) graphs_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_PERSIST")) persist_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_DUAL")) dual_on_ = atoi(e) != 0;
+  if (const char* e = getenv("AOCR_FUSE")) fuse_on_ = atoi(e) != 0;
   if (c.batch_size > 128 || c.gemm_mode == 2) persist_on_ = false;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));
@@ -175,7 +176,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     // tensor-core encoder recurrence (engine_enc_tc.cu)
     const int64_t He_ = c.encoder_num_hidden;
     for (int d = 0; d < 2; d++) {
-      Whp[d] = alloc_pack(4 * He_, He_); WhTp[d] = alloc_pack(He_, 4 * He_);
+      Whp[d] = alloc_pack(4 * He_, He_); WhTp[d] = alloc_pack(He_, 4 * He_); WhpG[d] = alloc_pack(4 * He_, He_);
       HencP[d] = alloc_pack((S + 1) * B, He_); dGeP[d] = alloc_pack(B, 4 * He_);
     }
   }

@@ -109,6 +109,19 @@ class Engine {
   void build_decoder_packs();
   // emitters: launch a piece of a recurrence as its own kernel, or record it into a persistent program
   TcOut emit_gemm(const Pack& W, int M, const Pack& X, int64_t row0, int64_t k0, int K, float* ws);
+  template <typename CellT>
+  void emit_gemm_fused(int type, const Pack& W, int M, const Pack& X, int64_t row0, int64_t k0, int K, const CellT& cell) {
+    const int terms = cfg.gemm_mode == 1 ? 1 : 3;
+    PGemmPlan pl = persist_plan_gemm_fused(M, b_, K, rec_->cluster);
+    PGemm g{};
+    g.map_a = rec_->add_map_pair(tc_map_2d(W.hi, W.rows, W.kp, 128), tc_map_2d(W.lo, W.rows, W.kp, 128));
+    g.map_b = rec_->add_map_pair(tc_map_2d(X.hi, X.rows, X.kp, rec_->bn), tc_map_2d(X.lo, X.rows, X.kp, rec_->bn));
+    g.m_tiles = pl.m_tiles; g.splits = pl.splits; g.kb_per = pl.kb_per; g.num_kb = pl.num_kb;
+    g.b_row0 = (int)row0; g.b_k0 = (int)k0; g.M = M; g.N = b_; g.terms = terms;
+    g.ws = nullptr; g.part_stride = 0; g.ldc = M;
+    rec_->add2(type, g, cell);
+    if (pl.m_tiles * pl.splits > rec_->grid) rec_->grid = pl.m_tiles * pl.splits;
+  }
   void emit(const CellFwdTc& p); void emit(const CellBwdTc& p);
   void emit(const EncCellFwdTc& p); void emit(const EncCellBwdTc& p); void emit(const AttnOutTc& p); void emit(const AttnDuTc& p);
   void emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols);
@@ -189,6 +202,9 @@ class Engine {
   Pack X1p, X2p, H2p, dUQp, dG2p, dG1p;
   Pack actp_[8];   // act[l] (input of conv l+1) as bf16 planes, written by the producing kernel; reused by the weight gradient
   Pack Whp[2], WhTp[2], HencP[2], dGeP[2];
+  Pack WhpG[2];     // W_h with gate-interleaved rows (fused GEMM -> cell commands of the executor)
+  bool fuse_on_ = true;   // AOCR_FUSE=0: separate GEMM and cell commands
+  int cluster_ = 4;       // thread-block cluster size of the executor launches
   float* dec_ws[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t dec_ws_floats = 0;
   int64_t dec_packs_version_ = -1;

@@ -20,12 +20,17 @@ void Engine::encoder_dir_forward(int d) {
   for (int i = 0; i < S; i++) {
     const int t = d == 0 ? i : S - 1 - i;
     const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
-    TcOut o = emit_gemm(Whp[d], 4 * He, HencP[d], (int64_t)prev_slot * B, 0, He, dec_ws[d]);
     EncCellFwdTc c;
-    c.G[d].p = o.base; c.G[d].nz = o.nz; c.G[d].stride = o.stride; c.G[d].ld = 4 * He;
     c.hp[d] = out_of(HencP[d], (int64_t)out_slot * B);
     c.xg = xg; c.H = Henc; c.Cst = Cenc; c.acts = acts_enc; c.ctx = ctx; c.B = B; c.S = S; c.He = He; c.step = i;
     c.d_only = d;
+    if (rec_ && fuse_on_ && rec_->cluster > 1 && He % 32 == 0 && pad64(He) / 64 >= rec_->cluster) {
+      // one command: GEMM tile per cluster (rows gate-interleaved), split-K over the cluster ranks, DSMEM reduce + cell
+      emit_gemm_fused(P_GEMM_ENC_FWD, WhpG[d], 4 * He, HencP[d], (int64_t)prev_slot * B, 0, He, c);
+      continue;
+    }
+    TcOut o = emit_gemm(Whp[d], 4 * He, HencP[d], (int64_t)prev_slot * B, 0, He, dec_ws[d]);
+    c.G[d].p = o.base; c.G[d].nz = o.nz; c.G[d].stride = o.stride; c.G[d].ld = 4 * He;
     emit(c);
   }
 }
@@ -53,6 +58,7 @@ void Engine::encoder_forward_steps_tc() {
   if (enc_packs_version_ != weights_version_) {
     for (int d = 0; d < 2; d++) {
       split_to_pack(ctx_, d_params + L.enc_wh[d], 4 * He, He, He, 1, Whp[d]);       // rows = gate units
+      if (He % 32 == 0) split_to_pack(ctx_, d_params + L.enc_wh[d], 4 * He, He, He, 1, WhpG[d], -1, He);   // gate-interleaved
       split_to_pack(ctx_, d_params + L.enc_wh[d], He, 4 * He, 1, He, WhTp[d]);      // rows = input units (transpose)
     }
     enc_packs_version_ = weights_version_;

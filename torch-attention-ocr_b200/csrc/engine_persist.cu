@@ -17,6 +17,8 @@ void Engine::run_program(int kind, int nsteps, int variant) {
     int cap = persist_max_ctas(bn);
     rec_max_ctas_ = enc ? (cap / 2 < 64 ? cap / 2 : 64) : (cap < 128 ? cap : 128);   // both encoder directions co-resident
     prog.grid = 1;
+    prog.cluster = cluster_;
+    if (const char* e = getenv("AOCR_CLUSTER")) prog.cluster = atoi(e);
     rec_ = &prog;
     try {
       switch (kind) {
@@ -77,6 +79,7 @@ void Engine::run_program(int kind, int nsteps, int variant) {
     rec_ = nullptr;
     if (prog.grid < 16) prog.grid = 16;      // the bodies are grid-stride: a few more CTAs cost nothing
     if (prog.grid > rec_max_ctas_) prog.grid = rec_max_ctas_;
+    prog.grid = ((prog.grid + prog.cluster - 1) / prog.cluster) * prog.cluster;
     it = programs_.emplace(key, std::move(prog)).first;
   }
   PersistProgram& prog = it->second;

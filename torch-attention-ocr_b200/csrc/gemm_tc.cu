@@ -297,7 +297,7 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& h, __nv_bfloat16&
 __global__ void __launch_bounds__(256) split_kfast_kernel(const float* __restrict__ src, int64_t rows, int64_t K,
                                                           int64_t srs, int64_t kp, int64_t kw,
                                                           __nv_bfloat16* __restrict__ hi,
-                                                          __nv_bfloat16* __restrict__ lo) {
+                                                          __nv_bfloat16* __restrict__ lo, int64_t gate_h) {
   pdl_launch_dependents();
   pdl_wait();
   const int64_t kq = kw / 4;   // kw = columns written (zero padded past K), kp = row pitch of the planes
@@ -317,8 +317,11 @@ __global__ void __launch_bounds__(256) split_kfast_kernel(const float* __restric
     __nv_bfloat16 h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) split2(v[j], h[j], l[j]);
-    *reinterpret_cast<uint2*>(hi + r * kp + k) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + r * kp + k) = *reinterpret_cast<uint2*>(l);
+    // gate_h > 0: source rows are [gate][unit] (4 x gate_h); destination rows are gate-interleaved in blocks of 32
+    // units, (unit/32)*128 + gate*32 + unit%32, so one 128-row UMMA tile holds all four gates of 32 hidden units
+    const int64_t rd = gate_h > 0 ? ((r % gate_h) / 32) * 128 + (r / gate_h) * 32 + (r % gate_h) % 32 : r;
+    *reinterpret_cast<uint2*>(hi + rd * kp + k) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + rd * kp + k) = *reinterpret_cast<uint2*>(l);
   }
 }
 // general strides (typically srs == 1: the transposing case): 32x32 tile through shared memory
@@ -459,7 +462,8 @@ bool gemm_tc_available() {
 }
 
 void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst,
-                   int64_t kwrite) {
+                   int64_t kwrite, int64_t gate_h) {
+  AOCR_CHECK(gate_h == 0 || (sks == 1 && rows == 4 * gate_h && gate_h % 32 == 0), "split_to_pack: bad gate interleave request");
   int64_t kw = kwrite;
   if (kw < 0) {
     AOCR_CHECK(dst.kp == pad64(K), "split_to_pack: destination pitch must be K rounded up to 64");
@@ -471,7 +475,7 @@ void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t 
     int64_t g = (total + 255) / 256;
     int64_t cap = (int64_t)ctx.num_sms * 8;
     launch_pdl(ctx, split_kfast_kernel, dim3((unsigned)(g < cap ? (g > 0 ? g : 1) : cap)), dim3(256), 0, src, rows, K, srs,
-               dst.kp, kw, dst.hi, dst.lo);
+               dst.kp, kw, dst.hi, dst.lo, gate_h);
   } else {
     dim3 grid((unsigned)((kw + 31) / 32), (unsigned)((rows + 31) / 32));
     launch_pdl(ctx, split_tile_kernel, grid, dim3(256), 0, src, rows, K, srs, sks, dst.kp, kw, dst.hi, dst.lo);

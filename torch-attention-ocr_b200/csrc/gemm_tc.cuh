@@ -20,7 +20,7 @@ inline int64_t pad64(int64_t k) { return (k + 63) & ~(int64_t)63; }
 // kwrite < 0: write the whole padded row (dst.kp == pad64(K)); otherwise write exactly `kwrite` (>= K, % 4 == 0)
 // columns of a wider pack (used to assemble concatenated weight packs).
 void split_to_pack(Ctx& ctx, const float* src, int64_t rows, int64_t K, int64_t srs, int64_t sks, const Pack& dst,
-                   int64_t kwrite = -1);
+                   int64_t kwrite = -1, int64_t gate_h = 0);
 
 // NHWC view of a Pack for the implicit-GEMM convolution: rows = n*H*W pixels, kp = C channels.
 struct ConvView {

@@ -6,6 +6,8 @@
 // the next one on every SM) replaces the kernel boundary between consecutive commands.
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "persist.h"
 
 #include "dec_bodies.cuh"
@@ -15,6 +17,7 @@ namespace aocr {
 
 namespace {
 using namespace tcp;
+namespace cg = cooperative_groups;
 
 template <int BN> struct PCfg {
   static constexpr int kStages = (BN == 128) ? 3 : 4;
@@ -39,6 +42,50 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned nblk, unsigned
     } while (v < target);
   }
   __syncthreads();
+}
+
+// ---- fused GEMM -> cell: the cluster owns 32 hidden units x 4 gates (gate-interleaved weight rows: tile row =
+// gate*32 + unit) for the whole batch; rank z holds the split-K partial z in shared memory as stage[column][row].
+// Rank z finishes batch columns [z*BN/nz, (z+1)*BN/nz): sums the nz partials of the 4 gates through DSMEM, applies the
+// LSTM cell and writes what the stand-alone cell body writes.
+template <int BN>
+__device__ __forceinline__ void fused_enc_cell_fwd(const EncCellFwdTc& p, cg::cluster_group& cluster, float* stage, int mt,
+                                                   int z, int nz) {
+  const int He = p.He, B = p.B, S = p.S;
+  const int d = p.d_only;
+  const int ul = threadIdx.x & 31, unit = mt * 32 + ul;
+  const int cols = BN / nz;
+  const int t = d == 0 ? p.step : S - 1 - p.step;
+  const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
+  const float* rs[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) rs[q] = q < nz ? cluster.map_shared_rank(stage, q) : stage;
+  for (int bq = threadIdx.x >> 5; bq < cols; bq += 8) {
+    const int b = z * cols + bq;
+    if (b >= B || unit >= He) continue;
+    float gsum[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = q < nz ? rs[q][b * BM + g * 32 + ul] : 0.f;
+      gsum[g] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    const float* xg = p.xg + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
+    const float i_ = decb::sigmoidf_(gsum[0] + xg[0]);
+    const float f_ = decb::sigmoidf_(gsum[1] + xg[He]);
+    const float o_ = decb::sigmoidf_(gsum[2] + xg[2 * He]);
+    const float g_ = tanhf(gsum[3] + xg[3 * He]);
+    const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
+    const float c = f_ * cp + i_ * g_;
+    const float h = o_ * tanhf(c);
+    p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit] = c;
+    p.H[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit] = h;
+    float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
+    a[0] = i_; a[He] = f_; a[2 * He] = o_; a[3 * He] = g_;
+    p.ctx[((int64_t)b * S + t) * (2 * He) + d * He + unit] = h;
+    decb::pack_store(p.hp[d], b, unit, h);
+  }
 }
 
 template <typename T>
@@ -91,11 +138,17 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
       if (bid == 0) trace[2 * c] = t_begin;
     }
-    if (type == P_GEMM) {
+    if (type == P_GEMM || type == P_GEMM_ENC_FWD) {
+      // P_GEMM: tile (mt, z) = (bid % m_tiles, bid / m_tiles), raw split-K partial -> global workspace.
+      // Fused commands: the cluster is the M tile and the rank in the cluster is the split; the partial goes to this
+      // CTA's shared memory (the idle TMA ring), the cluster reduces through DSMEM and applies the cell right away.
+      const bool fused = (type != P_GEMM);
       const PGemm g = payload<PGemm>(cmd);
       const int ntiles = g.m_tiles * g.splits;
+      const int z = fused ? (int)(bid % g.splits) : bid / g.m_tiles;
+      const int mt = fused ? (int)(bid / g.splits) : bid % g.m_tiles;
+      float* stage = reinterpret_cast<float*>(smem_raw + (base - raw));   // [BN columns][128 rows] fp32
       if (bid < ntiles) {
-        const int z = bid / g.m_tiles, mt = bid % g.m_tiles;
         const int kb_begin = z * g.kb_per;
         const int kb_end = min(g.num_kb, kb_begin + g.kb_per);
         const int nkb = kb_end - kb_begin;
@@ -166,7 +219,11 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < g.M) {
+            if (fused) {
+              // all of this CTA's MMAs have retired (tmem_full), so the ring is free: stage[column][tile row]
+#pragma unroll
+              for (int j = 0; j < 16; j++) stage[(c0 + j) * BM + q * 32 + lane] = __uint_as_float(r[j]);
+            } else if (row < g.M) {
 #pragma unroll
               for (int j = 0; j < 16; j++) {
                 const int n = c0 + j;
@@ -178,6 +235,16 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         }
         it += (uint32_t)nkb;
         tiles += 1;
+      }
+      if (fused) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();                                       // every rank's partial tile is in its shared memory
+        if (bid < ntiles) {
+          if (type == P_GEMM_ENC_FWD)
+            fused_enc_cell_fwd<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z,
+                                   g.splits);
+        }
+        cluster.sync();                                       // peers are done reading this CTA's partial
       }
     } else if (type == P_CELL_FWD) {
       decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);
@@ -241,8 +308,17 @@ void launch_bn(Ctx& ctx, PersistProgram& prog) {
   unsigned long long* trace = prog.d_trace;
   void* args[] = {(void*)&cmds, (void*)&ncmds, (void*)&maps, (void*)&bar, (void*)&trace};
   AOCR_CUDA(cudaMemsetAsync(prog.d_barrier, 0, sizeof(unsigned), ctx.st));
-  AOCR_CUDA(cudaLaunchCooperativeKernel((const void*)persist_kernel<BN>, dim3(prog.grid), dim3(256), args,
-                                        (size_t)PCfg<BN>::kSmemBytes, ctx.st));
+  // cooperative (all CTAs co-resident: the grid barrier spins) + thread-block clusters of kCluster CTAs (the fused
+  // GEMM -> cell commands reduce their split-K partials through distributed shared memory inside a cluster)
+  cudaLaunchConfig_t cfgl = {};
+  cfgl.gridDim = dim3(prog.grid); cfgl.blockDim = dim3(256);
+  cfgl.dynamicSmemBytes = (size_t)PCfg<BN>::kSmemBytes; cfgl.stream = ctx.st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = prog.cluster; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+  cfgl.attrs = attrs; cfgl.numAttrs = prog.cluster > 1 ? 2 : 1;
+  AOCR_CUDA(cudaLaunchKernelExC(&cfgl, (const void*)persist_kernel<BN>, args));
   ctx.launches++;
 }
 
@@ -270,6 +346,17 @@ PGemmPlan persist_plan_gemm(int M, int N, int K, int max_ctas, long long ws_floa
   while (splits > 1 && (long long)splits * p.part_stride > ws_floats) splits--;
   p.kb_per = (p.num_kb + splits - 1) / splits;
   p.splits = (p.num_kb + p.kb_per - 1) / p.kb_per;
+  return p;
+}
+
+PGemmPlan persist_plan_gemm_fused(int M, int N, int K, int cluster) {
+  PGemmPlan p;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.num_kb = (int)(pad64(K) / BK);
+  p.part_stride = 0;
+  p.kb_per = (p.num_kb + cluster - 1) / cluster;
+  p.splits = cluster;
+  AOCR_CHECK((p.num_kb + p.kb_per - 1) / p.kb_per == cluster, "fused GEMM: K too short for one k-block range per cluster rank");
   return p;
 }
 

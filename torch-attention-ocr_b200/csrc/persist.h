@@ -13,7 +13,8 @@
 namespace aocr {
 
 enum PType {
-  P_GEMM = 0, P_CELL_FWD, P_CELL_BWD, P_ATTN_OUT, P_ATTN_DU, P_ENC_CELL_FWD, P_ENC_CELL_BWD, P_TO_DENSE, P_GENERATOR, P_GREEDY
+  P_GEMM = 0, P_CELL_FWD, P_CELL_BWD, P_ATTN_OUT, P_ATTN_DU, P_ENC_CELL_FWD, P_ENC_CELL_BWD, P_TO_DENSE, P_GENERATOR, P_GREEDY,
+  P_GEMM_ENC_FWD      // fused: PGemm immediately followed by the EncCellFwdTc of the same step
 };
 
 // swap-AB GEMM with the batch on the UMMA N side: partial z of out(n, m) at ws[z*part_stride + n*ldc + m]
@@ -30,7 +31,7 @@ struct PToDense { PartIn in; float* dst; long long ld; int B, cols; };
 struct alignas(16) PCmd {
   int type;
   int pad[3];
-  unsigned char payload[240];
+  unsigned char payload[368];
 };
 
 struct PersistProgram {                 // host-side, then uploaded
@@ -38,6 +39,7 @@ struct PersistProgram {                 // host-side, then uploaded
   std::vector<CUtensorMap> maps;
   int grid = 1;                         // CTAs (>= the largest number of GEMM tiles of any command)
   int bn = 64;                          // UMMA N = batch rounded up to {16,32,64,128}
+  int cluster = 1;                      // thread-block cluster size of the launch (grid is a multiple of it)
   // device copies
   PCmd* d_cmds = nullptr;
   CUtensorMap* d_maps = nullptr;
@@ -48,6 +50,14 @@ struct PersistProgram {                 // host-side, then uploaded
   int add_map_pair(const CUtensorMap& hi, const CUtensorMap& lo) {
     maps.push_back(hi); maps.push_back(lo);
     return (int)maps.size() - 2;
+  }
+  template <typename A, typename B> void add2(int type, const A& a, const B& b) {   // fused command: two payloads back to back
+    static_assert(sizeof(A) + sizeof(B) <= sizeof(PCmd::payload), "fused command payload too large");
+    PCmd c{};
+    c.type = type;
+    memcpy(c.payload, &a, sizeof(A));
+    memcpy(c.payload + sizeof(A), &b, sizeof(B));
+    cmds.push_back(c);
   }
   template <typename T> void add(int type, const T& p) {
     static_assert(sizeof(T) <= sizeof(PCmd::payload), "command payload too large");
@@ -61,6 +71,8 @@ struct PersistProgram {                 // host-side, then uploaded
 // plan of one swap-AB GEMM inside a program: split factor such that m_tiles * splits <= max_ctas
 struct PGemmPlan { int m_tiles, splits, kb_per, num_kb; long long part_stride; };
 PGemmPlan persist_plan_gemm(int M, int N, int K, int max_ctas, long long ws_floats);
+// fused GEMM -> cell: exactly `cluster` splits (one per CTA of the cluster that owns the M tile)
+PGemmPlan persist_plan_gemm_fused(int M, int N, int K, int cluster);
 
 void persist_upload(Ctx& ctx, PersistProgram& prog);     // allocates + copies (once)
 void persist_launch(Ctx& ctx, PersistProgram& prog);     // cooperative launch on ctx.st
