@@ -113,6 +113,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (const char* e = getenv("AOCR_PERSIST")) persist_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_DUAL")) dual_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_FUSE")) fuse_on_ = atoi(e) != 0;
+  if (const char* e = getenv("AOCR_CLUSTER")) cluster_ = atoi(e) > 0 ? atoi(e) : 1;
   if (c.batch_size > 128 || c.gemm_mode == 2) persist_on_ = false;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));
@@ -165,6 +166,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     // tensor-core decoder path (engine_dec_tc.cu)
     const int64_t Hd_ = 2 * c.encoder_num_hidden, K1_ = c.input_feed ? 2 * Hd_ : Hd_, Tm = c.max_decoder_l;
     Wcat1p = alloc_pack(4 * Hd_, K1_); Wcat2p = alloc_pack(4 * Hd_, 2 * Hd_);
+    Wcat1pG = alloc_pack(4 * Hd_, K1_); Wcat2pG = alloc_pack(4 * Hd_, 2 * Hd_);
     W3p = alloc_pack(2 * Hd_, Hd_);
     Wcat1Tp = alloc_pack(K1_, 4 * Hd_); Wcat2Tp = alloc_pack(2 * Hd_, 4 * Hd_);
     W3Tp = alloc_pack(Hd_, 2 * Hd_);

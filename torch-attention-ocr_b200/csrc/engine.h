@@ -107,6 +107,12 @@ class Engine {
   void decoder_backward_steps_simt();
   void decoder_backward_steps_tc();
   void build_decoder_packs();
+  bool fused_rec() const { return rec_ && fuse_on_ && rec_->cluster > 1; }
+  // the decoder layers use the fused GEMM -> cell commands (and therefore the gate-interleaved weight packs)
+  bool dec_fused_ok() const {
+    return persist_on_ && fuse_on_ && cluster_ > 1 && b_ <= 128 && cfg.gemm_mode != 2 && Hd % 32 == 0 &&
+           pad64(K1) / 64 >= cluster_ && pad64(2 * Hd) / 64 >= cluster_;
+  }
   // emitters: launch a piece of a recurrence as its own kernel, or record it into a persistent program
   TcOut emit_gemm(const Pack& W, int M, const Pack& X, int64_t row0, int64_t k0, int K, float* ws);
   template <typename CellT>
@@ -202,6 +208,8 @@ class Engine {
   Pack X1p, X2p, H2p, dUQp, dG2p, dG1p;
   Pack actp_[8];   // act[l] (input of conv l+1) as bf16 planes, written by the producing kernel; reused by the weight gradient
   Pack Whp[2], WhTp[2], HencP[2], dGeP[2];
+  Pack Wcat1pG, Wcat2pG;   // decoder [W_i | W_h] with gate-interleaved rows (fused commands)
+  bool dec_packs_inter_ = false;   // which row order the forward packs currently hold
   Pack WhpG[2];     // W_h with gate-interleaved rows (fused GEMM -> cell commands of the executor)
   bool fuse_on_ = true;   // AOCR_FUSE=0: separate GEMM and cell commands
   int cluster_ = 4;       // thread-block cluster size of the executor launches

@@ -91,14 +91,21 @@ void Engine::emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int 
 
 // (re)build the decoder weight packs after a parameter change
 void Engine::build_decoder_packs() {
-  if (dec_packs_version_ == weights_version_) return;
+  const bool want_inter = dec_fused_ok();
+  if (dec_packs_version_ == weights_version_ && dec_packs_inter_ == want_inter) return;
   const int in1 = E + (cfg.input_feed ? Hd : 0);
   const float* P = d_params;
-  // forward packs: rows = output units (the UMMA M side), K = concatenated inputs
-  if (cfg.input_feed) split_to_pack(ctx_, P + L.l1_wi + E, 4 * Hd, Hd, in1, 1, sub_cols(Wcat1p, 0), Hd);
-  split_to_pack(ctx_, P + L.l1_wh, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat1p, h1off), Hd);
-  split_to_pack(ctx_, P + L.l2_wi, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat2p, 0), Hd);
-  split_to_pack(ctx_, P + L.l2_wh, 4 * Hd, Hd, Hd, 1, sub_cols(Wcat2p, Hd), Hd);
+  // forward packs: rows = output units (the UMMA M side), K = concatenated inputs.  The executor's fused GEMM -> cell
+  // commands want the gate-interleaved row order, the per-kernel path the plain [gate][unit] order: build what is used
+  const bool inter = dec_fused_ok();
+  const int64_t gh = inter ? Hd : 0;
+  const Pack& W1 = inter ? Wcat1pG : Wcat1p;
+  const Pack& W2 = inter ? Wcat2pG : Wcat2p;
+  if (cfg.input_feed) split_to_pack(ctx_, P + L.l1_wi + E, 4 * Hd, Hd, in1, 1, sub_cols(W1, 0), Hd, gh);
+  split_to_pack(ctx_, P + L.l1_wh, 4 * Hd, Hd, Hd, 1, sub_cols(W1, h1off), Hd, gh);
+  split_to_pack(ctx_, P + L.l2_wi, 4 * Hd, Hd, Hd, 1, sub_cols(W2, 0), Hd, gh);
+  split_to_pack(ctx_, P + L.l2_wh, 4 * Hd, Hd, Hd, 1, sub_cols(W2, Hd), Hd, gh);
+  dec_packs_inter_ = inter;
   split_to_pack(ctx_, P + L.wa, Hd, Hd, Hd, 1, sub_rows(W3p, 0, Hd));                 // rows 0..H-1   : W_a
   split_to_pack(ctx_, P + L.wc + Hd, Hd, Hd, 2 * Hd, 1, sub_rows(W3p, Hd, Hd));        // rows H..2H-1  : W_c[:, H:]
   // backward packs: rows = input units, K = output units (transposes)
@@ -135,9 +142,9 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   float* cat = CAT + (int64_t)t * B * 2 * Hd;
   const int64_t r0 = (int64_t)t * B, r1 = (int64_t)(t + 1) * B;
   // ---- layer 1
-  TcOut g1 = emit_gemm(Wcat1p, 4 * Hd, X1p, r0, 0, K1, dec_ws[0]);
+  const bool fuse = fused_rec() && dec_packs_inter_ && rec_->cluster == cluster_;
   CellFwdTc c1;
-  c1.G = part_in(g1, 4 * Hd); c1.addrows = Ptab; c1.rowsel = tokens; c1.addld = 4 * Hd;
+  c1.addrows = Ptab; c1.rowsel = tokens; c1.addld = 4 * Hd;
   c1.c_prev = C1 + (int64_t)t * B * Hd; c1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
   c1.acts = ACT1 + (int64_t)t * B * 4 * Hd;
   c1.h_out0 = x2; c1.ld0 = 2 * Hd;
@@ -145,11 +152,16 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   c1.pk0 = pack_out(X2p, r0, 0);
   c1.pk1 = has_next ? pack_out(X1p, r1, h1off) : PackOut();
   c1.B = B; c1.H = Hd;
-  emit(c1);
+  if (fuse) {
+    emit_gemm_fused(P_GEMM_CELL_FWD, Wcat1pG, 4 * Hd, X1p, r0, 0, K1, c1);
+  } else {
+    TcOut g1 = emit_gemm(Wcat1p, 4 * Hd, X1p, r0, 0, K1, dec_ws[0]);
+    c1.G = part_in(g1, 4 * Hd);
+    emit(c1);
+  }
   // ---- layer 2
-  TcOut g2 = emit_gemm(Wcat2p, 4 * Hd, X2p, r0, 0, 2 * Hd, dec_ws[1]);
   CellFwdTc c2;
-  c2.G = part_in(g2, 4 * Hd); c2.addrows = bsum2; c2.rowsel = nullptr; c2.addld = 0;
+  c2.addrows = bsum2; c2.rowsel = nullptr; c2.addld = 0;
   c2.c_prev = C2 + (int64_t)t * B * Hd; c2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
   c2.acts = ACT2 + (int64_t)t * B * 4 * Hd;
   c2.h_out0 = cat + Hd; c2.ld0 = 2 * Hd;
@@ -157,7 +169,13 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   c2.pk0 = pack_out(H2p, r0, 0);
   c2.pk1 = has_next ? pack_out(X2p, r1, Hd) : PackOut();
   c2.B = B; c2.H = Hd;
-  emit(c2);
+  if (fuse) {
+    emit_gemm_fused(P_GEMM_CELL_FWD, Wcat2pG, 4 * Hd, X2p, r0, 0, 2 * Hd, c2);
+  } else {
+    TcOut g2 = emit_gemm(Wcat2p, 4 * Hd, X2p, r0, 0, 2 * Hd, dec_ws[1]);
+    c2.G = part_in(g2, 4 * Hd);
+    emit(c2);
+  }
   // ---- [q ; v] = [W_a ; W_c2] h2, then scores / softmax / alpha-weighted ctxwc + v / tanh in one body
   TcOut g3 = emit_gemm(W3p, 2 * Hd, H2p, r0, 0, Hd, dec_ws[2]);
   AttnOutTc ao;

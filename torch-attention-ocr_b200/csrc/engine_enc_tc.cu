@@ -40,12 +40,17 @@ void Engine::encoder_dir_backward(int d) {
   const int64_t slot = (int64_t)B * He;
   PartIn dh;
   dh.p = enc_dh + d * slot; dh.nz = 1; dh.stride = 0; dh.ld = He;    // decoder seeds
-  for (int i = 0; i < S; i++) {
+  auto cell_of = [&](int i) {
     EncCellBwdTc c;
-    c.dh[d] = dh;
     c.Cst = Cenc; c.acts = acts_enc; c.Dctx = Dctx; c.dc = enc_dc; c.dG = dGe;
     c.dgp[d] = out_of(dGeP[d], 0);
     c.B = B; c.S = S; c.He = He; c.step = i; c.d_only = d;
+    return c;
+  };
+  // (a fused GEMM -> cell-backward command was measured and lost: M = He gives only 4 tiles = 16 CTAs per direction)
+  for (int i = 0; i < S; i++) {
+    EncCellBwdTc c = cell_of(i);
+    c.dh[d] = dh;
     emit(c);
     // dh_prev = dG_t W_h : rows of W_h^T on the M side, K = 4He
     TcOut o = emit_gemm(WhTp[d], He, dGeP[d], 0, 0, 4 * He, dec_ws[2 + d]);

@@ -18,7 +18,6 @@ void Engine::run_program(int kind, int nsteps, int variant) {
     rec_max_ctas_ = enc ? (cap / 2 < 64 ? cap / 2 : 64) : (cap < 128 ? cap : 128);   // both encoder directions co-resident
     prog.grid = 1;
     prog.cluster = cluster_;
-    if (const char* e = getenv("AOCR_CLUSTER")) prog.cluster = atoi(e);
     rec_ = &prog;
     try {
       switch (kind) {

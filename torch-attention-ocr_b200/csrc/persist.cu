@@ -88,6 +88,45 @@ __device__ __forceinline__ void fused_enc_cell_fwd(const EncCellFwdTc& p, cg::cl
   }
 }
 
+// decoder layer: same structure, CellFwdTc semantics (embedding / bias rows added per batch row)
+template <int BN>
+__device__ __forceinline__ void fused_cell_fwd(const CellFwdTc& p, cg::cluster_group& cluster, float* stage, int mt, int z,
+                                               int nz) {
+  const int H = p.H;
+  const int ul = threadIdx.x & 31, u = mt * 32 + ul;
+  const int cols = BN / nz;
+  const float* rs[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) rs[q] = q < nz ? cluster.map_shared_rank(stage, q) : stage;
+  for (int bq = threadIdx.x >> 5; bq < cols; bq += 8) {
+    const int b = z * cols + bq;
+    if (b >= p.B || u >= H) continue;
+    float gsum[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) v[q] = q < nz ? rs[q][b * BM + g * 32 + ul] : 0.f;
+      gsum[g] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    const float* ar = p.addrows + (p.rowsel ? (int64_t)(__ldcg(p.rowsel + b) - 1) * p.addld : 0) + u;
+    const float i_ = decb::sigmoidf_(gsum[0] + ar[0]);
+    const float f_ = decb::sigmoidf_(gsum[1] + ar[H]);
+    const float o_ = decb::sigmoidf_(gsum[2] + ar[2 * H]);
+    const float g_ = tanhf(gsum[3] + ar[3 * H]);
+    const int64_t e = (int64_t)b * H + u;
+    const float c = f_ * p.c_prev[e] + i_ * g_;
+    const float h = o_ * tanhf(c);
+    p.c_new[e] = c;
+    float* a = p.acts + (int64_t)b * 4 * H + u;
+    a[0] = i_; a[H] = f_; a[2 * H] = o_; a[3 * H] = g_;
+    p.h_out0[(int64_t)b * p.ld0 + u] = h;
+    if (p.h_out1) p.h_out1[(int64_t)b * p.ld1 + u] = h;
+    decb::pack_store(p.pk0, b, u, h);
+    decb::pack_store(p.pk1, b, u, h);
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ const T& payload(const PCmd& c) { return *reinterpret_cast<const T*>(c.payload); }
 
@@ -138,7 +177,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
       if (bid == 0) trace[2 * c] = t_begin;
     }
-    if (type == P_GEMM || type == P_GEMM_ENC_FWD) {
+    if (type == P_GEMM || type >= P_GEMM_ENC_FWD) {
       // P_GEMM: tile (mt, z) = (bid % m_tiles, bid / m_tiles), raw split-K partial -> global workspace.
       // Fused commands: the cluster is the M tile and the rank in the cluster is the split; the partial goes to this
       // CTA's shared memory (the idle TMA ring), the cluster reduces through DSMEM and applies the cell right away.
@@ -243,8 +282,11 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
           if (type == P_GEMM_ENC_FWD)
             fused_enc_cell_fwd<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z,
                                    g.splits);
+          else
+            fused_cell_fwd<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z, g.splits);
         }
-        cluster.sync();                                       // peers are done reading this CTA's partial
+        // no second cluster barrier: the grid barrier that ends the command orders the peers' reads of this CTA's
+        // partial before anything reuses the ring
       }
     } else if (type == P_CELL_FWD) {
       decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);

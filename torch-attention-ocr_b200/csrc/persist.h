@@ -14,7 +14,8 @@ namespace aocr {
 
 enum PType {
   P_GEMM = 0, P_CELL_FWD, P_CELL_BWD, P_ATTN_OUT, P_ATTN_DU, P_ENC_CELL_FWD, P_ENC_CELL_BWD, P_TO_DENSE, P_GENERATOR, P_GREEDY,
-  P_GEMM_ENC_FWD      // fused: PGemm immediately followed by the EncCellFwdTc of the same step
+  P_GEMM_ENC_FWD,     // fused: PGemm immediately followed by the EncCellFwdTc of the same step
+  P_GEMM_CELL_FWD     // fused: PGemm + CellFwdTc (decoder layer)
 };
 
 // swap-AB GEMM with the batch on the UMMA N side: partial z of out(n, m) at ws[z*part_stride + n*ldc + m]
