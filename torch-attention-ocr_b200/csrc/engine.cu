@@ -142,6 +142,8 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (cfg.gemm_mode != 2) {
     const int64_t n_act[7] = {0, B * 16 * W1 * 64, B * 8 * W2 * 128, B * 8 * W2 * 256, B * 4 * W2 * 256, B * 4 * W2 * 512, B * 2 * W2 * 512};
     for (int l = 1; l <= 6; l++) actp_[l] = alloc_pack(1, n_act[l]);
+    const int64_t n_z[7] = {0, B * 16 * W1 * 128, B * 8 * W2 * 256, B * 8 * W2 * 256, B * 4 * W2 * 512, B * 4 * W2 * 512, B * S * 512};
+    for (int l = 1; l <= 6; l++) dzp_[l] = alloc_pack(1, n_z[l]);   // dz of conv_{l+1} has the shape of zb[l+1]
   }
   const int bnc[3] = {256, 512, 512};
   for (int i = 0; i < 3; i++) {
@@ -521,8 +523,7 @@ void Engine::cnn_backward() {
     // dz as bf16 planes, written by the kernel that produces dz: shared by the weight- and the data-gradient GEMM
     const bool tc = cfg.gemm_mode != 2;
     Pack dzp;
-    dzp.rows = rows; dzp.kp = c.cout; dzp.hi = tc ? scratch_[0].hi : nullptr; dzp.lo = tc ? scratch_[0].lo : nullptr;
-    if (tc) AOCR_CHECK(rows * c.cout <= scratch_elems_, "dz larger than the scratch pack");
+    dzp.rows = rows; dzp.kp = c.cout; dzp.hi = tc ? dzp_[l].hi : nullptr; dzp.lo = tc ? dzp_[l].lo : nullptr;
     if (c.bn >= 0) {
       const bool last = (l == 6);
       const float* mean = cnn_train_ ? bn_mean[c.bn] : bn_rmean[c.bn];
@@ -537,7 +538,13 @@ void Engine::cnn_backward() {
     col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);
     // weight grad: dW[co][tap,ci] = sum_rows dz[row][co] * col[row][tap,ci]
     if (cfg.gemm_mode != 2) {
+      // the weight gradient feeds nothing downstream: lane 2 (idle since the encoder backward), so it fills the
+      // partial waves of the data-gradient chain that continues on lane 0; operands are per-layer packs (no reuse race)
+      fork_to(2);
+      use_lane(2);
       conv_wgrad_tc(dz, act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, c.cout, d_grads + L.conv_w[l], &dzp, &actp_[l]);
+      if (l == 4 && cnn_bucket_split_ >= 0) grad_range(cnn_bucket_split_, L.goff[G_CNN] + L.gphys[G_CNN]);
+      use_lane(0);
     } else {
       im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
       Gemm gw;
@@ -564,10 +571,10 @@ void Engine::cnn_backward() {
     }
     dcur = gB;
     // next iteration writes dz into gA again and reads dcur=gB: fine (distinct buffers)
-    if (l == 4 && cnn_bucket_split_ >= 0) grad_range(cnn_bucket_split_, L.goff[G_CNN] + L.gphys[G_CNN]);
   }
   const int nblk = 256;
   conv1_bwd(ctx_, x0, act[1], pidx[1], dcur, d_grads + L.conv_w[0], d_grads + L.conv_b[0], partial, nblk, B, W_);
+  join_from(2);
 }
 
 // ---------------------------------------------------------------------------------------------
