@@ -199,13 +199,6 @@ void Engine::decoder_backward() {
   g.B = d_params + L.wo; g.sbk = Hd; g.sbn = 1;
   g.C = dAgen; g.ldc = Hd;
   gemm(g);
-  g = Gemm();
-  g.M = V; g.N = Hd; g.K = (int)R;                       // dW_o = dZ^T A
-  g.A = dZ; g.sam = 1; g.sak = V;
-  g.B = A_all; g.sbk = Hd; g.sbn = 1;
-  g.C = d_grads + L.wo; g.ldc = Hd;
-  gemm(g);
-  col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
 
   if (cfg.gemm_mode != 2) {
     if (persist_on_) {
@@ -232,6 +225,13 @@ void Engine::decoder_backward() {
   fork_to(1);
   use_lane(1);
   // ---- time-batched parameter gradients (weights are tied across t: clone_many_times, model_utils.lua:3-50)
+  g = Gemm();
+  g.M = V; g.N = Hd; g.K = (int)R;                       // dW_o = dZ^T A   (feeds nothing in the chain: lane 1)
+  g.A = dZ; g.sam = 1; g.sak = V;
+  g.B = A_all; g.sbk = Hd; g.sbn = 1;
+  g.C = d_grads + L.wo; g.ldc = Hd;
+  gemm(g);
+  col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
   auto wgrad = [&](const float* dY, int M, const float* X, int64_t ldx, int N, float* dW, int64_t ldw) {
     Gemm w;
     w.M = M; w.N = N; w.K = (int)R;

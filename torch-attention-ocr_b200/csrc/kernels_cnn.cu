@@ -262,6 +262,46 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
     partial[(int64_t)blockIdx.y * C + c] = s;
   }
 }
+// both batch-norm backward sums in one pass over dy and z: s1 = sum dy, s2 = sum dy * xhat.  partial: [2][nslab][C]
+__global__ void __launch_bounds__(256) col_reduce_bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                                                                const float* __restrict__ mean, const float* __restrict__ var,
+                                                                int64_t R, int C, int64_t rows_per, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + tx;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per;
+  int64_t r1 = r0 + rows_per < R ? r0 + rows_per : R;
+  float a1 = 0.f, a2 = 0.f;
+  if (c < C) {
+    const float mu = mean[c], inv = rsqrtf(var[c] + BN_EPS);
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float v = dy[r * C + c];
+      a1 += v;
+      a2 = fmaf(v, (z[r * C + c] - mu) * inv, a2);
+    }
+  }
+  __shared__ float red[2][8][33];
+  red[0][ty][tx] = a1; red[1][ty][tx] = a2;
+  __syncthreads();
+  if (ty < 2 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += red[ty][i][tx];
+    partial[((int64_t)ty * gridDim.y + blockIdx.y) * C + c] = s;
+  }
+}
+__global__ void col_reduce_final2_kernel(const float* __restrict__ partial, int nslab, int C, float* __restrict__ out1,
+                                         float* __restrict__ out2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * C) return;
+  const int which = c / C, cc = c % C;
+  float s = 0.f;
+  for (int i = 0; i < nslab; i++) s += partial[((int64_t)which * nslab + i) * C + cc];
+  (which ? out2 : out1)[cc] = s;
+}
 // out[c] (op)= scale * sum_slab partial ; op: 0 set, 1 add
 __global__ void col_reduce_final_kernel(const float* __restrict__ partial, int nslab, int C, float scale, int accumulate,
                                         float* __restrict__ out) {
@@ -476,8 +516,16 @@ void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, cons
   launch_pdl(ctx, relu_mask_kernel, dim3(grid_for(R * (C / 4), 256, ctx.num_sms)), dim3(256), 0, da, a, dz, R, C, tm_S, tm_B);
   AOCR_CUDA(cudaGetLastError());
   // dbeta = s1 ; dgamma = s2 (each BN parameter receives gradient exactly once per step)
-  col_reduce(ctx, dz, nullptr, nullptr, nullptr, R, C, 0, 1.0f, 0, dbeta, partial);
-  col_reduce(ctx, dz, z, mean, var, R, C, 2, 1.0f, 0, dgamma, partial);
+  {   // one pass, the summation order of the two separate reductions
+    int ns = nslabs_for(R, ctx.num_sms, C);
+    if (ns > 128) ns = 128;                       // partial holds [2][ns][C]
+    int64_t rows_per = (R + ns - 1) / ns;
+    launch_pdl(ctx, col_reduce_bn_bwd_kernel, dim3(cdiv(C, 32), ns), dim3(256), 0, (const float*)dz, z, mean, var, R, C, rows_per,
+               partial);
+    AOCR_CUDA(cudaGetLastError());
+    launch_pdl(ctx, col_reduce_final2_kernel, dim3(cdiv(2 * C, 128)), dim3(128), 0, (const float*)partial, ns, C, dbeta, dgamma);
+    AOCR_CUDA(cudaGetLastError());
+  }
   if (sync.world > 1) {   // global sums of dy and dy*xhat (dgamma, dbeta are adjacent: one all-reduce when contiguous)
     if (dbeta == dgamma + C) sync.fn(sync.user, dgamma, 2 * (int64_t)C);
     else { sync.fn(sync.user, dgamma, C); sync.fn(sync.user, dbeta, C); }
