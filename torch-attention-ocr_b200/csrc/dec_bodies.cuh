@@ -114,7 +114,7 @@ constexpr int ATT_WARPS = 8;
 constexpr int ATT_MAXV = 8;
 
 // attention + output projection of batch row b (see AttnOutTc)
-__device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, float* sm) {
+__device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, float* sm, bool keep_a = false) {
   const int S = p.S, H = p.H;
   float* es = sm;
   float* wm = es + ((S + 3) & ~3);
@@ -201,6 +201,7 @@ __device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, floa
     *reinterpret_cast<float4*>(p.a_out + (int64_t)b * H + e4) = a;
     if (p.x_next) *reinterpret_cast<float4*>(p.x_next + (int64_t)b * p.ld_next + e4) = a;
     pack_store4(p.pk_next, b, e4, a);
+    if (keep_a) *reinterpret_cast<float4*>(qs + e4) = a;      // q is dead: a_t stays in shared memory for the generator tail
   }
   for (int s = threadIdx.x; s < S; s += blockDim.x) p.alpha[(int64_t)b * S + s] = expf(es[s] - M) / L;
 }
@@ -409,6 +410,74 @@ __device__ __forceinline__ void generator_body(const GenTc& p, int bid, int nblk
       }
     }
     __syncthreads();
+  }
+}
+// Generator + selection for ONE batch row r whose a_t is in shared memory (`as`): logits, log-softmax, then either the
+// greedy selection (rows < g.split: sticky PAD, argmax with lowest-index ties, score, next token; model.lua:393-404,
+// 446-459) or the teacher-forced row loss (rows >= g.split).  Tail of the dual decode pass: no grid barrier between
+// attention+output, generator and selection, all three are local to the CTA that owns the row.
+__device__ __forceinline__ void gen_select_tail(const GenTc& g, const GreedyTc& s, int r, const float* as, float* zs) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nw = blockDim.x / 32;
+  const int nv = g.H / 128, V = g.V, H = g.H;
+  __syncthreads();                                   // a_t complete in shared memory
+  float4 av[ATT_MAXV];
+#pragma unroll
+  for (int i = 0; i < ATT_MAXV; i++)
+    av[i] = (i < nv) ? *reinterpret_cast<const float4*>(as + lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = warp; v < V; v += nw) {
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < ATT_MAXV; i++) {
+      if (i < nv) {
+        const float4 w = *reinterpret_cast<const float4*>(g.W + (int64_t)v * H + lane * 4 + 128 * i);
+        dot += w.x * av[i].x + w.y * av[i].y + w.z * av[i].z + w.w * av[i].w;
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) zs[v] = dot + g.bias[v];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const float z0 = lane < V ? zs[lane] : -INFINITY;
+    const float z1 = lane + 32 < V ? zs[lane + 32] : -INFINITY;
+    const float mx = warp_max_(fmaxf(z0, z1));
+    float se = (lane < V ? expf(z0 - mx) : 0.f) + (lane + 32 < V ? expf(z1 - mx) : 0.f);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    float lp0 = z0 - lse, lp1 = z1 - lse;            // log-probs of v = lane, lane + 32
+    const bool second = r >= g.split;
+    const int64_t ro = second ? r - g.split : r;
+    float* lpo = second ? g.logp2 : g.logp;
+    if (second) {
+      const int yy = g.y[ro] - 1;
+      const float w = yy != 0 ? 1.f : 0.f;
+      if (lane < V) lpo[ro * V + lane] = lp0;
+      if (lane + 32 < V) lpo[ro * V + lane + 32] = lp1;
+      if (lane == yy) g.rowloss[ro] = -w * lp0;
+      if (lane + 32 == yy) g.rowloss[ro] = -w * lp1;
+    } else {
+      if (s.t > 0 && lane == 0) {
+        const int prev = __ldcg(s.tok + r);
+        if (prev == 1 || prev == 3) lp0 = 0.f;       // sticky PAD: log-prob[PAD] <- 0 (model.lua:448-449)
+      }
+      if (lane < V) lpo[ro * V + lane] = lp0;
+      if (lane + 32 < V) lpo[ro * V + lane + 32] = lp1;
+      // argmax, ties to the lowest index (the reference's max returns the first maximum)
+      float best = lane < V ? lp0 : -INFINITY;
+      int bi = lane;
+      if (lane + 32 < V && lp1 > best) { best = lp1; bi = lane + 32; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) {
+        s.score[r] = (s.t == 0 ? 0.0 : __ldcg(s.score + r)) + (double)best;
+        s.tok_out[r] = bi + 1;
+        s.labels[(int64_t)r * s.ldl + s.t] = bi + 1;
+      }
+    }
   }
 }
 // sticky-PAD edit, argmax, score accumulate, next token (model.lua:402,448-458); one thread per batch row

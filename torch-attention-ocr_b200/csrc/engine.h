@@ -134,6 +134,8 @@ class Engine {
   void encoder_dir_forward(int d);
   void encoder_dir_backward(int d);
   enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4, PK_DEC_GREEDY = 6, PK_DEC_DUAL = 7 };
+  struct StepTail { GenTc gen; GreedyTc sel; };
+  const StepTail* tail_ = nullptr;   // set while recording a dual decode step: generator + selection ride on the attention command
   int dual_rows_ = 0;   // > 0 while the dual decode pass is recorded / initialised: the number of real batch rows
   struct ProgKey { int kind, b, S, nsteps, variant; bool operator<(const ProgKey& o) const {
     return std::tie(kind, b, S, nsteps, variant) < std::tie(o.kind, o.b, o.S, o.nsteps, o.variant); } };

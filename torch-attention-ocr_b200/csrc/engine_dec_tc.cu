@@ -184,7 +184,8 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   ao.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; ao.ld_next = K1;
   ao.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();
   ao.B = B; ao.S = S; ao.H = Hd; ao.ctx_rows = dual_rows_;
-  emit(ao);
+  if (rec_ && tail_) rec_->add3(P_ATTN_OUT_GEN, ao, tail_->gen, tail_->sel);
+  else emit(ao);
 }
 
 // per-timestep part of the decoder backward (model.lua:643-661) on tensor cores: three bodies + three GEMMs per step

@@ -49,17 +49,18 @@ void Engine::run_program(int kind, int nsteps, int variant) {
           const int save = dec_steps_, Bh = dual_rows_;
           dec_steps_ = nsteps;
           for (int t = 0; t < nsteps; t++) {
-            decoder_step_tc(t, tokseq + (int64_t)t * b_);
-            GenTc gp;
+            StepTail tl;
+            GenTc& gp = tl.gen;
             gp.a = A_all + (int64_t)t * b_ * Hd; gp.W = d_params + L.wo; gp.bias = d_params + L.bo;
             gp.y = tev_tb + (int64_t)t * Bh; gp.logp = logp[1] + (int64_t)t * Bh * V; gp.logp2 = logp[2] + (int64_t)t * Bh * V;
             gp.dz = nullptr; gp.rowloss = rowloss + (int64_t)t * Bh; gp.split = Bh;
             gp.R = b_; gp.H = Hd; gp.V = V; gp.inv_bn = 1.0f;
-            prog.add(P_GENERATOR, gp);
-            GreedyTc gs;
+            GreedyTc& gs = tl.sel;
             gs.logp = gp.logp; gs.tok = tokseq + (int64_t)t * b_; gs.tok_out = tokseq + (int64_t)(t + 1) * b_;
             gs.score = score; gs.labels = labels; gs.ldl = Tmax; gs.t = t; gs.B = Bh; gs.V = V;
-            prog.add(P_GREEDY, gs);
+            tail_ = &tl;                // generator + selection ride on the step's attention+output command
+            try { decoder_step_tc(t, tokseq + (int64_t)t * b_); } catch (...) { tail_ = nullptr; throw; }
+            tail_ = nullptr;
           }
           dec_steps_ = save;
           break;

@@ -130,7 +130,9 @@ __device__ __forceinline__ void fused_cell_fwd(const CellFwdTc& p, cg::cluster_g
 template <typename T>
 __device__ __forceinline__ const T& payload(const PCmd& c) { return *reinterpret_cast<const T*>(c.payload); }
 
-template <int BN>
+// kDecode: the decode-only commands (generator, selection, merged attention tail) are compiled in.  Training programs use
+// the instance without them: their register allocation and code layout do not pay for the decode tail.
+template <int BN, bool kDecode>
 __global__ void __launch_bounds__(256, 1)
 persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __restrict__ maps, unsigned* barrier,
                unsigned long long* trace) {
@@ -177,7 +179,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
       if (bid == 0) trace[2 * c] = t_begin;
     }
-    if (type == P_GEMM || type >= P_GEMM_ENC_FWD) {
+    if (type == P_GEMM || type == P_GEMM_ENC_FWD || type == P_GEMM_CELL_FWD) {
       // P_GEMM: tile (mt, z) = (bid % m_tiles, bid / m_tiles), raw split-K partial -> global workspace.
       // Fused commands: the cluster is the M tile and the rank in the cluster is the split; the partial goes to this
       // CTA's shared memory (the idle TMA ring), the cluster reduces through DSMEM and applies the cell right away.
@@ -299,15 +301,28 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
     } else if (type == P_TO_DENSE) {
       const PToDense p = payload<PToDense>(cmd);
       decb::part_to_dense_body(p.in, p.dst, p.ld, p.B, p.cols, bid, nblk, scratch);
-    } else if (type == P_GENERATOR) {
-      decb::generator_body(payload<GenTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_GREEDY) {
-      decb::greedy_select_body(payload<GreedyTc>(cmd), bid, nblk, scratch);
+    } else if (kDecode && type == P_GENERATOR) {
+      if constexpr (kDecode) decb::generator_body(payload<GenTc>(cmd), bid, nblk, scratch);
+    } else if (kDecode && type == P_GREEDY) {
+      if constexpr (kDecode) decb::greedy_select_body(payload<GreedyTc>(cmd), bid, nblk, scratch);
     } else if (type == P_ATTN_OUT) {
       const AttnOutTc p = payload<AttnOutTc>(cmd);
       for (int b = bid; b < p.B; b += nblk) {
         decb::attn_out_tc_body(p, b, scratch);
         __syncthreads();
+      }
+    } else if (kDecode && type == P_ATTN_OUT_GEN) {
+      if constexpr (kDecode) {
+      const AttnOutTc p = payload<AttnOutTc>(cmd);
+      const GenTc& gp = *reinterpret_cast<const GenTc*>(cmd.payload + sizeof(AttnOutTc));
+      const GreedyTc& gs = *reinterpret_cast<const GreedyTc*>(cmd.payload + sizeof(AttnOutTc) + sizeof(GenTc));
+      float* as = scratch + ((p.S + 3) & ~3) + 16 + 8 * p.H;     // = the `qs` region of the attention body
+      float* zs = as + p.H;
+      for (int b = bid; b < p.B; b += nblk) {
+        decb::attn_out_tc_body(p, b, scratch, true);
+        decb::gen_select_tail(gp, gs, b, as, zs);
+        __syncthreads();
+      }
       }
     } else if (type == P_ATTN_DU) {
       const AttnDuTc p = payload<AttnDuTc>(cmd);
@@ -336,11 +351,11 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
   }
 }
 
-template <int BN>
+template <int BN, bool kDecode>
 void launch_bn(Ctx& ctx, PersistProgram& prog) {
   static bool attr_set = false;
   if (!attr_set) {
-    AOCR_CUDA(cudaFuncSetAttribute(persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes));
+    AOCR_CUDA(cudaFuncSetAttribute(persist_kernel<BN, kDecode>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes));
     attr_set = true;
   }
   const PCmd* cmds = prog.d_cmds;
@@ -360,7 +375,7 @@ void launch_bn(Ctx& ctx, PersistProgram& prog) {
   attrs[1].id = cudaLaunchAttributeClusterDimension;
   attrs[1].val.clusterDim.x = prog.cluster; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
   cfgl.attrs = attrs; cfgl.numAttrs = prog.cluster > 1 ? 2 : 1;
-  AOCR_CUDA(cudaLaunchKernelExC(&cfgl, (const void*)persist_kernel<BN>, args));
+  AOCR_CUDA(cudaLaunchKernelExC(&cfgl, (const void*)persist_kernel<BN, kDecode>, args));
   ctx.launches++;
 }
 
@@ -369,8 +384,8 @@ int max_ctas_bn() {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaFuncSetAttribute(persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel<BN>, 256, (size_t)PCfg<BN>::kSmemBytes);
+  cudaFuncSetAttribute(persist_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel<BN, true>, 256, (size_t)PCfg<BN>::kSmemBytes);
   return sms * per_sm;
 }
 
@@ -430,11 +445,13 @@ void persist_upload(Ctx& ctx, PersistProgram& prog) {
 
 void persist_launch(Ctx& ctx, PersistProgram& prog) {
   AOCR_CHECK(prog.uploaded, "persistent program not uploaded");
+  bool dec = false;
+  for (const PCmd& c : prog.cmds) dec = dec || c.type == P_GENERATOR || c.type == P_GREEDY || c.type == P_ATTN_OUT_GEN;
   switch (prog.bn) {
-    case 128: launch_bn<128>(ctx, prog); break;
-    case 64: launch_bn<64>(ctx, prog); break;
-    case 32: launch_bn<32>(ctx, prog); break;
-    default: launch_bn<16>(ctx, prog); break;
+    case 128: dec ? launch_bn<128, true>(ctx, prog) : launch_bn<128, false>(ctx, prog); break;
+    case 64: dec ? launch_bn<64, true>(ctx, prog) : launch_bn<64, false>(ctx, prog); break;
+    case 32: dec ? launch_bn<32, true>(ctx, prog) : launch_bn<32, false>(ctx, prog); break;
+    default: dec ? launch_bn<16, true>(ctx, prog) : launch_bn<16, false>(ctx, prog); break;
   }
 }
 

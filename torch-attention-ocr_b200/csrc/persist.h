@@ -15,7 +15,8 @@ namespace aocr {
 enum PType {
   P_GEMM = 0, P_CELL_FWD, P_CELL_BWD, P_ATTN_OUT, P_ATTN_DU, P_ENC_CELL_FWD, P_ENC_CELL_BWD, P_TO_DENSE, P_GENERATOR, P_GREEDY,
   P_GEMM_ENC_FWD,     // fused: PGemm immediately followed by the EncCellFwdTc of the same step
-  P_GEMM_CELL_FWD     // fused: PGemm + CellFwdTc (decoder layer)
+  P_GEMM_CELL_FWD,    // fused: PGemm + CellFwdTc (decoder layer)
+  P_ATTN_OUT_GEN      // AttnOutTc + GenTc + GreedyTc: attention+output, generator and selection of a dual decode step
 };
 
 // swap-AB GEMM with the batch on the UMMA N side: partial z of out(n, m) at ws[z*part_stride + n*ldc + m]
@@ -51,6 +52,16 @@ struct PersistProgram {                 // host-side, then uploaded
   int add_map_pair(const CUtensorMap& hi, const CUtensorMap& lo) {
     maps.push_back(hi); maps.push_back(lo);
     return (int)maps.size() - 2;
+  }
+  template <typename A, typename B, typename C> void add3(int type, const A& a, const B& b, const C& c3) {
+    static_assert(sizeof(A) + sizeof(B) + sizeof(C) <= sizeof(PCmd::payload), "fused command payload too large");
+    static_assert(sizeof(A) % 8 == 0 && sizeof(B) % 8 == 0, "payload parts must keep 8-byte alignment");
+    PCmd c{};
+    c.type = type;
+    memcpy(c.payload, &a, sizeof(A));
+    memcpy(c.payload + sizeof(A), &b, sizeof(B));
+    memcpy(c.payload + sizeof(A) + sizeof(B), &c3, sizeof(C));
+    cmds.push_back(c);
   }
   template <typename A, typename B> void add2(int type, const A& a, const B& b) {   // fused command: two payloads back to back
     static_assert(sizeof(A) + sizeof(B) <= sizeof(PCmd::payload), "fused command payload too large");
