@@ -5,6 +5,7 @@
 // release, preceded by fence.proxy.async so the generic-proxy stores of a command are visible to the TMA loads of
 // the next one on every SM) replaces the kernel boundary between consecutive commands.
 #include <algorithm>
+#include <type_traits>
 
 #include <cooperative_groups.h>
 
@@ -130,9 +131,17 @@ __device__ __forceinline__ void fused_cell_fwd(const CellFwdTc& p, cg::cluster_g
 template <typename T>
 __device__ __forceinline__ const T& payload(const PCmd& c) { return *reinterpret_cast<const T*>(c.payload); }
 
-// kDecode: the decode-only commands (generator, selection, merged attention tail) are compiled in.  Training programs use
-// the instance without them: their register allocation and code layout do not pay for the decode tail.
-template <int BN, bool kDecode>
+// kSet: bit mask of the command types compiled into this instance.  Every program family (encoder forward / backward,
+// decoder forward / backward, decode) runs the instance that holds just its commands: measured, an interpreter that
+// carries the decode tail costs the training programs ~3 % through register allocation and code layout alone.
+__host__ __device__ constexpr unsigned bit(int t) { return 1u << t; }
+constexpr unsigned kSetEncFwd = bit(P_GEMM) | bit(P_ENC_CELL_FWD) | bit(P_GEMM_ENC_FWD);
+constexpr unsigned kSetEncBwd = bit(P_GEMM) | bit(P_ENC_CELL_BWD);
+constexpr unsigned kSetDecFwd = bit(P_GEMM) | bit(P_CELL_FWD) | bit(P_GEMM_CELL_FWD) | bit(P_ATTN_OUT);
+constexpr unsigned kSetDecBwd = bit(P_GEMM) | bit(P_CELL_BWD) | bit(P_ATTN_DU) | bit(P_TO_DENSE);
+constexpr unsigned kSetDecode = kSetDecFwd | bit(P_GENERATOR) | bit(P_GREEDY) | bit(P_ATTN_OUT_GEN);
+constexpr unsigned kSetAll = 0xffffffffu;
+template <int BN, unsigned kSet>
 __global__ void __launch_bounds__(256, 1)
 persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __restrict__ maps, unsigned* barrier,
                unsigned long long* trace) {
@@ -179,11 +188,12 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
       if (bid == 0) trace[2 * c] = t_begin;
     }
-    if (type == P_GEMM || type == P_GEMM_ENC_FWD || type == P_GEMM_CELL_FWD) {
+    auto is = [&](int t) { return (kSet & bit(t)) != 0 && type == t; };
+    if (is(P_GEMM) || is(P_GEMM_ENC_FWD) || is(P_GEMM_CELL_FWD)) {
       // P_GEMM: tile (mt, z) = (bid % m_tiles, bid / m_tiles), raw split-K partial -> global workspace.
       // Fused commands: the cluster is the M tile and the rank in the cluster is the split; the partial goes to this
       // CTA's shared memory (the idle TMA ring), the cluster reduces through DSMEM and applies the cell right away.
-      const bool fused = (type != P_GEMM);
+      const bool fused = (kSet & (bit(P_GEMM_ENC_FWD) | bit(P_GEMM_CELL_FWD))) != 0 && (type != P_GEMM);
       const PGemm g = payload<PGemm>(cmd);
       const int ntiles = g.m_tiles * g.splits;
       const int z = fused ? (int)(bid % g.splits) : bid / g.m_tiles;
@@ -281,38 +291,46 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();                                       // every rank's partial tile is in its shared memory
         if (bid < ntiles) {
-          if (type == P_GEMM_ENC_FWD)
-            fused_enc_cell_fwd<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z,
-                                   g.splits);
-          else
-            fused_cell_fwd<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z, g.splits);
+          if constexpr ((kSet & bit(P_GEMM_ENC_FWD)) != 0) {
+            if (type == P_GEMM_ENC_FWD)
+              fused_enc_cell_fwd<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z,
+                                     g.splits);
+          }
+          if constexpr ((kSet & bit(P_GEMM_CELL_FWD)) != 0) {
+            if (type == P_GEMM_CELL_FWD)
+              fused_cell_fwd<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z, g.splits);
+          }
         }
         // no second cluster barrier: the grid barrier that ends the command orders the peers' reads of this CTA's
         // partial before anything reuses the ring
       }
-    } else if (type == P_CELL_FWD) {
-      decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_CELL_BWD) {
-      decb::cell_bwd_tc_body(payload<CellBwdTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_ENC_CELL_FWD) {
-      decb::enc_cell_fwd_tc_body(payload<EncCellFwdTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_ENC_CELL_BWD) {
-      decb::enc_cell_bwd_tc_body(payload<EncCellBwdTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_TO_DENSE) {
-      const PToDense p = payload<PToDense>(cmd);
-      decb::part_to_dense_body(p.in, p.dst, p.ld, p.B, p.cols, bid, nblk, scratch);
-    } else if (kDecode && type == P_GENERATOR) {
-      if constexpr (kDecode) decb::generator_body(payload<GenTc>(cmd), bid, nblk, scratch);
-    } else if (kDecode && type == P_GREEDY) {
-      if constexpr (kDecode) decb::greedy_select_body(payload<GreedyTc>(cmd), bid, nblk, scratch);
-    } else if (type == P_ATTN_OUT) {
-      const AttnOutTc p = payload<AttnOutTc>(cmd);
-      for (int b = bid; b < p.B; b += nblk) {
-        decb::attn_out_tc_body(p, b, scratch);
-        __syncthreads();
+    } else if (is(P_CELL_FWD)) {
+      if constexpr ((kSet & bit(P_CELL_FWD)) != 0) decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);
+    } else if (is(P_CELL_BWD)) {
+      if constexpr ((kSet & bit(P_CELL_BWD)) != 0) decb::cell_bwd_tc_body(payload<CellBwdTc>(cmd), bid, nblk, scratch);
+    } else if (is(P_ENC_CELL_FWD)) {
+      if constexpr ((kSet & bit(P_ENC_CELL_FWD)) != 0) decb::enc_cell_fwd_tc_body(payload<EncCellFwdTc>(cmd), bid, nblk, scratch);
+    } else if (is(P_ENC_CELL_BWD)) {
+      if constexpr ((kSet & bit(P_ENC_CELL_BWD)) != 0) decb::enc_cell_bwd_tc_body(payload<EncCellBwdTc>(cmd), bid, nblk, scratch);
+    } else if (is(P_TO_DENSE)) {
+      if constexpr ((kSet & bit(P_TO_DENSE)) != 0) {
+        const PToDense p = payload<PToDense>(cmd);
+        decb::part_to_dense_body(p.in, p.dst, p.ld, p.B, p.cols, bid, nblk, scratch);
       }
-    } else if (kDecode && type == P_ATTN_OUT_GEN) {
-      if constexpr (kDecode) {
+    } else if (is(P_GENERATOR)) {
+      if constexpr ((kSet & bit(P_GENERATOR)) != 0) decb::generator_body(payload<GenTc>(cmd), bid, nblk, scratch);
+    } else if (is(P_GREEDY)) {
+      if constexpr ((kSet & bit(P_GREEDY)) != 0) decb::greedy_select_body(payload<GreedyTc>(cmd), bid, nblk, scratch);
+    } else if (is(P_ATTN_OUT)) {
+      if constexpr ((kSet & bit(P_ATTN_OUT)) != 0) {
+        const AttnOutTc p = payload<AttnOutTc>(cmd);
+        for (int b = bid; b < p.B; b += nblk) {
+          decb::attn_out_tc_body(p, b, scratch);
+          __syncthreads();
+        }
+      }
+    } else if (is(P_ATTN_OUT_GEN)) {
+      if constexpr ((kSet & bit(P_ATTN_OUT_GEN)) != 0) {
       const AttnOutTc p = payload<AttnOutTc>(cmd);
       const GenTc& gp = *reinterpret_cast<const GenTc*>(cmd.payload + sizeof(AttnOutTc));
       const GreedyTc& gs = *reinterpret_cast<const GreedyTc*>(cmd.payload + sizeof(AttnOutTc) + sizeof(GenTc));
@@ -324,11 +342,13 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         __syncthreads();
       }
       }
-    } else if (type == P_ATTN_DU) {
-      const AttnDuTc p = payload<AttnDuTc>(cmd);
-      for (int b = bid; b < p.B; b += nblk) {
-        decb::attn_du_tc_body(p, b, scratch);
-        __syncthreads();
+    } else if (is(P_ATTN_DU)) {
+      if constexpr ((kSet & bit(P_ATTN_DU)) != 0) {
+        const AttnDuTc p = payload<AttnDuTc>(cmd);
+        for (int b = bid; b < p.B; b += nblk) {
+          decb::attn_du_tc_body(p, b, scratch);
+          __syncthreads();
+        }
       }
     }
     if (trace) {
@@ -351,11 +371,11 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
   }
 }
 
-template <int BN, bool kDecode>
+template <int BN, unsigned kSet>
 void launch_bn(Ctx& ctx, PersistProgram& prog) {
   static bool attr_set = false;
   if (!attr_set) {
-    AOCR_CUDA(cudaFuncSetAttribute(persist_kernel<BN, kDecode>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes));
+    AOCR_CUDA(cudaFuncSetAttribute(persist_kernel<BN, kSet>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes));
     attr_set = true;
   }
   const PCmd* cmds = prog.d_cmds;
@@ -375,7 +395,7 @@ void launch_bn(Ctx& ctx, PersistProgram& prog) {
   attrs[1].id = cudaLaunchAttributeClusterDimension;
   attrs[1].val.clusterDim.x = prog.cluster; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
   cfgl.attrs = attrs; cfgl.numAttrs = prog.cluster > 1 ? 2 : 1;
-  AOCR_CUDA(cudaLaunchKernelExC(&cfgl, (const void*)persist_kernel<BN, kDecode>, args));
+  AOCR_CUDA(cudaLaunchKernelExC(&cfgl, (const void*)persist_kernel<BN, kSet>, args));
   ctx.launches++;
 }
 
@@ -384,8 +404,8 @@ int max_ctas_bn() {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaFuncSetAttribute(persist_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel<BN, true>, 256, (size_t)PCfg<BN>::kSmemBytes);
+  cudaFuncSetAttribute(persist_kernel<BN, kSetAll>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel<BN, kSetAll>, 256, (size_t)PCfg<BN>::kSmemBytes);
   return sms * per_sm;
 }
 
@@ -445,14 +465,24 @@ void persist_upload(Ctx& ctx, PersistProgram& prog) {
 
 void persist_launch(Ctx& ctx, PersistProgram& prog) {
   AOCR_CHECK(prog.uploaded, "persistent program not uploaded");
-  bool dec = false;
-  for (const PCmd& c : prog.cmds) dec = dec || c.type == P_GENERATOR || c.type == P_GREEDY || c.type == P_ATTN_OUT_GEN;
-  switch (prog.bn) {
-    case 128: dec ? launch_bn<128, true>(ctx, prog) : launch_bn<128, false>(ctx, prog); break;
-    case 64: dec ? launch_bn<64, true>(ctx, prog) : launch_bn<64, false>(ctx, prog); break;
-    case 32: dec ? launch_bn<32, true>(ctx, prog) : launch_bn<32, false>(ctx, prog); break;
-    default: dec ? launch_bn<16, true>(ctx, prog) : launch_bn<16, false>(ctx, prog); break;
-  }
+  unsigned used = 0;
+  for (const PCmd& c : prog.cmds) used |= bit(c.type);
+  // the smallest predefined command set that covers the program
+  auto go = [&](auto set) {
+    constexpr unsigned S = decltype(set)::value;
+    switch (prog.bn) {
+      case 128: launch_bn<128, S>(ctx, prog); break;
+      case 64: launch_bn<64, S>(ctx, prog); break;
+      case 32: launch_bn<32, S>(ctx, prog); break;
+      default: launch_bn<16, S>(ctx, prog); break;
+    }
+  };
+  if ((used & ~kSetEncFwd) == 0) go(std::integral_constant<unsigned, kSetEncFwd>());
+  else if ((used & ~kSetEncBwd) == 0) go(std::integral_constant<unsigned, kSetEncBwd>());
+  else if ((used & ~kSetDecFwd) == 0) go(std::integral_constant<unsigned, kSetDecFwd>());
+  else if ((used & ~kSetDecBwd) == 0) go(std::integral_constant<unsigned, kSetDecBwd>());
+  else if ((used & ~kSetDecode) == 0) go(std::integral_constant<unsigned, kSetDecode>());
+  else go(std::integral_constant<unsigned, kSetAll>());
 }
 
 void persist_free(PersistProgram& prog) {
