@@ -77,9 +77,9 @@ void Engine::run_program(int kind, int nsteps, int variant) {
       throw;
     }
     rec_ = nullptr;
-    // the bodies are grid-stride and memory-latency bound: give them every CTA the program may use, not just the
-    // number of GEMM tiles (encoder backward: 32 tiles, but its cell body halves in time on 64 CTAs)
-    prog.grid = rec_max_ctas_;
+    // grid = the largest number of GEMM tiles of any command.  (Giving the encoder-backward bodies 64 CTAs instead of
+    // 32 halves their time but changes nothing end to end: the executor's SMs are taken from the weight-gradient lanes.)
+    if (prog.grid < 16) prog.grid = 16;
     if (prog.grid > rec_max_ctas_) prog.grid = rec_max_ctas_;
     prog.grid = ((prog.grid + prog.cluster - 1) / prog.cluster) * prog.cluster;
     it = programs_.emplace(key, std::move(prog)).first;
