@@ -128,7 +128,8 @@ int aocr_synchronize(aocr_handle* h);
 /* number of kernel launches the library has issued on this handle (bench `gpu_launches`) */
 int64_t aocr_launch_count(const aocr_handle* h);
 /* timing of the dominant kernel class, for bench.py's roofline: accumulates CUDA-event time (ms) of
- * kernel class `cls` (0=tensor GEMM/conv, 1=attention step, 2=recurrence) between reset and read. */
+ * kernel class `cls` (0=tensor GEMM/conv [flops], 1=attention kernels [bytes], 2=recurrence executor [flops of its
+ * GEMM commands], 3=recurrence executor [operand bytes its GEMM commands stream]) between reset and read. */
 int aocr_prof_enable(aocr_handle* h, int on);
 int aocr_prof_read(aocr_handle* h, int cls, double* ms, int64_t* launches, double* work /* flops or bytes */);
 

@@ -204,12 +204,12 @@ int aocr_prof_enable(aocr_handle* h, int on) {
   AOCR_API_BEGIN(h)
   h->eng->prof_collect();
   h->eng->prof_on = on != 0;
-  for (int i = 0; i < 3; i++) { h->eng->prof_ms[i] = 0; h->eng->prof_launches[i] = 0; h->eng->prof_work[i] = 0; }
+  for (int i = 0; i < 4; i++) { h->eng->prof_ms[i] = 0; h->eng->prof_launches[i] = 0; h->eng->prof_work[i] = 0; }
   AOCR_API_END(h)
 }
 int aocr_prof_read(aocr_handle* h, int cls, double* ms, int64_t* launches, double* work) {
   AOCR_API_BEGIN(h)
-  AOCR_CHECK(cls >= 0 && cls < 3, "cls must be in [0,3)");
+  AOCR_CHECK(cls >= 0 && cls < 4, "cls must be in [0,4)");
   h->eng->prof_collect();
   if (ms) *ms = h->eng->prof_ms[cls];
   if (launches) *launches = h->eng->prof_launches[cls];

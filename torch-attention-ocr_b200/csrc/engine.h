@@ -83,11 +83,12 @@ class Engine {
   float* d_params = nullptr;
   float* d_grads = nullptr;
   std::string last_error;
-  // profiling of kernel classes (bench roofline): 0 tensor GEMM/conv, 1 attention, 2 recurrence
+  // profiling of kernel classes (bench roofline): 0 tensor GEMM/conv (flops), 1 attention kernels (bytes),
+  // 2 executor (flops of its GEMM commands), 3 executor again (operand bytes its GEMM commands stream)
   bool prof_on = false;
-  double prof_ms[3] = {0, 0, 0};
-  int64_t prof_launches[3] = {0, 0, 0};
-  double prof_work[3] = {0, 0, 0};
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_launches[4] = {0, 0, 0, 0};
+  double prof_work[4] = {0, 0, 0, 0};
 
  private:
   template <typename T> T* alloc(int64_t n);

@@ -86,16 +86,20 @@ void Engine::run_program(int kind, int nsteps, int variant) {
   }
   PersistProgram& prog = it->second;
   if (!prog.uploaded) persist_upload(ctx_, prog);
-  double flops = 0.0;
+  double flops = 0.0, bytes = 0.0;
   if (prof_on)
     for (const PCmd& c : prog.cmds)
-      if (c.type == P_GEMM) {
+      if (c.type == P_GEMM || c.type == P_GEMM_ENC_FWD || c.type == P_GEMM_CELL_FWD) {
         const PGemm* g = reinterpret_cast<const PGemm*>(c.payload);
-        flops += 2.0 * g->M * (double)g->N * (double)g->num_kb * 64.0;
+        const double kp = (double)g->num_kb * 64.0, planes = g->terms == 3 ? 2.0 : 1.0;
+        flops += 2.0 * g->M * (double)g->N * kp;
+        bytes += ((double)g->M + (double)g->N) * kp * 2.0 * planes;   // every weight / activation plane element once
       }
+  prof_begin(3);
   prof_begin(2);
   persist_launch(ctx_, prog);
   prof_end(2, flops);
+  prof_end(3, bytes);
 }
 
 }  // namespace aocr
