@@ -488,9 +488,8 @@ void Engine::cnn_forward(bool train) {
     if (c.bn >= 0) {
       const float *mean, *var;
       if (train) {
-        bn_stats(ctx_, zb[l + 1], rows, c.cout, bn_mean[c.bn], bn_var[c.bn], partial, stat_sync());
-        bn_update_running(ctx_, bn_mean[c.bn], bn_var[c.bn], bn_rmean[c.bn], bn_rvar[c.bn], c.cout,
-                          rows * (cfg.dp_world > 1 ? cfg.dp_world : 1));
+        bn_stats(ctx_, zb[l + 1], rows, c.cout, bn_mean[c.bn], bn_var[c.bn], bn_rmean[c.bn], bn_rvar[c.bn], partial, tmpvec,
+                 stat_sync());
         mean = bn_mean[c.bn]; var = bn_var[c.bn];
       } else {
         mean = bn_rmean[c.bn]; var = bn_rvar[c.bn];

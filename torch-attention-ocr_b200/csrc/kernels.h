@@ -25,8 +25,10 @@ void im2col(Ctx&, const float* a, float* col, int B, int H, int Wi, int C, int k
 void col_sum(Ctx&, const float* z, int64_t R, int C, float* out /*[C]*/, float* partial, int accumulate);
 // cross-rank summation hook for batch-norm statistics (data parallelism); world == 1: unused
 struct StatSync { void (*fn)(void* user, float* buf, int64_t n) = nullptr; void* user = nullptr; int world = 1; };
-void bn_stats(Ctx&, const float* z, int64_t R, int C, float* mean, float* var /*biased*/, float* partial,
-              const StatSync& sync);
+// one pass over z: batch mean / biased variance (global over the data-parallel ranks: ONE all-reduce of [sum | sum sq])
+// and the running-statistics update (momentum 0.1, unbiased variance) [T7 nn.SpatialBatchNormalization]
+void bn_stats(Ctx&, const float* z, int64_t R, int C, float* mean, float* var /*biased*/, float* rmean, float* rvar,
+              float* partial, float* sums /* [2C] scratch */, const StatSync& sync);
 // running stats update (momentum 0.1, unbiased var) [T7 nn.SpatialBatchNormalization]
 void bn_update_running(Ctx&, const float* mean, const float* var, float* rmean, float* rvar, int C, int64_t R);
 // y = relu(gamma*(z-mean)/sqrt(var+eps)+beta).  If tm_S>0 rows (n,s) are written time-major to row s*tm_B+n.

@@ -262,6 +262,52 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
     partial[(int64_t)blockIdx.y * C + c] = s;
   }
 }
+// batch-norm forward statistics in ONE pass: s1 = sum (z - k), s2 = sum (z - k)^2 with the shift k = running mean
+// (identical on every data-parallel rank, and close to the batch mean after a few steps: no cancellation in
+// s2/R - (s1/R)^2).  partial: [2][nslab][C]
+__global__ void __launch_bounds__(256) col_reduce_bn_fwd_kernel(const float* __restrict__ z, const float* __restrict__ shift,
+                                                                int64_t R, int C, int64_t rows_per, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + tx;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per;
+  int64_t r1 = r0 + rows_per < R ? r0 + rows_per : R;
+  float a1 = 0.f, a2 = 0.f;
+  if (c < C) {
+    const float k = shift[c];
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float d = z[r * C + c] - k;
+      a1 += d;
+      a2 = fmaf(d, d, a2);
+    }
+  }
+  __shared__ float red[2][8][33];
+  red[0][ty][tx] = a1; red[1][ty][tx] = a2;
+  __syncthreads();
+  if (ty < 2 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += red[ty][i][tx];
+    partial[((int64_t)ty * gridDim.y + blockIdx.y) * C + c] = s;
+  }
+}
+// mean / biased variance from the (globally summed) shifted sums, and the running-statistics update (momentum 0.1,
+// unbiased variance) in the same kernel
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float invR, float unbias, float* __restrict__ mean,
+                                   float* __restrict__ var, float* __restrict__ rmean, float* __restrict__ rvar) {
+  pdl_launch_dependents();
+  pdl_wait();
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float k = rmean[c];
+  const float m1 = sums[c] * invR, m2 = sums[C + c] * invR;
+  const float mu = k + m1;
+  const float v = fmaxf(m2 - m1 * m1, 0.f);
+  mean[c] = mu; var[c] = v;
+  rmean[c] = 0.9f * k + 0.1f * mu;
+  rvar[c] = 0.9f * rvar[c] + 0.1f * v * unbias;
+}
 // both batch-norm backward sums in one pass over dy and z: s1 = sum dy, s2 = sum dy * xhat.  partial: [2][nslab][C]
 __global__ void __launch_bounds__(256) col_reduce_bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                                 const float* __restrict__ mean, const float* __restrict__ var,
@@ -482,19 +528,20 @@ void col_sum(Ctx& ctx, const float* z, int64_t R, int C, float* out, float* part
 // Batch statistics.  Under data parallelism (sync.world > 1) the local column sums are summed across ranks
 // through sync.fn (an all-reduce ordered on the engine stream) before they are normalised by the GLOBAL row
 // count, so every rank normalises with the statistics of the whole batch, as the single-device reference does.
-void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* var, float* partial, const StatSync& sync) {
-  const float invR = 1.0f / ((float)R * (float)sync.world);
-  if (sync.world <= 1) {
-    col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, invR, 0, mean, partial);
-    col_reduce(ctx, z, nullptr, mean, nullptr, R, C, 1, invR, 0, var, partial);
-    return;
-  }
-  col_reduce(ctx, z, nullptr, nullptr, nullptr, R, C, 0, 1.0f, 0, mean, partial);
-  sync.fn(sync.user, mean, C);
-  scale_vec(ctx, mean, C, invR);
-  col_reduce(ctx, z, nullptr, mean, nullptr, R, C, 1, 1.0f, 0, var, partial);
-  sync.fn(sync.user, var, C);
-  scale_vec(ctx, var, C, invR);
+void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* var, float* rmean, float* rvar, float* partial,
+              float* sums, const StatSync& sync) {
+  int ns = nslabs_for(R, ctx.num_sms, C);
+  if (ns > 128) ns = 128;
+  const int64_t rows_per = (R + ns - 1) / ns;
+  launch_pdl(ctx, col_reduce_bn_fwd_kernel, dim3(cdiv(C, 32), ns), dim3(256), 0, z, (const float*)rmean, R, C, rows_per, partial);
+  AOCR_CUDA(cudaGetLastError());
+  launch_pdl(ctx, col_reduce_final2_kernel, dim3(cdiv(2 * C, 128)), dim3(128), 0, (const float*)partial, ns, C, sums, sums + C);
+  AOCR_CUDA(cudaGetLastError());
+  if (sync.world > 1) sync.fn(sync.user, sums, 2 * (int64_t)C);       // ONE all-reduce: [sum | sum of squares]
+  const double Rg = (double)R * sync.world;
+  launch_pdl(ctx, bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, (const float*)sums, C, (float)(1.0 / Rg),
+             Rg > 1 ? (float)(Rg / (Rg - 1)) : 1.f, mean, var, rmean, rvar);
+  AOCR_CUDA(cudaGetLastError());
 }
 
 void bn_update_running(Ctx& ctx, const float* mean, const float* var, float* rmean, float* rvar, int C, int64_t R) {
