@@ -143,7 +143,9 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     const int64_t n_act[7] = {0, B * 16 * W1 * 64, B * 8 * W2 * 128, B * 8 * W2 * 256, B * 4 * W2 * 256, B * 4 * W2 * 512, B * 2 * W2 * 512};
     for (int l = 1; l <= 6; l++) actp_[l] = alloc_pack(1, n_act[l]);
     const int64_t n_z[7] = {0, B * 16 * W1 * 128, B * 8 * W2 * 256, B * 8 * W2 * 256, B * 4 * W2 * 512, B * 4 * W2 * 512, B * S * 512};
-    for (int l = 1; l <= 6; l++) dzp_[l] = alloc_pack(1, n_z[l]);   // dz of conv_{l+1} has the shape of zb[l+1]
+    for (int l = 1; l <= 6; l++) dzp_[l] = alloc_pack(1, n_z[l]);
+    srcP_ = alloc_pack(S * B, 512);
+    WiCatP = alloc_pack(8 * c.encoder_num_hidden, 512);   // dz of conv_{l+1} has the shape of zb[l+1]
   }
   const int bnc[3] = {256, 512, 512};
   for (int i = 0; i < 3; i++) {
@@ -495,9 +497,9 @@ void Engine::cnn_forward(bool train) {
         mean = bn_rmean[c.bn]; var = bn_rvar[c.bn];
       }
       const bool last = (l == 6);
-      // the next convolution's operand planes come straight from this kernel (the last layer feeds the encoder)
-      __nv_bfloat16* ph = (tc && !last) ? actp_[l + 1].hi : nullptr;
-      __nv_bfloat16* pl = (tc && !last) ? actp_[l + 1].lo : nullptr;
+      // the next contraction's operand planes come straight from this kernel (last layer: the encoder input projection)
+      __nv_bfloat16* ph = tc ? (last ? srcP_.hi : actp_[l + 1].hi) : nullptr;
+      __nv_bfloat16* pl = tc ? (last ? srcP_.lo : actp_[l + 1].lo) : nullptr;
       bn_relu_fwd(ctx_, zb[l + 1], mean, var, d_params + L.bn_g[c.bn], d_params + L.bn_b[c.bn], act[l + 1], rows, c.cout,
                   last ? S_ : 0, last ? B : 0, ph, pl);
     } else {
@@ -581,7 +583,27 @@ void Engine::cnn_backward() {
 // bw slot t = state after column t (slot S = zeros).
 void Engine::encoder_forward() {
   const int B = b_, S = S_;
-  for (int d = 0; d < 2; d++) {   // time-batched input projection for all columns (K10)
+  if (cfg.gemm_mode != 2) {
+    // time-batched input projection of BOTH directions as one GEMM: [W_i fw ; W_i bw] stacked on the UMMA M side,
+    // the CNN output (operand planes written by the last batch-norm kernel) on the N side
+    if (wicat_version_ != weights_version_) {
+      for (int d = 0; d < 2; d++) {
+        Pack half = WiCatP;
+        half.hi += (int64_t)d * 4 * He * 512; half.lo += (int64_t)d * 4 * He * 512; half.rows = 4 * He;
+        split_to_pack(ctx_, d_params + L.enc_wi[d], 4 * He, 512, 512, 1, half);
+      }
+      wicat_version_ = weights_version_;
+    }
+    prof_begin(0);
+    TcGemm t;
+    Pack sp = srcP_; sp.rows = (int64_t)S * B;
+    t.A = WiCatP; t.B = sp; t.M = 8 * He; t.N = S * B; t.K = 512;
+    t.C = xg; t.ldc = 8 * He; t.transpose_out = true; t.bias_m = encb;
+    t.terms = cfg.gemm_mode == 1 ? 1 : 3;
+    gemm_tc(ctx_, t);
+    prof_end(0, 2.0 * S * B * 8.0 * He * 512);
+  }
+  for (int d = 0; d < 2 && cfg.gemm_mode == 2; d++) {   // time-batched input projection for all columns (K10)
     Gemm g;
     g.M = S * B; g.N = 4 * He; g.K = 512;
     g.A = src; g.sam = 512; g.sak = 1;

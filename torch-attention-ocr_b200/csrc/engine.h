@@ -214,6 +214,8 @@ class Engine {
   Pack Whp[2], WhTp[2], HencP[2], dGeP[2];
   Pack Wcat1pG, Wcat2pG;   // decoder [W_i | W_h] with gate-interleaved rows (fused commands)
   bool dec_packs_inter_ = false;   // which row order the forward packs currently hold
+  Pack WiCatP, srcP_;   // [W_i fw ; W_i bw] stacked (8He x 512) and the CNN output as operand planes (one input-projection GEMM)
+  int64_t wicat_version_ = -1;
   Pack WhpG[2];     // W_h with gate-interleaved rows (fused GEMM -> cell commands of the executor)
   bool fuse_on_ = true;   // AOCR_FUSE=0: separate GEMM and cell commands
   int cluster_ = 4;       // thread-block cluster size of the executor launches

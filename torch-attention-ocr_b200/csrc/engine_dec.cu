@@ -379,6 +379,7 @@ void Engine::forward_backward_enqueue() {
   cnn_backward();
   phase_mark("cnn_bwd");
   join_from(1);                    // encoder (and decoder) weight gradients
+  phase_mark("lane_join");
   if (dp && !native) { grad_bucket(G_ENC_FW, G_ENC_BW); grad_bucket(G_CNN, G_CNN); }
   if (native) grad_range(L.goff[G_CNN], cnn_bucket_split_);
   grad_join();
