@@ -64,6 +64,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // C[m][n] (ldc) = act( sum_k A(m,k) * B(k,n) + bias_n[n] + bias_m[m] ) (+ C if accumulate)
 // A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]; batched over blockIdx.z with element strides.
 enum Act { ACT_NONE = 0, ACT_TANH = 1 };
+struct Pack;   // gemm_tc.cuh
 struct Gemm {
   int M = 0, N = 0, K = 0;
   const float* A = nullptr; int64_t sam = 0, sak = 0;
@@ -74,6 +75,10 @@ struct Gemm {
   int act = ACT_NONE;
   int accumulate = 0;
   int batch = 1; int64_t bsa = 0, bsb = 0, bsc = 0;
+  // dW = dY^T X contractions (both operands stored [K rows][columns]): the operand already exists as bf16 planes
+  // (pointer at its first column, kp = row pitch), written by the kernel that produced it - no conversion pass
+  const Pack* pa = nullptr;
+  const Pack* pb = nullptr;
 };
 void gemm_simt(Ctx& ctx, const Gemm& g);
 

@@ -176,7 +176,8 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     W3Tp = alloc_pack(Hd_, 2 * Hd_);
     // decoder forward state holds 2B rows: greedy decode runs its greedy and its gold pass as ONE batch of 2B
     X1p = alloc_pack(Tm * 2 * B, K1_); X2p = alloc_pack(Tm * 2 * B, 2 * Hd_); H2p = alloc_pack(Tm * 2 * B, Hd_);
-    dUQp = alloc_pack(B, 2 * Hd_); dG2p = alloc_pack(B, 4 * Hd_); dG1p = alloc_pack(B, 4 * Hd_);
+    // backward operands are kept for ALL timesteps: the time-batched weight gradients read them as they are
+    dUQp = alloc_pack(Tm * B, 2 * Hd_); dG2p = alloc_pack(Tm * B, 4 * Hd_); dG1p = alloc_pack(Tm * B, 4 * Hd_);
     dec_ws_floats = (int64_t)16 * 2 * B * 4 * Hd_ + 1024;
     for (int i = 0; i < 4; i++) dec_ws[i] = alloc<float>(dec_ws_floats);
     // tensor-core encoder recurrence (engine_enc_tc.cu)

@@ -232,20 +232,31 @@ void Engine::decoder_backward() {
   g.C = d_grads + L.wo; g.ldc = Hd;
   gemm(g);
   col_sum(ctx_, dZ, R, V, d_grads + L.bo, partial, 0);
-  auto wgrad = [&](const float* dY, int M, const float* X, int64_t ldx, int N, float* dW, int64_t ldw) {
+  // operand planes of a column range of a saved per-timestep pack (rows = time*batch, as the fp32 tensors)
+  auto cols_of = [&](const Pack& p, int64_t col0) {
+    Pack v = p;
+    v.hi += col0; v.lo += col0;
+    return v;
+  };
+  auto wgrad = [&](const float* dY, int M, const float* X, int64_t ldx, int N, float* dW, int64_t ldw,
+                   const Pack* pY = nullptr, const Pack* pX = nullptr) {
     Gemm w;
     w.M = M; w.N = N; w.K = (int)R;
     w.A = dY; w.sam = 1; w.sak = M;
     w.B = X; w.sbk = ldx; w.sbn = 1;
     w.C = dW; w.ldc = ldw;
+    if (tc) { w.pa = pY; w.pb = pX; }     // written by the recurrence bodies: no conversion pass
     gemm(w);
   };
+  const Pack pdU = tc ? cols_of(dUQp, 0) : Pack(), pdQ = tc ? cols_of(dUQp, Hd) : Pack();
+  const Pack pX2a = tc ? cols_of(X2p, 0) : Pack(), pX2b = tc ? cols_of(X2p, Hd) : Pack();
+  const Pack pX1a = tc ? cols_of(X1p, 0) : Pack(), pX1b = tc ? cols_of(X1p, h1off) : Pack();
   if (!tc) {
     wgrad(dU, Hd, CAT, 2 * Hd, 2 * Hd, d_grads + L.wc, 2 * Hd);
   } else {
     // the tensor-core path never forms cv_t (engine_dec_tc.cu): dW_c[:, H:] = dU^T H2, and dW_c[:, :H] from dctxwc
     // (dW_c1 = sum_t du_t^T cv_t re-associated over source positions)
-    wgrad(dU, Hd, CAT + Hd, 2 * Hd, Hd, d_grads + L.wc + Hd, 2 * Hd);
+    wgrad(dU, Hd, CAT + Hd, 2 * Hd, Hd, d_grads + L.wc + Hd, 2 * Hd, &pdU, &H2p);
     g = Gemm();                                           // dW_c[:, :H] = dctxwc^T ctx   (K = B*S)
     g.M = Hd; g.N = Hd; g.K = B * S;
     g.A = dCtxWc; g.sam = 1; g.sak = Hd;
@@ -253,14 +264,14 @@ void Engine::decoder_backward() {
     g.C = d_grads + L.wc; g.ldc = 2 * Hd;
     gemm(g);
   }
-  wgrad(dQ, Hd, CAT + Hd, 2 * Hd, Hd, d_grads + L.wa, Hd);
-  wgrad(dG2, 4 * Hd, X2, 2 * Hd, Hd, d_grads + L.l2_wi, Hd);
-  wgrad(dG2, 4 * Hd, X2 + Hd, 2 * Hd, Hd, d_grads + L.l2_wh, Hd);
+  wgrad(dQ, Hd, CAT + Hd, 2 * Hd, Hd, d_grads + L.wa, Hd, tc ? &pdQ : nullptr, tc ? &H2p : nullptr);
+  wgrad(dG2, 4 * Hd, X2, 2 * Hd, Hd, d_grads + L.l2_wi, Hd, tc ? &dG2p : nullptr, tc ? &pX2a : nullptr);
+  wgrad(dG2, 4 * Hd, X2 + Hd, 2 * Hd, Hd, d_grads + L.l2_wh, Hd, tc ? &dG2p : nullptr, tc ? &pX2b : nullptr);
   col_sum(ctx_, dG2, R, 4 * Hd, d_grads + L.l2_bi, partial, 0);
   AOCR_CUDA(cudaMemcpyAsync(d_grads + L.l2_bh, d_grads + L.l2_bi, (size_t)4 * Hd * sizeof(float), cudaMemcpyDeviceToDevice,
                             ctx_.st));
-  if (cfg.input_feed) wgrad(dG1, 4 * Hd, X1, K1, Hd, d_grads + L.l1_wi + E, in1);
-  wgrad(dG1, 4 * Hd, X1 + h1off, K1, Hd, d_grads + L.l1_wh, Hd);
+  if (cfg.input_feed) wgrad(dG1, 4 * Hd, X1, K1, Hd, d_grads + L.l1_wi + E, in1, tc ? &dG1p : nullptr, tc ? &pX1a : nullptr);
+  wgrad(dG1, 4 * Hd, X1 + h1off, K1, Hd, d_grads + L.l1_wh, Hd, tc ? &dG1p : nullptr, tc ? &pX1b : nullptr);
   col_sum(ctx_, dG1, R, 4 * Hd, d_grads + L.l1_bi, partial, 0);
   AOCR_CUDA(cudaMemcpyAsync(d_grads + L.l1_bh, d_grads + L.l1_bi, (size_t)4 * Hd * sizeof(float), cudaMemcpyDeviceToDevice,
                             ctx_.st));
@@ -272,6 +283,7 @@ void Engine::decoder_backward() {
     g.A = dZ; g.sam = 1; g.sak = V;
     g.B = dG1; g.sbk = 4 * Hd; g.sbn = 1;
     g.C = dP; g.ldc = 4 * Hd;
+    g.pb = &dG1p;
     gemm(g);
   } else {
     token_segment_sum(ctx_, dG1, tgt_tb, dP, R, 4 * Hd, V);

@@ -204,30 +204,31 @@ void Engine::decoder_backward_steps_tc() {
     ad.da_carry = (!last && cfg.input_feed) ? part_in(dx1, K1, 0) : PartIn();
     ad.da_gen = dAgen + (int64_t)t * B * Hd; ad.a = A_all + (int64_t)t * B * Hd;
     ad.du_out = dU + (int64_t)t * B * Hd; ad.de = DE + (int64_t)t * B * S; ad.dq = dQ + (int64_t)t * B * Hd;
-    ad.pk = pack_out(dUQp, 0, 0); ad.B = B; ad.S = S; ad.H = Hd;
+    const int64_t rt = (int64_t)t * B;     // operand rows of this step
+    ad.pk = pack_out(dUQp, rt, 0); ad.B = B; ad.S = S; ad.H = Hd;
     emit(ad);
     // dh2 (through the output projection and the query) = [du | dq] [W_c2 ; W_a]
-    TcOut dh2 = emit_gemm(W3Tp, Hd, dUQp, 0, 0, 2 * Hd, dec_ws[1]);
+    TcOut dh2 = emit_gemm(W3Tp, Hd, dUQp, rt, 0, 2 * Hd, dec_ws[1]);
     CellBwdTc b2;
     b2.dh_a = part_in(dh2, Hd, 0);
     b2.dh_b = last ? PartIn() : part_in(dx2, 2 * Hd, Hd);
     b2.dh_c = PartIn();
     b2.dc = dc2; b2.c_prev = C2 + (int64_t)t * B * Hd; b2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
-    b2.acts = ACT2 + (int64_t)t * B * 4 * Hd; b2.dG = dG2 + (int64_t)t * B * 4 * Hd; b2.pk = pack_out(dG2p, 0, 0);
+    b2.acts = ACT2 + (int64_t)t * B * 4 * Hd; b2.dG = dG2 + (int64_t)t * B * 4 * Hd; b2.pk = pack_out(dG2p, rt, 0);
     b2.B = B; b2.H = Hd;
     emit(b2);
     // [dh1 | dh2_prev] = dg2 [W_i2 | W_h2]      (slot 2 must outlive this iteration: read again at t-1)
-    dx2 = emit_gemm(Wcat2Tp, 2 * Hd, dG2p, 0, 0, 4 * Hd, dec_ws[2]);
+    dx2 = emit_gemm(Wcat2Tp, 2 * Hd, dG2p, rt, 0, 4 * Hd, dec_ws[2]);
     CellBwdTc b1;
     b1.dh_a = part_in(dx2, 2 * Hd, 0);
     b1.dh_b = last ? PartIn() : part_in(dx1, K1, h1off);
     b1.dh_c = PartIn();
     b1.dc = dc1; b1.c_prev = C1 + (int64_t)t * B * Hd; b1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
-    b1.acts = ACT1 + (int64_t)t * B * 4 * Hd; b1.dG = dG1 + (int64_t)t * B * 4 * Hd; b1.pk = pack_out(dG1p, 0, 0);
+    b1.acts = ACT1 + (int64_t)t * B * 4 * Hd; b1.dG = dG1 + (int64_t)t * B * 4 * Hd; b1.pk = pack_out(dG1p, rt, 0);
     b1.B = B; b1.H = Hd;
     emit(b1);
     // [da_prev | dh1_prev] = dg1 [W_i1[:,E:] | W_h1]
-    dx1 = emit_gemm(Wcat1Tp, K1, dG1p, 0, 0, 4 * Hd, dec_ws[3]);
+    dx1 = emit_gemm(Wcat1Tp, K1, dG1p, rt, 0, 4 * Hd, dec_ws[3]);
   }
   // hand d h1(0) to the encoder backward through the dense dX1 buffer (model.lua:666-667,680-681; quirk Q14)
   emit_to_dense(part_in(dx1, K1, 0), dX1, K1, B, K1);

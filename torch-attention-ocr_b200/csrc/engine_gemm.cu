@@ -51,11 +51,20 @@ void Engine::gemm(const Gemm& g, int cls) {
     // memory - no transposing conversion, the contraction index K (time*batch) is the TMA row coordinate
     TcGemm t;
     Pack pa, pb;
-    pa.rows = g.K; pa.kp = pad64(g.M); pa.hi = scratch_[0].hi; pa.lo = scratch_[0].lo;
-    pb.rows = g.K; pb.kp = pad64(g.N); pb.hi = scratch_[1].hi; pb.lo = scratch_[1].lo;
-    AOCR_CHECK(pa.rows * pa.kp <= scratch_elems_ && pb.rows * pb.kp <= scratch_elems_, "wgrad operand exceeds scratch");
-    split_to_pack(ctx_, g.A, g.K, g.M, g.sak, 1, pa);
-    split_to_pack(ctx_, g.B, g.K, g.N, g.sbk, 1, pb);
+    if (g.pa) {
+      pa = *g.pa; pa.rows = g.K;
+    } else {
+      pa.rows = g.K; pa.kp = pad64(g.M); pa.hi = scratch_[0].hi; pa.lo = scratch_[0].lo;
+      AOCR_CHECK(pa.rows * pa.kp <= scratch_elems_, "wgrad operand exceeds scratch");
+      split_to_pack(ctx_, g.A, g.K, g.M, g.sak, 1, pa);
+    }
+    if (g.pb) {
+      pb = *g.pb; pb.rows = g.K;
+    } else {
+      pb.rows = g.K; pb.kp = pad64(g.N); pb.hi = scratch_[1].hi; pb.lo = scratch_[1].lo;
+      AOCR_CHECK(pb.rows * pb.kp <= scratch_elems_, "wgrad operand exceeds scratch");
+      split_to_pack(ctx_, g.B, g.K, g.N, g.sbk, 1, pb);
+    }
     t.mn = 1; t.K = g.K; t.C = g.C; t.ldc = g.ldc; t.act = g.act; t.accumulate = g.accumulate;
     t.terms = cfg.gemm_mode == 1 ? 1 : 3;
     if (g.M >= g.N) {
