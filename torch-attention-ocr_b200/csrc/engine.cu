@@ -184,7 +184,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     const int64_t He_ = c.encoder_num_hidden;
     for (int d = 0; d < 2; d++) {
       Whp[d] = alloc_pack(4 * He_, He_); WhTp[d] = alloc_pack(He_, 4 * He_); WhpG[d] = alloc_pack(4 * He_, He_);
-      HencP[d] = alloc_pack((S + 1) * B, He_); dGeP[d] = alloc_pack(B, 4 * He_);
+      HencP[d] = alloc_pack((S + 1) * B, He_); dGeP[d] = alloc_pack(S * B, 4 * He_);   // all timesteps (weight gradients)
     }
   }
   for (int l = 1; l < 7; l++) wt[l] = alloc<float>((int64_t)kConv[l].cout * kConv[l].cin * kConv[l].k * kConv[l].k);
@@ -670,6 +670,7 @@ void Engine::encoder_backward() {
     g.A = dGe + d * 4 * He; g.sam = 8 * He; g.sak = 1;
     g.B = d_params + L.enc_wi[d]; g.sbk = 512; g.sbn = 1;
     g.C = dsrc; g.ldc = 512; g.accumulate = d;
+    if (cfg.gemm_mode != 2) g.pa = &dGeP[d];       // written by the cell-backward bodies, rows = time*batch
     gemm(g);
   }
   // time-batched parameter gradients: independent of the CNN backward -> lane 1
@@ -682,6 +683,9 @@ void Engine::encoder_backward() {
     gi.A = dG; gi.sam = 1; gi.sak = 8 * He;
     gi.B = src; gi.sbk = 512; gi.sbn = 1;
     gi.C = d_grads + L.enc_wi[d]; gi.ldc = 512;
+    Pack hprev = HencP[d];                          // h_prev(t): slot t (fw) / slot t+1 (bw)
+    if (d == 1) { hprev.hi += (int64_t)B * He; hprev.lo += (int64_t)B * He; }
+    if (cfg.gemm_mode != 2) { gi.pa = &dGeP[d]; gi.pb = &srcP_; }
     gemm(gi);
     // dW_h = sum_t dG_t^T h_prev(t).  fw: h_prev(t) = slot t -> rows [0, S*B) of Henc[0]; bw: h_prev(t) = slot t+1.
     Gemm gh;
@@ -689,6 +693,7 @@ void Engine::encoder_backward() {
     gh.A = dG; gh.sam = 1; gh.sak = 8 * He;
     gh.B = Henc + (int64_t)d * (S + 1) * slot + (d == 0 ? 0 : slot); gh.sbk = He; gh.sbn = 1;
     gh.C = d_grads + L.enc_wh[d]; gh.ldc = He;
+    if (cfg.gemm_mode != 2) { gh.pa = &dGeP[d]; gh.pb = &hprev; }
     gemm(gh);
   }
   // bias grads: b_i and b_h both receive the column sums of dG (two biases per cell, LSTM.lua:79-87)

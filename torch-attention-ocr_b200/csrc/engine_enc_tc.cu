@@ -41,9 +41,10 @@ void Engine::encoder_dir_backward(int d) {
   PartIn dh;
   dh.p = enc_dh + d * slot; dh.nz = 1; dh.stride = 0; dh.ld = He;    // decoder seeds
   auto cell_of = [&](int i) {
+    const int t = d == 0 ? S - 1 - i : i;            // the time index this backward step works on
     EncCellBwdTc c;
     c.Cst = Cenc; c.acts = acts_enc; c.Dctx = Dctx; c.dc = enc_dc; c.dG = dGe;
-    c.dgp[d] = out_of(dGeP[d], 0);
+    c.dgp[d] = out_of(dGeP[d], (int64_t)t * B);      // kept for all timesteps: the weight gradients read the planes
     c.B = B; c.S = S; c.He = He; c.step = i; c.d_only = d;
     return c;
   };
@@ -53,7 +54,8 @@ void Engine::encoder_dir_backward(int d) {
     c.dh[d] = dh;
     emit(c);
     // dh_prev = dG_t W_h : rows of W_h^T on the M side, K = 4He
-    TcOut o = emit_gemm(WhTp[d], He, dGeP[d], 0, 0, 4 * He, dec_ws[2 + d]);
+    const int t = d == 0 ? S - 1 - i : i;
+    TcOut o = emit_gemm(WhTp[d], He, dGeP[d], (int64_t)t * B, 0, 4 * He, dec_ws[2 + d]);
     dh.p = o.base; dh.nz = o.nz; dh.stride = o.stride; dh.ld = He;
   }
 }

@@ -76,7 +76,8 @@ void Engine::gemm(const Gemm& g, int cls) {
   } else {
     TcGemm t;
     const bool swap = g.M < g.N;   // the larger side becomes the 128-row M side of the UMMA tile
-    Pack pa = operand_pack(g.A, g.M, g.K, g.sam, g.sak, 0);                 // rows m
+    Pack pa = g.pa ? *g.pa : operand_pack(g.A, g.M, g.K, g.sam, g.sak, 0);  // rows m (K-major planes may be given)
+    if (g.pa) pa.rows = g.M;
     Pack pb = operand_pack(g.B, g.N, g.K, g.sbn, g.sbk, 1);                 // rows n
     t.K = g.K; t.C = g.C; t.ldc = g.ldc; t.act = g.act; t.accumulate = g.accumulate;
     t.terms = cfg.gemm_mode == 1 ? 1 : 3;
