@@ -436,8 +436,13 @@ void Engine::conv_dims(int l, int& Hin, int& Win, int& Hout, int& Wout) const {
   Wout = Win + 2 * kConv[l].pad - kConv[l].k + 1;
 }
 
-void Engine::prep_weights() {
-  if (!weights_dirty_) return;
+// Everything derived from the parameters after an update (flipped convolution weights, fused biases, the embedding
+// table of the decoder's first layer, the decoder's concatenated / transposed weight planes).  None of it is needed by
+// the CNN forward, so it is built on lane 1 while the CNN forward runs; the caller joins before the encoder.
+bool Engine::prep_weights() {
+  if (!weights_dirty_) return false;
+  fork_to(1);
+  use_lane(1);
   for (int l = 1; l < 7; l++) {
     const ConvSpec& c = kConv[l];
     int64_t total = (int64_t)c.cout * c.k * c.k * c.cin;
@@ -458,7 +463,9 @@ void Engine::prep_weights() {
   g.C = Ptab; g.ldc = 4 * Hd; g.bias_n = bsum1;
   gemm_simt(ctx_, g);
   if (cfg.gemm_mode != 2) build_decoder_packs();
+  use_lane(0);
   weights_dirty_ = false;
+  return true;      // lane 1 carries the work: join before the encoder
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -94,7 +94,7 @@ class Engine {
   template <typename T> T* alloc(int64_t n);
   void layout_params();
   void gemm(const Gemm& g, int cls = 0);
-  void prep_weights();
+  bool prep_weights();
   void cnn_forward(bool train);
   void cnn_backward();
   void encoder_forward();

@@ -355,12 +355,13 @@ void Engine::forward_backward_enqueue() {
   AOCR_CHECK(have_batch_, "no batch staged");
   AOCR_CUDA(cudaSetDevice(device_));
   const int B = b_, T = T_;
-  prep_weights();
+  const bool prepped = prep_weights();
   gather_tokens(ctx_, tgt_bt, tgt_tb, B, T, T, 1);
   gather_tokens(ctx_, tev_bt, tev_tb, B, T, T, 1);
   phase_mark("start");
   fill_zero(ctx_, d_grads, (size_t)L.total * sizeof(float));   // model.lua:637-639
   cnn_forward(true);
+  if (prepped) join_from(1);       // prep_weights (lane 1) is complete
   phase_mark("cnn_fwd");
   encoder_forward();
   attention_precompute();
@@ -521,10 +522,11 @@ void Engine::decode_enqueue() {
   AOCR_CHECK(have_batch_, "no batch staged");
   AOCR_CUDA(cudaSetDevice(device_));
   const int B = b_, T = T_, Ld = Tmax;
-  prep_weights();
+  const bool prepped = prep_weights();
   gather_tokens(ctx_, tgt_bt, tgt_tb, B, T, Ld, 1);   // model.lua:266-274: pad to max_decoder_l with PAD
   gather_tokens(ctx_, tev_bt, tev_tb, B, T, Ld, 1);
   cnn_forward(false);
+  if (prepped) join_from(1);       // prep_weights (lane 1), when the weights changed since the last call
   encoder_forward();
   attention_precompute();
   dec_steps_ = Ld;
