@@ -359,9 +359,13 @@ void Engine::forward_backward_enqueue() {
   gather_tokens(ctx_, tgt_bt, tgt_tb, B, T, T, 1);
   gather_tokens(ctx_, tev_bt, tev_tb, B, T, T, 1);
   phase_mark("start");
-  fill_zero(ctx_, d_grads, (size_t)L.total * sizeof(float));   // model.lua:637-639
+  fork_to(1);                      // model.lua:637-639: gradients are not touched before the decoder backward
+  use_lane(1);
+  fill_zero(ctx_, d_grads, (size_t)L.total * sizeof(float));
+  use_lane(0);
   cnn_forward(true);
-  if (prepped) join_from(1);       // prep_weights (lane 1) is complete
+  (void)prepped;
+  join_from(1);                    // prep_weights and the gradient clear (lane 1) are complete
   phase_mark("cnn_fwd");
   encoder_forward();
   attention_precompute();
