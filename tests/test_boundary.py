@@ -29,6 +29,24 @@ def test_library_exports_every_declared_symbol():
     assert sorted(exported_symbols()) == declared, "ctypes prototypes out of sync with include/aocr.h"
 
 
+def test_lua_ffi_cdef_declares_every_entry_point():
+    """the LuaJIT twin cannot run here; at least its cdef must name every entry point of the header, with the same
+    parameter count"""
+    def protos(txt):
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        out = {}
+        for m in re.finditer(r"\b(aocr_[a-z_0-9]+)\s*\(([^;]*?)\)\s*;", txt, flags=re.S):
+            if "(*" in m.group(0):
+                continue                     # the callback typedef
+            out[m.group(1)] = len([a for a in m.group(2).split(",") if a.strip()])
+        return out
+    hdr = protos(open(os.path.join(ROOT, "include", "aocr.h")).read())
+    lua_txt = open(os.path.join(ROOT, "torch-attention-ocr_b200", "lua", "aocr_ffi.lua")).read()
+    lua = protos(lua_txt.split("ffi.cdef[[", 1)[1].split("]]", 1)[0])
+    assert set(hdr) == set(header_symbols())
+    assert lua == hdr
+
+
 def test_config_struct_matches_header():
     from aocr.capi import AocrConfig
     txt = open(os.path.join(ROOT, "include", "aocr.h")).read()

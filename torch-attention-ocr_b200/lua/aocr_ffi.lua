@@ -32,6 +32,26 @@ int aocr_decode_greedy(aocr_handle* h, const float* images, int b, int W, const 
                        const int32_t* targets_eval, int T, int32_t* labels, double* pred_scores,
                        double* gold_scores, double* loss_sum, int32_t* num_correct);
 int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n);
+int aocr_debug_read(aocr_handle* h, const char* name, float* out, int64_t n);
+/* device-resident entry points and the data-parallel plumbing (no reference counterpart: train.lua is single-device) */
+int aocr_stage_batch(aocr_handle* h, const float* images, int b, int W, const int32_t* targets,
+                     const int32_t* targets_eval, int T);
+int aocr_train_step_staged(aocr_handle* h, double lr, int sync, double* loss_sum);
+int aocr_decode_greedy_staged(aocr_handle* h, int sync);
+int aocr_grad_buffer(aocr_handle* h, void** dev_ptr, int64_t* n_floats);
+int aocr_group_extent(aocr_handle* h, int group, int64_t* offset_floats, int64_t* n_floats);
+int aocr_forward_backward_staged(aocr_handle* h);
+int aocr_sgd_update_async(aocr_handle* h, double lr, double clip);
+int aocr_read_loss(aocr_handle* h, double* loss_sum);
+int aocr_stream(aocr_handle* h, void** cuda_stream);
+typedef void (*aocr_allreduce_fn)(void* user, void* dev_ptr, int64_t n_floats, int kind);
+int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user);
+int aocr_dp_unique_id(void* out128);
+int aocr_dp_init(aocr_handle* h, const void* id128);
+int aocr_synchronize(aocr_handle* h);
+int64_t aocr_launch_count(const aocr_handle* h);
+int aocr_prof_enable(aocr_handle* h, int on);
+int aocr_prof_read(aocr_handle* h, int cls, double* ms, int64_t* launches, double* work);
 ]]
 
 local lib = ffi.load(os.getenv('AOCR_LIB') or 'torch-attention-ocr_b200/lib/libaocr.so')
