@@ -105,16 +105,20 @@ def run_reference(args):
     sample_b = 16                                   # bounded sample: 16 of the 64 images per step
     sub = {k: (v[:sample_b] if hasattr(v, "shape") else v) for k, v in batch.items()}
     orc = Oracle(cfg, init_params(cfg, SEED), init_bn_stats(cfg))
-    for _ in range(min(args.warmup, 1)):
+    warm = min(args.warmup, 3)
+    for _ in range(warm):
         orc.train_step(sub["images"], sub["targets"], sub["targets_eval"], 0.1)
-    steps = max(1, min(args.steps, 5))
-    t0 = time.time()
-    for _ in range(steps):
+    # exactly K steps unless that would take more than ~3 minutes on this host (then as many as fit, reported)
+    steps, t0, budget = 0, time.time(), 180.0
+    while steps < max(1, args.steps):
         orc.train_step(sub["images"], sub["targets"], sub["targets_eval"], 0.1)
+        steps += 1
+        if time.time() - t0 > budget:
+            break
     dt = (time.time() - t0) / steps
     ips = sample_b / dt
     line = {"impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"{sample_b} of {B_PER_GPU} images per step"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
