@@ -1,6 +1,7 @@
-// persist.cu — persistent recurrence executor (see persist.h).  One cooperative kernel, 256 threads per CTA, one CTA
-// per SM (197 KB of shared memory for the TMA ring): warp 0 = TMA producer, warp 1 = tcgen05 issuer and TMEM owner,
-// warps 2-5 = epilogue (TMEM -> split-K partials in global memory), all 8 warps = the fused cell / attention bodies.
+// persist.cu — persistent recurrence executor (see persist.h).  256 threads per CTA, one CTA per SM (197 KB of shared
+// memory for the TMA ring): warp 0 = TMA producer, warp 1 = tcgen05 issuer and TMEM owner, warps 2-5 = epilogue (TMEM ->
+// split-K partials in global memory, or -> this CTA's shared memory for the fused GEMM -> cell commands), all 8 warps =
+// the cell / attention bodies and the cluster-side cell of the fused commands.
 // mbarrier phases and the TMEM allocation persist across commands; a grid barrier (one global counter, acquire /
 // release, preceded by fence.proxy.async so the generic-proxy stores of a command are visible to the TMA loads of
 // the next one on every SM) replaces the kernel boundary between consecutive commands.

@@ -1,9 +1,11 @@
-// persist.h — the persistent recurrence executor: ONE cooperative kernel runs a whole recurrence (all timesteps of
-// the decoder forward, the decoder backward, or one encoder direction) as a command list.  Every command is either a
-// swap-AB tcgen05 GEMM (the CTA's tile of `weights x batch`, split-K partials) or one of the fused cell / attention /
-// output bodies of dec_bodies.cuh; a grid barrier separates consecutive commands.  Kernel boundaries (4-5 us each on
-// this part, ~9 per decoder step) disappear; TMEM, the mbarrier ring and the tensor-map table live for the whole
-// recurrence.  The command list is built once per (batch, S, T) shape on the host and cached on the device.
+// persist.h — the persistent recurrence executor: ONE kernel (cooperative launch, thread-block clusters) runs a whole
+// recurrence (all timesteps of the decoder forward, the decoder backward, one encoder direction, or the dual greedy
+// decode pass) as a command list.  A command is a swap-AB tcgen05 GEMM (the CTA's tile of `weights x batch`, split-K
+// partials to global memory), a fused GEMM -> LSTM-cell (the cluster owns the M tile, split-K partials reduced through
+// distributed shared memory), or one of the cell / attention+output / generator bodies of dec_bodies.cuh; a grid
+// barrier separates consecutive commands.  Kernel boundaries (4-5 us each on this part) disappear; TMEM, the mbarrier
+// ring and the tensor-map table live for the whole recurrence.  The command list is built once per (batch, S, T) shape
+// on the host and cached on the device.
 #pragma once
 #include <vector>
 
