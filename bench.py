@@ -329,7 +329,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": total_imgs, "parallelism": f"dp{world}",
                            "l2": "flushed (256 MB memset) between timed iterations", "loss_sum_last_step": loss,
-                           "model_flop_per_image": FLOP_PER_IMG_TRAIN},
+                           "algorithmic_flop_per_image": FLOP_PER_IMG_TRAIN},
                 "clocks": sampler.summary(),
                 "e2e": {"value": total_imgs / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
@@ -340,7 +340,7 @@ def main():
                            "e2e": {"value": total_imgs / (ms_dec_e2e / 1e3), "unit": "images/s",
                                    "ms_per_batch": ms_dec_e2e}},
                 "roofline": roof,
-                "step_model_flops_frac_of_peak": value * FLOP_PER_IMG_TRAIN / 1e12 / world / peaks["bf16_sustained"]}
+                "step_algorithmic_flops_frac_of_bf16_peak": value * FLOP_PER_IMG_TRAIN / 1e12 / world / peaks["bf16_sustained"]}
         if not args.no_cpu_baseline and world >= 1:
             from oracle import Oracle
             cores = os.cpu_count() or 1
