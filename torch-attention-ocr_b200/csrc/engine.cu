@@ -114,6 +114,16 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (const char* e = getenv("AOCR_DUAL")) dual_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_FUSE")) fuse_on_ = atoi(e) != 0;
   if (const char* e = getenv("AOCR_CLUSTER")) cluster_ = atoi(e) > 0 ? atoi(e) : 1;
+  // Clusters must fit inside a GPC: if this part cannot keep the 128 CTAs the programs need (the decoder, or the two
+  // encoder directions side by side) co-resident as clusters, run the executor without clusters and fused commands.
+  // Decided here, before any weight plane is built (their row order depends on it).
+  if (cluster_ > 1 && c.gemm_mode != 2) {
+    const int cap = persist_max_cluster_ctas(64, cluster_);
+    if (cap < 128) {
+      fprintf(stderr, "[aocr] %d CTAs can be co-resident in clusters of %d (< 128): executor runs without clusters\n", cap, cluster_);
+      cluster_ = 1;
+    }
+  }
   if (c.batch_size > 128 || c.gemm_mode == 2) persist_on_ = false;
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
   AOCR_CUDA(cudaEventCreate(&ev0_));

@@ -438,6 +438,39 @@ PGemmPlan persist_plan_gemm_fused(int M, int N, int K, int cluster) {
   return p;
 }
 
+// co-resident CTAs when the executor is launched with clusters of `cluster` CTAs: clusters must fit inside a GPC, so this
+// can be less than the plain occupancy (148 SMs in unequal GPCs)
+template <int BN>
+int max_cluster_ctas_bn(int cluster) {
+  cudaFuncSetAttribute(persist_kernel<BN, kSetAll>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes);
+  cudaFuncSetAttribute(persist_kernel<BN, kSetAll>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaLaunchConfig_t cfgl = {};
+  cfgl.gridDim = dim3((sms / cluster) * cluster); cfgl.blockDim = dim3(256);
+  cfgl.dynamicSmemBytes = (size_t)PCfg<BN>::kSmemBytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfgl.attrs = &attr; cfgl.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, (const void*)persist_kernel<BN, kSetAll>, &cfgl) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n * cluster;
+}
+int persist_max_cluster_ctas(int bn, int cluster) {
+  if (cluster <= 1) return persist_max_ctas(bn);
+  switch (bn) {
+    case 128: return max_cluster_ctas_bn<128>(cluster);
+    case 64: return max_cluster_ctas_bn<64>(cluster);
+    case 32: return max_cluster_ctas_bn<32>(cluster);
+    default: return max_cluster_ctas_bn<16>(cluster);
+  }
+}
+
 int persist_max_ctas(int bn) {
   switch (bn) {
     case 128: return max_ctas_bn<128>();

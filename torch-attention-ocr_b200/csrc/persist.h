@@ -92,5 +92,6 @@ void persist_upload(Ctx& ctx, PersistProgram& prog);     // allocates + copies (
 void persist_launch(Ctx& ctx, PersistProgram& prog);     // cooperative launch on ctx.st
 void persist_free(PersistProgram& prog);
 int persist_max_ctas(int bn);                            // co-resident CTAs of the executor on this device
+int persist_max_cluster_ctas(int bn, int cluster);       // the same when launched with thread-block clusters
 
 }  // namespace aocr
