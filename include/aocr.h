@@ -55,6 +55,13 @@ int aocr_create(const aocr_config* cfg, int device, aocr_handle** out);
 void aocr_destroy(aocr_handle* h);
 const char* aocr_last_error(const aocr_handle* h);   /* h may be NULL: error of a failed aocr_create */
 
+/* Fresh parameters for a created handle: what the module constructors behind model:create draw
+ * (src/model/model.lua:83-112 -> cnn.lua:9-45, LSTM.lua:18-162, output_projector.lua:3-8; nn.LinearNoBias:reset,
+ * src/utils/model_utils.lua:68-85).  Torch7 reset() distributions: Linear / convolution weight and bias
+ * U(+-1/sqrt(fan_in)), batch-norm gamma U(0,1), beta 0, LookupTable N(0,1); running statistics (0,1).
+ * A handle refuses to step until aocr_init_params or aocr_set_params has been called (an all-zero model trains nothing). */
+int aocr_init_params(aocr_handle* h, uint64_t seed);
+
 /* self.params[i] / self.grad_params[i] — src/model/model.lua:161-168 (getParameters per layer) */
 int aocr_param_groups(const aocr_handle* h, int32_t* n_groups, int64_t sizes[AOCR_NUM_GROUPS]);
 int aocr_set_params(aocr_handle* h, int group, const float* host, int64_t n);
@@ -123,6 +130,12 @@ int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user);
  * aocr_dp_unique_id (128 bytes = ncclUniqueId), the host ships it to every rank, every rank of the handle's
  * dp_world calls aocr_dp_init (collective).  Takes precedence over a hook.  No reference counterpart. */
 int aocr_dp_unique_id(void* out128);
+/* text of the last failure of a handle-less call (aocr_create, aocr_dp_unique_id) on this thread */
+const char* aocr_last_global_error(void);
+/* data parallelism: the GLOBAL batch of the next steps (loss scale 1/B and batch-norm row count).  Needed
+ * when a step carries fewer images than aocr_config.global_batch (the reference's final bucket flush,
+ * src/data/data_gen.lua:125-153); shards of a step need not be equal. */
+int aocr_set_global_batch(aocr_handle* h, int32_t global_batch);
 int aocr_dp_init(aocr_handle* h, const void* id128);
 int aocr_synchronize(aocr_handle* h);
 /* number of kernel launches the library has issued on this handle (bench `gpu_launches`) */

@@ -1,0 +1,75 @@
+"""GPU parity at the shapes bench.py measures (BASELINE.json configs 2-5): the float64 oracle against libaocr on the
+SAME batch size the throughput numbers are quoted on, not on a scaled-down batch.  Each shape exercises a different
+launch plan of the library:
+
+  batch 64  (config 2)          executor BN=64, 128 CTAs, cluster-4 fused GEMM->cell commands, dual decode pass (2 x 64 rows)
+  batch 128 (config 5 per GPU)  executor BN=128 (its limit); decode as two sequential passes
+  batch 256 (configs 3, 4)      beyond one UMMA N tile: two N tiles per command / per-kernel chain
+
+Bars: parity_util.py (loss and log-probs 1e-3, every gradient tensor, greedy tokens exact outside ties)."""
+import numpy as np
+import pytest
+
+from oracle import Config, make_batch
+from parity_util import train_parity, decode_parity, check_train, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode_ok(res):
+    assert res["token_mismatch"] == 0, res
+    assert res["tokens_compared"] > 0
+    assert res["gold_logp"] < TOL and res["loss"] < TOL and res["gold_scores"] < TOL, res
+    assert res["num_correct"][0] == res["num_correct"][1], res
+
+
+def test_config2_train_step_full_batch():
+    """BASELINE configs[1] exactly as bench.py runs it: batch 64, 32x100, T = 20, -input_feed, max_enc 80, max_dec 50"""
+    cfg = Config(batch_size=64, max_encoder_l=80, max_decoder_l=50, input_feed=True)
+    batch = make_batch(64, 100, 19, seed=910820, force_T=20, kind="noise")
+    out, _ = train_parity(cfg, batch, gemm_mode=0)
+    check_train(out, gemm_mode=0)
+
+
+def test_config2_greedy_decode_full_batch():
+    """the decode half of the metric at config 2: 50 greedy + 50 gold steps over 64 images (dual pass of 128 rows)"""
+    cfg = Config(batch_size=64, max_encoder_l=80, max_decoder_l=50, input_feed=True)
+    batch = make_batch(64, 100, 19, seed=910821, force_T=20)
+    res, _, _ = decode_parity(cfg, batch, gemm_mode=0)
+    _decode_ok(res)
+
+
+def test_batch128_executor_limit():
+    """batch 128 = one full UMMA N tile per command (config 5's per-GPU batch at N=1), short target"""
+    cfg = Config(batch_size=128, max_encoder_l=30, max_decoder_l=8, input_feed=True)
+    batch = make_batch(128, 100, 5, seed=71, force_T=6)
+    out, _ = train_parity(cfg, batch, gemm_mode=0)
+    check_train(out, gemm_mode=0)
+    res, _, _ = decode_parity(cfg, batch, gemm_mode=0)
+    _decode_ok(res)
+
+
+def test_batch256_config4_per_rank_train_step():
+    """config 4's per-rank shape: batch 256, 32x100, T = 20"""
+    cfg = Config(batch_size=256, max_encoder_l=30, max_decoder_l=20, input_feed=True)
+    batch = make_batch(256, 100, 19, seed=72, force_T=20, kind="noise")
+    out, _ = train_parity(cfg, batch, gemm_mode=0)
+    check_train(out, gemm_mode=0)
+
+
+def test_batch256_config3_decode_bucket():
+    """config 3: batch 256 greedy decode of one width bucket (W = 132 -> S = 32)"""
+    cfg = Config(batch_size=256, max_encoder_l=40, max_decoder_l=12, input_feed=True)
+    batch = make_batch(256, 132, 8, seed=73)
+    res, _, _ = decode_parity(cfg, batch, gemm_mode=0)
+    _decode_ok(res)
+
+
+def test_partial_batch_in_large_handle():
+    """b < batch_size (the reference's final bucket flush, data_gen.lua:125-153) on a handle sized for 256"""
+    cfg = Config(batch_size=256, max_encoder_l=30, max_decoder_l=10, input_feed=True)
+    batch = make_batch(37, 100, 6, seed=74)
+    out, _ = train_parity(cfg, batch, gemm_mode=0)
+    check_train(out, gemm_mode=0)
+    res, _, _ = decode_parity(cfg, batch, gemm_mode=0)
+    _decode_ok(res)

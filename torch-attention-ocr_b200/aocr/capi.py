@@ -33,6 +33,7 @@ _SYMBOLS = {
     "aocr_destroy": (None, [C.c_void_p]),
     "aocr_last_error": (C.c_char_p, [C.c_void_p]),
     "aocr_param_groups": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "aocr_init_params": (C.c_int, [C.c_void_p, C.c_uint64]),
     "aocr_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "aocr_get_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "aocr_get_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
@@ -65,6 +66,8 @@ _SYMBOLS = {
     "aocr_launch_count": (C.c_int64, [C.c_void_p]),
     "aocr_dp_unique_id": (C.c_int, [C.c_void_p]),
     "aocr_dp_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "aocr_last_global_error": (C.c_char_p, []),
+    "aocr_set_global_batch": (C.c_int, [C.c_void_p, C.c_int32]),
     "aocr_prof_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "aocr_prof_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_double)]),
@@ -125,7 +128,7 @@ class Lib:
         buf = C.create_string_buffer(128)
         rc = self.dll.aocr_dp_unique_id(buf)
         if rc != 0:
-            raise RuntimeError("aocr_dp_unique_id failed: NCCL (libnccl.so.2) not loadable")
+            raise RuntimeError("aocr_dp_unique_id failed: " + self.dll.aocr_last_global_error().decode())
         return buf.raw
 
 
@@ -164,6 +167,13 @@ class Handle:
             pass
 
     # ---- parameters
+    def init_params(self, seed=910820):
+        """fresh parameters with Torch7's reset() distributions (what Model:create's module constructors draw)"""
+        self._ck(self.lib.dll.aocr_init_params(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def set_global_batch(self, n):
+        self._ck(self.lib.dll.aocr_set_global_batch(self.h, int(n)))
+
     def set_params(self, group, arr):
         a = np.ascontiguousarray(arr, dtype=np.float32)
         self._ck(self.lib.dll.aocr_set_params(self.h, group, _ptr(a), a.size))

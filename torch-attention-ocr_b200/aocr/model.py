@@ -57,7 +57,7 @@ class Model:
         self.visualize = False
         self.visualize_file = None
 
-    # model:create(config) — model.lua:83-112
+    # model:create(config) — model.lua:83-112: builds the modules, whose constructors draw the initial weights
     def create(self, config):
         c = dict(_DEFAULTS)
         c.update({k: v for k, v in dict(config).items() if k in _DEFAULTS})
@@ -65,6 +65,7 @@ class Model:
         self.global_step = 0
         self.optim_state = {"learningRate": c["learning_rate"]}
         self._build()
+        self.handle.init_params(dict(config).get("seed", 910820))   # Torch7 reset() distributions, seeded (train.lua:60)
         return self
 
     def _build(self):
@@ -83,7 +84,7 @@ class Model:
         self.grad_params = [_GroupProxy(self, i, True) for i in range(5)]
         self.log("Number of parameters: %d" % sum(self.handle.group_sizes))
 
-    # random-init import (the library holds no RNG: weights come from the caller)
+    # parameter import (parity runs load the oracle's weights; checkpoints)
     def set_parameters(self, params, bn_stats=None):
         for i, g in enumerate(GROUPS):
             self.handle.set_params(i, params[g] if isinstance(params, dict) else params[i])

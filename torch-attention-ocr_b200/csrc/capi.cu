@@ -60,6 +60,14 @@ int aocr_param_groups(const aocr_handle* h, int32_t* n_groups, int64_t sizes[AOC
   return AOCR_OK;
 }
 
+int aocr_init_params(aocr_handle* h, uint64_t seed) {
+  AOCR_API_BEGIN(h) h->eng->init_params(seed); AOCR_API_END(h)
+}
+int aocr_set_global_batch(aocr_handle* h, int32_t global_batch) {
+  AOCR_API_BEGIN(h) h->eng->set_global_batch(global_batch); AOCR_API_END(h)
+}
+const char* aocr_last_global_error(void) { return g_create_error.c_str(); }
+
 int aocr_set_params(aocr_handle* h, int group, const float* host, int64_t n) {
   AOCR_API_BEGIN(h) h->eng->set_params(group, host, n); AOCR_API_END(h)
 }
@@ -181,7 +189,8 @@ int aocr_dp_unique_id(void* out128) {
     if (!out128) return AOCR_ERR_INVALID;
     aocr::dp_unique_id(out128);
     return AOCR_OK;
-  } catch (...) {
+  } catch (const std::exception& e) {
+    g_create_error = e.what();        // aocr_last_global_error() / aocr_last_error(NULL)
     return AOCR_ERR_CUDA;
   }
 }

@@ -42,6 +42,7 @@ struct Ctx {
   int* tc_counters = nullptr;
   int tc_counters_n = 0;
   bool pdl = true;   // AOCR_PDL=0 disables programmatic dependent launch
+  bool persist_coop = true;   // executor launches carry the cooperative attribute (see Engine: launch-mode probe)
 };
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -6,6 +6,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <random>
+
 namespace aocr {
 
 const ConvSpec kConv[7] = {
@@ -51,9 +53,14 @@ void Engine::layout_params() {
   int64_t off = 0;
   int cur_group = 0;
   int64_t ext = 0;
-  auto take = [&](int64_t n, int cout = 0, int cin = 0, int kk = 0) {
+  // init / fan_in: see TensorEntry (a bias takes the bound of the weight in front of it)
+  int last_fan = 1;
+  auto take = [&](int64_t n, int cout = 0, int cin = 0, int kk = 0, int init = 1, int fan_in = 0) {
     off = (off + 63) & ~(int64_t)63;
     TensorEntry e{cur_group, ext, off, n, cout, cin, kk};
+    if (cout) { init = 0; fan_in = cin * kk; }
+    if (init == 0) last_fan = fan_in;
+    e.init = init; e.fan_in = init <= 1 ? last_fan : 0;
     L.tensors.push_back(e);
     int64_t o = off;
     off += n; ext += n;
@@ -64,21 +71,21 @@ void Engine::layout_params() {
   const int in1 = E + (cfg.input_feed ? Hd : 0);
   // physical order: proj | decoder | enc_fw | enc_bw | cnn ; within a group the caller-visible tensor order
   begin_group(G_PROJ);
-  L.wo = take((int64_t)V * Hd); L.bo = take(V);
+  L.wo = take((int64_t)V * Hd, 0, 0, 0, 0, Hd); L.bo = take(V);
   end_group(G_PROJ);
   begin_group(G_DEC);
-  L.emb = take((int64_t)V * E);
-  L.l1_wi = take((int64_t)4 * Hd * in1); L.l1_bi = take(4 * Hd);
-  L.l1_wh = take((int64_t)4 * Hd * Hd);  L.l1_bh = take(4 * Hd);
-  L.l2_wi = take((int64_t)4 * Hd * Hd);  L.l2_bi = take(4 * Hd);
-  L.l2_wh = take((int64_t)4 * Hd * Hd);  L.l2_bh = take(4 * Hd);
-  L.wa = take((int64_t)Hd * Hd); L.wc = take((int64_t)Hd * 2 * Hd);
+  L.emb = take((int64_t)V * E, 0, 0, 0, 4);
+  L.l1_wi = take((int64_t)4 * Hd * in1, 0, 0, 0, 0, in1); L.l1_bi = take(4 * Hd);
+  L.l1_wh = take((int64_t)4 * Hd * Hd, 0, 0, 0, 0, Hd);   L.l1_bh = take(4 * Hd);
+  L.l2_wi = take((int64_t)4 * Hd * Hd, 0, 0, 0, 0, Hd);   L.l2_bi = take(4 * Hd);
+  L.l2_wh = take((int64_t)4 * Hd * Hd, 0, 0, 0, 0, Hd);   L.l2_bh = take(4 * Hd);
+  L.wa = take((int64_t)Hd * Hd, 0, 0, 0, 0, Hd); L.wc = take((int64_t)Hd * 2 * Hd, 0, 0, 0, 0, 2 * Hd);
   end_group(G_DEC);
   for (int d = 0; d < 2; d++) {
     int g = d == 0 ? G_ENC_FW : G_ENC_BW;
     begin_group(g);
-    L.enc_wi[d] = take((int64_t)4 * He * 512); L.enc_bi[d] = take(4 * He);
-    L.enc_wh[d] = take((int64_t)4 * He * He);  L.enc_bh[d] = take(4 * He);
+    L.enc_wi[d] = take((int64_t)4 * He * 512, 0, 0, 0, 0, 512); L.enc_bi[d] = take(4 * He);
+    L.enc_wh[d] = take((int64_t)4 * He * He, 0, 0, 0, 0, He);   L.enc_bh[d] = take(4 * He);
     end_group(g);
   }
   begin_group(G_CNN);
@@ -86,7 +93,7 @@ void Engine::layout_params() {
     const ConvSpec& c = kConv[l];
     L.conv_w[l] = take((int64_t)c.cout * c.cin * c.k * c.k, c.cout, c.cin, c.k * c.k);
     L.conv_b[l] = take(c.cout);
-    if (c.bn >= 0) { L.bn_g[c.bn] = take(c.cout); L.bn_b[c.bn] = take(c.cout); }
+    if (c.bn >= 0) { L.bn_g[c.bn] = take(c.cout, 0, 0, 0, 2); L.bn_b[c.bn] = take(c.cout, 0, 0, 0, 3); }
   }
   end_group(G_CNN);
   L.total = off;
@@ -124,8 +131,26 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
       cluster_ = 1;
     }
   }
-  if (c.batch_size > 128 || c.gemm_mode == 2) persist_on_ = false;
+  if (c.batch_size > 256 || c.gemm_mode == 2) persist_on_ = false;   // one UMMA N tile (<= 256 rows) per command
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
+  // Launch mode of the executor.  Preferred: cooperative (co-residency of the spinning CTAs is checked by the driver) +
+  // clusters.  A launch interceptor may refuse that combination (Nsight Compute: LaunchFailed): then clusters without
+  // the cooperative attribute (the grids are <= 128 CTAs of one CTA per SM, co-resident on this part - checked above
+  // through the occupancy query), and as the last resort cooperative without clusters (no fused GEMM -> cell commands).
+  // Decided here, before any weight plane is built (their row order depends on it).
+  if (const char* e = getenv("AOCR_COOP")) ctx_.persist_coop = atoi(e) != 0;
+  if (persist_on_ && cluster_ > 1 && ctx_.persist_coop && !getenv("AOCR_NO_PROBE")) {
+    if (persist_probe(ctx_.st, 128, cluster_, true) != cudaSuccess) {
+      if (persist_probe(ctx_.st, 128, cluster_, false) == cudaSuccess) {
+        ctx_.persist_coop = false;
+        fprintf(stderr, "[aocr] cooperative + cluster launch refused: executor launches with clusters, without the cooperative attribute\n");
+      } else {
+        cluster_ = 1;
+        fprintf(stderr, "[aocr] cluster launches refused: executor runs without clusters\n");
+        AOCR_CHECK(persist_probe(ctx_.st, 128, 1, true) == cudaSuccess, "the persistent executor cannot be launched on this device");
+      }
+    }
+  }
   AOCR_CUDA(cudaEventCreate(&ev0_));
   AOCR_CUDA(cudaEventCreate(&ev1_));
   He = c.encoder_num_hidden; Hd = 2 * He; E = c.target_embedding_size; V = c.target_vocab_size;
@@ -240,6 +265,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   dc1 = alloc<float>(B * Hd); dc2 = alloc<float>(B * Hd); dP = alloc<float>((int64_t)V * 4 * Hd);
   tok = alloc<int32_t>(B); labels = alloc<int32_t>(B * T);
   score = alloc<double>(B); d_loss = alloc<double>(1); d_sumsq = alloc<double>(16); d_sq_partial = alloc<double>(5 * 1024);
+  d_lrclip = alloc<double>(2);
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
 }
 
@@ -288,6 +314,45 @@ void Engine::set_params(int group, const float* host, int64_t n) {
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
   AOCR_CUDA(cudaMemcpy(d_params + L.goff[group], tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
   mark_weights_dirty();
+  params_set_ = true;
+}
+
+// Fresh parameters, as the module constructors behind Model:create draw them (model.lua:83-112 -> cnn.lua, LSTM.lua,
+// output_projector.lua; reset() semantics [T7]; nn.LinearNoBias: model_utils.lua:68-85): Linear / conv
+// weight and bias ~ U(+-1/sqrt(fan_in)), batch-norm gamma ~ U(0,1), beta = 0, LookupTable ~ N(0,1); running statistics
+// (0, 1).  Generator: mt19937 with Torch7's transforms (uniform = a + (b-a) * u32 / 2^32, normal = Box-Muller); the draw
+// ORDER is this library's tensor order (group by group in the order of model.lua:150), not nngraph's, so a seed does not
+// reproduce Torch7's exact weights - distributions only (no Torch7 exists here to compare against).
+void Engine::init_params(uint64_t seed) {
+  std::mt19937 gen((uint32_t)(seed ^ (seed >> 32)));
+  auto uni = [&](double a, double b) { return a + (b - a) * ((double)gen() * (1.0 / 4294967296.0)); };
+  auto normal = [&]() {
+    const double u1 = uni(0.0, 1.0), u2 = uni(0.0, 1.0);
+    return sqrt(-2.0 * log(1.0 - u2)) * cos(2.0 * M_PI * u1);
+  };
+  for (int g = 0; g < 5; g++) {
+    std::vector<float> v((size_t)L.gsize[g]);
+    for (const TensorEntry& e : L.tensors) {
+      if (e.group != g) continue;
+      float* d = v.data() + e.ext_off;
+      const double bound = e.fan_in > 0 ? 1.0 / sqrt((double)e.fan_in) : 0.0;
+      for (int64_t i = 0; i < e.n; i++) {
+        switch (e.init) {
+          case 0: case 1: d[i] = (float)uni(-bound, bound); break;
+          case 2: d[i] = (float)uni(0.0, 1.0); break;
+          case 3: d[i] = 0.f; break;
+          default: d[i] = (float)normal(); break;
+        }
+      }
+    }
+    set_params(g, v.data(), (int64_t)v.size());
+  }
+  const int bnc[3] = {256, 512, 512};
+  for (int i = 0; i < 3; i++) {
+    std::vector<float> z(bnc[i], 0.f), o(bnc[i], 1.f);
+    set_bn(i, z.data(), o.data(), bnc[i]);
+  }
+  params_set_ = true;
 }
 
 void Engine::get_flat(bool grads, int group, float* host, int64_t n) {

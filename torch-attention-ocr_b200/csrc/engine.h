@@ -26,7 +26,9 @@ extern const ConvSpec kConv[7];
 // one parameter tensor: where it sits in the caller-visible ("Torch") group vector and in the device buffer.
 // Device offsets are padded to 64 floats so every tensor is 256-byte aligned (float4 / TMA requirements);
 // the padding holds zeros in both params and grads, so group norms and axpys are unaffected.
-struct TensorEntry { int group; int64_t ext_off, phys_off, n; int conv_cout, conv_cin, conv_kk; };
+// init: how Torch7's reset() draws the tensor: 0 = U(+-1/sqrt(fan_in)) weight, 1 = bias of the preceding
+// weight (same bound), 2 = batch-norm gamma U(0,1), 3 = batch-norm beta (0), 4 = LookupTable N(0,1)
+struct TensorEntry { int group; int64_t ext_off, phys_off, n; int conv_cout, conv_cin, conv_kk; int init = 0; int fan_in = 0; };
 
 struct ParamLayout {
   int64_t goff[5], gsize[5] /* caller-visible sizes */, gphys[5] /* device extent incl. padding */, total;
@@ -45,6 +47,7 @@ class Engine {
   ~Engine();
 
   void set_params(int group, const float* host, int64_t n);
+  void init_params(uint64_t seed);   // Model:create's module construction (model.lua:83-112): Torch7 reset() distributions
   void get_flat(bool grads, int group, float* host, int64_t n);
   void set_bn(int layer, const float* mean, const float* var, int64_t n);
   void get_bn(int layer, float* mean, float* var, int64_t n);
@@ -54,6 +57,10 @@ class Engine {
   double read_loss();
   void group_norms(double* pn, double* gn);
   void sgd_enqueue(double lr, double clip);
+  void set_lr_clip(double lr, double clip);
+  void sgd_enqueue_kernels();
+  void set_global_batch(int n) { AOCR_CHECK(n >= 0, "global batch must be >= 0"); cfg.global_batch = n; }
+  int global_b() const { return cfg.global_batch > 0 ? cfg.global_batch : b_; }
   void decode_enqueue();
   void decode_collect(int32_t* labels, double* pred, double* gold, double* loss_sum, int32_t* num_correct);
   void get_logprobs(int which, float* out, int64_t n);
@@ -111,7 +118,7 @@ class Engine {
   bool fused_rec() const { return rec_ && fuse_on_ && rec_->cluster > 1; }
   // the decoder layers use the fused GEMM -> cell commands (and therefore the gate-interleaved weight packs)
   bool dec_fused_ok() const {
-    return persist_on_ && fuse_on_ && cluster_ > 1 && b_ <= 128 && cfg.gemm_mode != 2 && Hd % 32 == 0 &&
+    return persist_on_ && fuse_on_ && cluster_ > 1 && b_ <= 256 && cfg.gemm_mode != 2 && Hd % 32 == 0 &&
            pad64(K1) / 64 >= cluster_ && pad64(2 * Hd) / 64 >= cluster_;
   }
   // emitters: launch a piece of a recurrence as its own kernel, or record it into a persistent program
@@ -176,8 +183,10 @@ class Engine {
   void join_from(int i);
   bool graphs_on_ = true;
   int64_t graph_launches_train_ = 0, graph_launches_decode_ = 0;
-  struct GraphKey { int kind, b, W, T; double lr, clip; bool operator<(const GraphKey& o) const {
-    return std::tie(kind, b, W, T, lr, clip) < std::tie(o.kind, o.b, o.W, o.T, o.lr, o.clip); } };
+  struct GraphKey { int kind, b, W, T, gb; bool operator<(const GraphKey& o) const {
+    return std::tie(kind, b, W, T, gb) < std::tie(o.kind, o.b, o.W, o.T, o.gb); } };
+  static constexpr size_t kMaxGraphs = 64, kMaxPrograms = 256;   // caches keyed by batch shape: dropped wholesale when full
+  void drop_graphs();
   struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; };
   std::map<GraphKey, GraphEntry> graphs_;
   bool phases_on_ = false;
@@ -231,6 +240,7 @@ class Engine {
   // current batch
   int b_ = 0, W_ = 0, T_ = 0, W1_ = 0, W2_ = 0, S_ = 0;
   bool have_batch_ = false, have_grads_ = false, weights_dirty_ = true;
+  bool params_set_ = false;   // a step on a handle whose parameters were never drawn / imported is refused (all-zero model)
   int dec_steps_ = 0;
   std::vector<int32_t> h_tev_;
   int last_logp_rows_[3] = {0, 0, 0};
@@ -253,7 +263,7 @@ class Engine {
         *DE = nullptr, *dQ = nullptr, *dH2q = nullptr, *dG2 = nullptr, *dG1 = nullptr, *dX2 = nullptr, *dX1 = nullptr,
         *dc1 = nullptr, *dc2 = nullptr, *dP = nullptr, *CtxWc = nullptr, *dCtxWc = nullptr;
   int32_t *tok = nullptr, *labels = nullptr, *tokseq = nullptr;
-  double *score = nullptr, *d_loss = nullptr, *d_sumsq = nullptr, *d_sq_partial = nullptr;
+  double *score = nullptr, *d_loss = nullptr, *d_sumsq = nullptr, *d_sq_partial = nullptr, *d_lrclip = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 };
 

@@ -189,7 +189,7 @@ void Engine::decoder_backward() {
   const int B = b_, S = S_, T = T_;
   const int in1 = E + (cfg.input_feed ? Hd : 0);
   const int64_t R = (int64_t)T * B;
-  const float inv_bn = 1.0f / (float)(cfg.global_batch > 0 ? cfg.global_batch : B);
+  const float inv_bn = 1.0f / (float)global_b();    // model.lua:645-647 (Q7: the GLOBAL batch under data parallelism)
   // generator + criterion for all steps at once (a_t are all known): model.lua:644-648
   generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[0], dZ, rowloss, R, Hd, V, inv_bn);
   reduce_sum_double(ctx_, rowloss, R, d_loss);
@@ -335,6 +335,7 @@ StatSync Engine::stat_sync() {
   StatSync s;
   if (cfg.dp_world > 1) {
     s.fn = stat_sync_tramp; s.user = this; s.world = cfg.dp_world;
+    s.grows = (double)global_b() / (double)b_;     // all ranks share H x W: global rows = rows * global batch / local batch
   }
   return s;
 }
@@ -353,6 +354,11 @@ void Engine::grad_join() {
 // feval, train branch (model.lua:284-316,537-569,634-695)
 void Engine::forward_backward_enqueue() {
   AOCR_CHECK(have_batch_, "no batch staged");
+  AOCR_CHECK(params_set_, "the model has no parameters yet: call aocr_init_params or aocr_set_params first");
+  // data parallelism: the loss scale and the batch-norm row count need the step's GLOBAL batch; a SUM all-reduce with
+  // the local 1/b would silently yield gradients `world` times too large
+  AOCR_CHECK(cfg.dp_world <= 1 || cfg.global_batch >= b_,
+             "dp_world > 1 needs global_batch (aocr_config.global_batch or aocr_set_global_batch) >= the local batch");
   AOCR_CUDA(cudaSetDevice(device_));
   const int B = b_, T = T_;
   const bool prepped = prep_weights();
@@ -433,15 +439,25 @@ void Engine::group_norms(double* pn, double* gn) {
 }
 
 // optim.sgd_list, default branch (optim_sgd.lua:49-52,90): per group clip to `clip`, p -= lr*g.  No host sync.
+void Engine::set_lr_clip(double lr, double clip) {
+  // pageable source: the runtime stages the 16 bytes before cudaMemcpyAsync returns, so back-to-back enqueues with
+  // different learning rates cannot race on a host buffer.  Never captured: the step size is data of a replayed graph.
+  const double v[2] = {lr, clip};
+  AOCR_CUDA(cudaMemcpyAsync(d_lrclip, v, sizeof(v), cudaMemcpyHostToDevice, ctx_.st));
+}
 void Engine::sgd_enqueue(double lr, double clip) {
   AOCR_CHECK(have_grads_, "no gradients yet: call aocr_forward_backward first");
+  set_lr_clip(lr, clip);
+  sgd_enqueue_kernels();
+}
+void Engine::sgd_enqueue_kernels() {
   SgdGroups G;
   for (int g = 0; g < 5; g++) {
     G.off[g] = L.goff[g]; G.n[g] = L.gphys[g];
     int64_t nb = L.gphys[g] / 16384 + 1;          // ~16k floats per block and pass
     G.nb[g] = (int)(nb < 1024 ? nb : 1024);
   }
-  sgd_groups(ctx_, d_params, d_grads, G, d_sq_partial, d_sumsq, lr, clip);
+  sgd_groups(ctx_, d_params, d_grads, G, d_sq_partial, d_sumsq, d_lrclip);
   mark_weights_dirty();
 }
 
@@ -453,12 +469,14 @@ void Engine::sgd_enqueue(double lr, double clip) {
 // native NCCL one (engine_nccl.cu); with a host hook (aocr_set_allreduce) they stay eager.  Never while profiling.
 void Engine::train_step_enqueue(double lr, double clip) {
   const bool eligible = graphs_on_ && (cfg.dp_world <= 1 || dp_native()) && !prof_on && !phases_on_;
+  set_lr_clip(lr, clip);           // outside any capture: one graph per shape serves every learning rate
   if (!eligible) {
     forward_backward_enqueue();
-    sgd_enqueue(lr, clip);
+    sgd_enqueue_kernels();
     return;
   }
-  GraphKey key{0, b_, W_, T_, lr, clip};
+  GraphKey key{0, b_, W_, T_, cfg.global_batch};
+  if (graphs_.size() >= kMaxGraphs && graphs_.find(key) == graphs_.end()) drop_graphs();   // variable T / W: bounded
   GraphEntry& e = graphs_[key];
   if (e.exec == nullptr && e.seen >= 1) {
     mark_weights_dirty();          // the captured sequence must contain the weight-pack refresh
@@ -466,7 +484,7 @@ void Engine::train_step_enqueue(double lr, double clip) {
     AOCR_CUDA(cudaStreamBeginCapture(ctx_.st, cudaStreamCaptureModeThreadLocal));
     try {
       forward_backward_enqueue();
-      sgd_enqueue(lr, clip);
+      sgd_enqueue_kernels();
     } catch (...) {
       cudaStreamEndCapture(ctx_.st, &graph);
       if (graph) cudaGraphDestroy(graph);
@@ -485,15 +503,22 @@ void Engine::train_step_enqueue(double lr, double clip) {
   } else {
     const int64_t l0 = ctx_.launches;
     forward_backward_enqueue();
-    sgd_enqueue(lr, clip);
+    sgd_enqueue_kernels();
     graph_launches_train_ = ctx_.launches - l0;
   }
+}
+
+void Engine::drop_graphs() {
+  AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  for (auto& kv : graphs_) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
 }
 
 void Engine::decode_step_enqueue() {
   const bool eligible = graphs_on_ && !prof_on && !phases_on_;
   if (!eligible) { decode_enqueue(); return; }
-  GraphKey key{1, b_, W_, T_, 0.0, 0.0};
+  GraphKey key{1, b_, W_, T_, 0};
+  if (graphs_.size() >= kMaxGraphs && graphs_.find(key) == graphs_.end()) drop_graphs();
   GraphEntry& e = graphs_[key];
   if (e.exec == nullptr && e.seen >= 1 && !weights_dirty_) {
     cudaGraph_t graph = nullptr;
@@ -524,6 +549,7 @@ void Engine::decode_step_enqueue() {
 // forward_only branch, beam 1, no trie (model.lua:360-404,446-459,516-536,570-627)
 void Engine::decode_enqueue() {
   AOCR_CHECK(have_batch_, "no batch staged");
+  AOCR_CHECK(params_set_, "the model has no parameters yet: call aocr_init_params or aocr_set_params first");
   AOCR_CUDA(cudaSetDevice(device_));
   const int B = b_, T = T_, Ld = Tmax;
   const bool prepped = prep_weights();
@@ -534,7 +560,7 @@ void Engine::decode_enqueue() {
   encoder_forward();
   attention_precompute();
   dec_steps_ = Ld;
-  if (persist_on_ && cfg.gemm_mode != 2 && 2 * B <= 128 && dual_on_) {
+  if (persist_on_ && cfg.gemm_mode != 2 && 2 * B <= 256 && dual_on_) {
     // Dual pass: the greedy pass and the teacher-forced gold pass are independent recurrences over the same encoder
     // state, and a decoder step is bound by streaming the weights, not by the batch: run them as ONE batch of 2B rows
     // (rows [0,B) greedy, rows [B,2B) gold) and halve the number of sequential steps (model.lua:360-404 + 589-627).

@@ -8,10 +8,17 @@ namespace aocr {
 void Engine::run_program(int kind, int nsteps, int variant) {
   ProgKey key{kind, b_, S_, nsteps, variant};
   auto it = programs_.find(key);
+  if (it == programs_.end() && programs_.size() >= kMaxPrograms) {
+    // variable S / T per batch: the cache is bounded.  Captured graphs reference the programs' device buffers.
+    drop_graphs();
+    for (int l = 1; l < 3; l++) if (lanes_on_ && lanes_[l].st) AOCR_CUDA(cudaStreamSynchronize(lanes_[l].st));
+    for (auto& kv : programs_) persist_free(kv.second);
+    programs_.clear();
+  }
   if (it == programs_.end()) {
     PersistProgram prog;
-    int bn = b_ > 64 ? 128 : (b_ > 32 ? 64 : (b_ > 16 ? 32 : 16));
-    AOCR_CHECK(b_ <= 128, "persistent executor: per-GPU batch must be <= 128");
+    int bn = b_ > 128 ? 256 : (b_ > 64 ? 128 : (b_ > 32 ? 64 : (b_ > 16 ? 32 : 16)));
+    AOCR_CHECK(b_ <= 256, "persistent executor: at most 256 rows per command (UMMA N <= 256)");
     prog.bn = bn;
     const bool enc = (kind == PK_ENC_FWD0 || kind == PK_ENC_FWD0 + 1 || kind == PK_ENC_BWD0 || kind == PK_ENC_BWD0 + 1);
     int cap = persist_max_ctas(bn);

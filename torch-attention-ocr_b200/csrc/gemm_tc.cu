@@ -14,6 +14,7 @@
 
 #include <map>
 #include <mutex>
+#include <set>
 #include <tuple>
 
 #include "gemm_tc.cuh"
@@ -439,10 +440,16 @@ const CUtensorMap& map_4d(const __nv_bfloat16* ptr, int N, int H, int W, int C, 
 template <int BN>
 void launch(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
             const TcParams& p, dim3 grid) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AOCR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
-    attr_set = true;
+  {   // function attributes are per device: once for every device a handle of this process launches on
+    static std::mutex mu;
+    static std::set<int> done;
+    int dev = 0;
+    AOCR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done.count(dev)) {
+      AOCR_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+      done.insert(dev);
+    }
   }
   launch_pdl(ctx, tc_gemm_kernel<BN>, grid, dim3(192), (p.dbg & 8) ? (size_t)4096 : (size_t)Cfg<BN>::kSmemBytes, ah, al, bh, bl, p);
   AOCR_CUDA(cudaGetLastError());

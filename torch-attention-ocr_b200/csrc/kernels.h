@@ -24,7 +24,8 @@ void im2col(Ctx&, const float* a, float* col, int B, int H, int Wi, int C, int k
 // column statistics of z (R,C): sum and (two-pass) centred sum of squares; deterministic.
 void col_sum(Ctx&, const float* z, int64_t R, int C, float* out /*[C]*/, float* partial, int accumulate);
 // cross-rank summation hook for batch-norm statistics (data parallelism); world == 1: unused
-struct StatSync { void (*fn)(void* user, float* buf, int64_t n) = nullptr; void* user = nullptr; int world = 1; };
+// grows: global rows / local rows of a batch-norm reduction (= global batch / this rank's batch; the shards need not be equal)
+struct StatSync { void (*fn)(void* user, float* buf, int64_t n) = nullptr; void* user = nullptr; int world = 1; double grows = 1.0; };
 // one pass over z: batch mean / biased variance (global over the data-parallel ranks: ONE all-reduce of [sum | sum sq])
 // and the running-statistics update (momentum 0.1, unbiased variance) [T7 nn.SpatialBatchNormalization]
 void bn_stats(Ctx&, const float* z, int64_t R, int C, float* mean, float* var /*biased*/, float* rmean, float* rvar,
@@ -121,7 +122,8 @@ void sgd_apply(Ctx&, float* p, float* g, int64_t n, const double* sumsq, double 
 // the three steps above for all 5 parameter groups in 3 launches; nb[g] <= 1024 blocks work on group g (fixed
 // assignment: deterministic), partial is [5][1024] doubles, sumsq [5]
 struct SgdGroups { int64_t off[5]; int64_t n[5]; int nb[5]; };
-void sgd_groups(Ctx&, float* params, float* grads, const SgdGroups& G, double* partial, double* sumsq, double lr, double clip);
+// lrclip: device pointer to {lr, clip} (the step size is data, not a launch parameter: a captured step is replayed with any lr)
+void sgd_groups(Ctx&, float* params, float* grads, const SgdGroups& G, double* partial, double* sumsq, const double* lrclip);
 void scale_vec(Ctx&, float* v, int64_t n, float s);
 void axpy_vec(Ctx&, float* y, const float* x, int64_t n, float a);
 

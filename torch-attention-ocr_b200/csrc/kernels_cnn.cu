@@ -538,7 +538,7 @@ void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* va
   launch_pdl(ctx, col_reduce_final2_kernel, dim3(cdiv(2 * C, 128)), dim3(128), 0, (const float*)partial, ns, C, sums, sums + C);
   AOCR_CUDA(cudaGetLastError());
   if (sync.world > 1) sync.fn(sync.user, sums, 2 * (int64_t)C);       // ONE all-reduce: [sum | sum of squares]
-  const double Rg = (double)R * sync.world;
+  const double Rg = (double)R * sync.grows;
   launch_pdl(ctx, bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, (const float*)sums, C, (float)(1.0 / Rg),
              Rg > 1 ? (float)(Rg / (Rg - 1)) : 1.f, mean, var, rmean, rvar);
   AOCR_CUDA(cudaGetLastError());
@@ -578,7 +578,7 @@ void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, cons
     else { sync.fn(sync.user, dgamma, C); sync.fn(sync.user, dbeta, C); }
   }
   launch_pdl(ctx, bn_bwd_apply_kernel, dim3(grid_for(R * C, 256, ctx.num_sms)), dim3(256), 0, dz, z, mean, var, gamma, dbeta, dgamma,
-                                                                           R, R * sync.world, C, train, phi, plo);
+                                                                           R, (int64_t)llround((double)R * sync.grows), C, train, phi, plo);
   AOCR_CUDA(cudaGetLastError());
   if (sync.world > 1) {   // the gradient all-reduce will sum these again over ranks: pre-divide
     scale_vec(ctx, dgamma, C, 1.0f / (float)sync.world);

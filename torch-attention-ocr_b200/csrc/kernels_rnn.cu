@@ -614,9 +614,11 @@ __global__ void __launch_bounds__(256) sumsq_final_groups_kernel(const double* _
   if (threadIdx.x == 0) out[g] = red[0];
 }
 __global__ void __launch_bounds__(256) sgd_apply_groups_kernel(float* __restrict__ pbase, float* __restrict__ gbase, SgdGroups G,
-                                                               const double* __restrict__ sumsq, double lr, double clip) {
+                                                               const double* __restrict__ sumsq,
+                                                               const double* __restrict__ lrclip) {
   pdl_launch_dependents();
   pdl_wait();
+  const double lr = lrclip[0], clip = lrclip[1];
   int local;
   const int g = group_of_block(G, blockIdx.x, local);
   const double norm = sqrt(sumsq[g]);
@@ -637,15 +639,15 @@ __global__ void __launch_bounds__(256) sgd_apply_groups_kernel(float* __restrict
 
 }  // namespace
 
-void sgd_groups(Ctx& ctx, float* params, float* grads, const SgdGroups& G, double* partial, double* sumsq, double lr,
-                double clip) {
+void sgd_groups(Ctx& ctx, float* params, float* grads, const SgdGroups& G, double* partial, double* sumsq,
+                const double* lrclip) {
   int total = 0;
   for (int g = 0; g < 5; g++) total += G.nb[g];
   launch_pdl(ctx, sumsq_groups_kernel, dim3(total), dim3(256), 0, (const float*)grads, G, partial);
   AOCR_CUDA(cudaGetLastError());
   launch_pdl(ctx, sumsq_final_groups_kernel, dim3(5), dim3(256), 0, (const double*)partial, G, sumsq);
   AOCR_CUDA(cudaGetLastError());
-  launch_pdl(ctx, sgd_apply_groups_kernel, dim3(total), dim3(256), 0, params, grads, G, (const double*)sumsq, lr, clip);
+  launch_pdl(ctx, sgd_apply_groups_kernel, dim3(total), dim3(256), 0, params, grads, G, (const double*)sumsq, lrclip);
   AOCR_CUDA(cudaGetLastError());
 }
 

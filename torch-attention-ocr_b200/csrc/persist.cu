@@ -6,6 +6,8 @@
 // release, preceded by fence.proxy.async so the generic-proxy stores of a command are visible to the TMA loads of
 // the next one on every SM) replaces the kernel boundary between consecutive commands.
 #include <algorithm>
+#include <mutex>
+#include <set>
 #include <type_traits>
 
 #include <cooperative_groups.h>
@@ -21,38 +23,83 @@ namespace {
 using namespace tcp;
 namespace cg = cooperative_groups;
 
+// Shared-memory layout (per CTA, one CTA per SM):
+//   [A ring: kStages x (hi 16 KB | lo 16 KB)]  weight tiles only.  Never overlaid by anything, so (i) the A tiles of the
+//        NEXT command are loaded before the grid barrier that ends the current one (weights do not depend on it) and
+//        (ii) a tile that is still in its slot from an earlier timestep is not loaded again (slot tags) - the encoder's
+//        recurrent weights (64 KB per CTA) become resident after two steps.
+//   [B ring: kStages x (hi | lo) of BN activation rows]  = the scratch region: dead once a command's MMAs have retired,
+//        it doubles as the fused commands' split-K staging tile ([BN columns][128 rows] fp32, read by the cluster
+//        peers through DSMEM until the grid barrier) and as the bodies' scratch; B loads are issued after the barrier.
+//   [mbarriers | slot tags | TMEM slot | 2 command buffers (the next command is fetched while the current one runs)]
 template <int BN> struct PCfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int kBPlane = BN * BK * 2;
-  static constexpr int kStageBytes = 2 * A_PLANE_BYTES + 2 * kBPlane;
+  static constexpr int kABytes = 2 * A_PLANE_BYTES;
+  static constexpr int kBBytes = 2 * kBPlane;
+  static constexpr int kARegion = kStages * kABytes;
+  static constexpr int kBRegion = kStages * kBBytes;
+  static constexpr int kScratch = kBRegion > 49152 ? kBRegion : 49152;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kCtlBytes = 256;                       // barriers (2*kStages + 1) * 8, TMEM slot, slot tags
+  static constexpr int kSmemBytes = kARegion + kScratch + kCtlBytes + 2 * (int)sizeof(PCmd) + 1024;
+  static_assert(BN * BM * 4 <= kScratch, "fused staging tile must fit in the scratch region");
 };
 
-__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned nblk, unsigned& epoch) {
-  asm volatile("fence.proxy.async;" ::: "memory");      // this thread's stores -> visible to the async proxy (TMA)
-  __syncthreads();
-  epoch++;
-  if (threadIdx.x == 0) {
-    // arrive: a release reduction (no return value, so no round trip before the polling starts); the release is
-    // cumulative over the CTA's writes ordered before it by the bar.sync above
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
-    const unsigned target = epoch * nblk;
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target);
-  }
-  __syncthreads();
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {   // no arrival: a prefetch posts its bytes early
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// identity of an A (weight) tile: tensor-map pair, row origin, k origin
+__device__ __forceinline__ unsigned long long a_tag(int map_a, int m0, int kc) {
+  return ((unsigned long long)(unsigned)map_a << 44) | ((unsigned long long)(unsigned)m0 << 22) | (unsigned long long)(unsigned)kc;
+}
+
+// tile assignment of a GEMM-type command: (mt, z) of this CTA, or has == false
+struct TileOf { int mt, z, kb_begin, nkb; bool has; };
+__device__ __forceinline__ TileOf tile_of(const PGemm& g, bool fused, int bid) {
+  TileOf t;
+  t.has = bid < g.m_tiles * g.splits;
+  t.z = fused ? (int)(bid % g.splits) : bid / g.m_tiles;
+  t.mt = fused ? (int)(bid / g.splits) : bid % g.m_tiles;
+  t.kb_begin = t.z * g.kb_per;
+  t.nkb = min(g.num_kb, t.kb_begin + g.kb_per) - t.kb_begin;
+  return t;
 }
 
 // ---- fused GEMM -> cell: the cluster owns 32 hidden units x 4 gates (gate-interleaved weight rows: tile row =
 // gate*32 + unit) for the whole batch; rank z holds the split-K partial z in shared memory as stage[column][row].
 // Rank z finishes batch columns [z*BN/nz, (z+1)*BN/nz): sums the nz partials of the 4 gates through DSMEM, applies the
 // LSTM cell and writes what the stand-alone cell body writes.
+// Everything the cell needs besides the gate sums (input projection / embedding row, previous cell state) is loaded
+// into registers at the START of the command (CellPre), so those L2 round trips overlap the GEMM instead of following
+// the cluster barrier.
+constexpr int kCellPre = 4;      // batch columns per thread whose inputs are preloaded (BN / cluster / 8 warps <= 4 up to BN = 128)
+struct CellPre { float a[kCellPre][4]; float c[kCellPre]; };
+
+template <int BN>
+__device__ __forceinline__ void enc_cell_preload(const EncCellFwdTc& p, int mt, int z, int nz, CellPre& r) {
+  const int He = p.He, B = p.B, S = p.S, d = p.d_only;
+  const int unit = mt * 32 + (threadIdx.x & 31), cols = BN / nz;
+  const int t = d == 0 ? p.step : S - 1 - p.step;
+  const int prev_slot = d == 0 ? t : t + 1;
+#pragma unroll
+  for (int j = 0; j < kCellPre; j++) {
+    const int bq = (threadIdx.x >> 5) + 8 * j, b = z * cols + bq;
+    if (bq >= cols || b >= B || unit >= He) continue;
+    const float* xg = p.xg + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
+#pragma unroll
+    for (int g = 0; g < 4; g++) r.a[j][g] = __ldcg(xg + g * He);
+    r.c[j] = __ldcg(p.Cst + ((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit);
+  }
+}
 template <int BN>
 __device__ __forceinline__ void fused_enc_cell_fwd(const EncCellFwdTc& p, cg::cluster_group& cluster, float* stage, int mt,
-                                                   int z, int nz) {
+                                                   int z, int nz, const CellPre& r) {
   const int He = p.He, B = p.B, S = p.S;
   const int d = p.d_only;
   const int ul = threadIdx.x & 31, unit = mt * 32 + ul;
@@ -62,9 +109,10 @@ __device__ __forceinline__ void fused_enc_cell_fwd(const EncCellFwdTc& p, cg::cl
   const float* rs[8];
 #pragma unroll
   for (int q = 0; q < 8; q++) rs[q] = q < nz ? cluster.map_shared_rank(stage, q) : stage;
-  for (int bq = threadIdx.x >> 5; bq < cols; bq += 8) {
-    const int b = z * cols + bq;
-    if (b >= B || unit >= He) continue;
+#pragma unroll 1
+  for (int j = 0; j * 8 < cols; j++) {
+    const int bq = (threadIdx.x >> 5) + 8 * j, b = z * cols + bq;
+    if (bq >= cols || b >= B || unit >= He) continue;
     float gsum[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -73,12 +121,20 @@ __device__ __forceinline__ void fused_enc_cell_fwd(const EncCellFwdTc& p, cg::cl
       for (int q = 0; q < 8; q++) v[q] = q < nz ? rs[q][b * BM + g * 32 + ul] : 0.f;
       gsum[g] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
-    const float* xg = p.xg + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
-    const float i_ = decb::sigmoidf_(gsum[0] + xg[0]);
-    const float f_ = decb::sigmoidf_(gsum[1] + xg[He]);
-    const float o_ = decb::sigmoidf_(gsum[2] + xg[2 * He]);
-    const float g_ = tanhf(gsum[3] + xg[3 * He]);
-    const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
+    float a4[4], cp;
+    if (j < kCellPre) {
+#pragma unroll
+      for (int jj = 0; jj < kCellPre; jj++)
+        if (jj == j) { a4[0] = r.a[jj][0]; a4[1] = r.a[jj][1]; a4[2] = r.a[jj][2]; a4[3] = r.a[jj][3]; cp = r.c[jj]; }
+    } else {
+      const float* xg = p.xg + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
+      a4[0] = __ldcg(xg); a4[1] = __ldcg(xg + He); a4[2] = __ldcg(xg + 2 * He); a4[3] = __ldcg(xg + 3 * He);
+      cp = __ldcg(p.Cst + ((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit);
+    }
+    const float i_ = decb::sigmoidf_(gsum[0] + a4[0]);
+    const float f_ = decb::sigmoidf_(gsum[1] + a4[1]);
+    const float o_ = decb::sigmoidf_(gsum[2] + a4[2]);
+    const float g_ = tanhf(gsum[3] + a4[3]);
     const float c = f_ * cp + i_ * g_;
     const float h = o_ * tanhf(c);
     p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit] = c;
@@ -92,17 +148,32 @@ __device__ __forceinline__ void fused_enc_cell_fwd(const EncCellFwdTc& p, cg::cl
 
 // decoder layer: same structure, CellFwdTc semantics (embedding / bias rows added per batch row)
 template <int BN>
+__device__ __forceinline__ void cell_preload(const CellFwdTc& p, int mt, int z, int nz, CellPre& r) {
+  const int H = p.H;
+  const int u = mt * 32 + (threadIdx.x & 31), cols = BN / nz;
+#pragma unroll
+  for (int j = 0; j < kCellPre; j++) {
+    const int bq = (threadIdx.x >> 5) + 8 * j, b = z * cols + bq;
+    if (bq >= cols || b >= p.B || u >= H) continue;
+    const float* ar = p.addrows + (p.rowsel ? (int64_t)(__ldcg(p.rowsel + b) - 1) * p.addld : 0) + u;
+#pragma unroll
+    for (int g = 0; g < 4; g++) r.a[j][g] = __ldcg(ar + g * H);
+    r.c[j] = __ldcg(p.c_prev + (int64_t)b * H + u);
+  }
+}
+template <int BN>
 __device__ __forceinline__ void fused_cell_fwd(const CellFwdTc& p, cg::cluster_group& cluster, float* stage, int mt, int z,
-                                               int nz) {
+                                               int nz, const CellPre& r) {
   const int H = p.H;
   const int ul = threadIdx.x & 31, u = mt * 32 + ul;
   const int cols = BN / nz;
   const float* rs[8];
 #pragma unroll
   for (int q = 0; q < 8; q++) rs[q] = q < nz ? cluster.map_shared_rank(stage, q) : stage;
-  for (int bq = threadIdx.x >> 5; bq < cols; bq += 8) {
-    const int b = z * cols + bq;
-    if (b >= p.B || u >= H) continue;
+#pragma unroll 1
+  for (int j = 0; j * 8 < cols; j++) {
+    const int bq = (threadIdx.x >> 5) + 8 * j, b = z * cols + bq;
+    if (bq >= cols || b >= p.B || u >= H) continue;
     float gsum[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -111,13 +182,22 @@ __device__ __forceinline__ void fused_cell_fwd(const CellFwdTc& p, cg::cluster_g
       for (int q = 0; q < 8; q++) v[q] = q < nz ? rs[q][b * BM + g * 32 + ul] : 0.f;
       gsum[g] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
-    const float* ar = p.addrows + (p.rowsel ? (int64_t)(__ldcg(p.rowsel + b) - 1) * p.addld : 0) + u;
-    const float i_ = decb::sigmoidf_(gsum[0] + ar[0]);
-    const float f_ = decb::sigmoidf_(gsum[1] + ar[H]);
-    const float o_ = decb::sigmoidf_(gsum[2] + ar[2 * H]);
-    const float g_ = tanhf(gsum[3] + ar[3 * H]);
     const int64_t e = (int64_t)b * H + u;
-    const float c = f_ * p.c_prev[e] + i_ * g_;
+    float a4[4], cp;
+    if (j < kCellPre) {
+#pragma unroll
+      for (int jj = 0; jj < kCellPre; jj++)
+        if (jj == j) { a4[0] = r.a[jj][0]; a4[1] = r.a[jj][1]; a4[2] = r.a[jj][2]; a4[3] = r.a[jj][3]; cp = r.c[jj]; }
+    } else {
+      const float* ar = p.addrows + (p.rowsel ? (int64_t)(__ldcg(p.rowsel + b) - 1) * p.addld : 0) + u;
+      a4[0] = __ldcg(ar); a4[1] = __ldcg(ar + H); a4[2] = __ldcg(ar + 2 * H); a4[3] = __ldcg(ar + 3 * H);
+      cp = __ldcg(p.c_prev + e);
+    }
+    const float i_ = decb::sigmoidf_(gsum[0] + a4[0]);
+    const float f_ = decb::sigmoidf_(gsum[1] + a4[1]);
+    const float o_ = decb::sigmoidf_(gsum[2] + a4[2]);
+    const float g_ = tanhf(gsum[3] + a4[3]);
+    const float c = f_ * cp + i_ * g_;
     const float h = o_ * tanhf(c);
     p.c_new[e] = c;
     float* a = p.acts + (int64_t)b * 4 * H + u;
@@ -142,27 +222,36 @@ constexpr unsigned kSetDecFwd = bit(P_GEMM) | bit(P_CELL_FWD) | bit(P_GEMM_CELL_
 constexpr unsigned kSetDecBwd = bit(P_GEMM) | bit(P_CELL_BWD) | bit(P_ATTN_DU) | bit(P_TO_DENSE);
 constexpr unsigned kSetDecode = kSetDecFwd | bit(P_GENERATOR) | bit(P_GREEDY) | bit(P_ATTN_OUT_GEN);
 constexpr unsigned kSetAll = 0xffffffffu;
+constexpr unsigned kGemmTypes = bit(P_GEMM) | bit(P_GEMM_ENC_FWD) | bit(P_GEMM_CELL_FWD);
+
 template <int BN, unsigned kSet>
 __global__ void __launch_bounds__(256, 1)
 persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __restrict__ maps, unsigned* barrier,
-               unsigned long long* trace) {
+               unsigned long long* trace, int flags) {
   using C_ = PCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bars = base + C_::kStages * C_::kStageBytes;
+  const uint32_t baseB = base + C_::kARegion;
+  const uint32_t bars = baseB + C_::kScratch;
+  auto slot_a = [&](int s) { return base + (uint32_t)s * C_::kABytes; };
+  auto slot_b = [&](int s) { return baseB + (uint32_t)s * C_::kBBytes; };
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C_::kStages + s); };
   const uint32_t tmem_full_bar = bars + 8u * (2 * C_::kStages);
   const uint32_t tmem_slot = bars + 8u * (2 * C_::kStages + 1);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-  float* scratch = reinterpret_cast<float*>(smem_raw + (base - raw));   // the (idle) TMA ring doubles as body scratch
+  unsigned long long* tags = reinterpret_cast<unsigned long long*>(smem_raw + (bars + 128u - raw));   // [kStages], producer thread only
+  const uint32_t cbuf0 = bars + C_::kCtlBytes;
+  auto cbuf = [&](int i) { return reinterpret_cast<const PCmd*>(smem_raw + (cbuf0 + (uint32_t)(i & 1) * (uint32_t)sizeof(PCmd) - raw)); };
+  float* scratch = reinterpret_cast<float*>(smem_raw + (baseB - raw));   // the (idle) B ring doubles as body scratch / fused stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bid = blockIdx.x, nblk = gridDim.x;
+  constexpr int kCmdChunks = (int)sizeof(PCmd) / 16;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C_::kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < C_::kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); tags[s] = ~0ull; }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,6 +261,10 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == 7 && lane < kCmdChunks && ncmds > 0) {
+    cp_async16(cbuf0 + lane * 16, reinterpret_cast<const uint8_t*>(cmds) + lane * 16);
+    cp_async_wait_all();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -180,10 +273,27 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
   unsigned epoch = 0;
   uint32_t it = 0;        // k-blocks this CTA has pushed through the ring so far (producer and issuer count alike)
   uint32_t tiles = 0;     // GEMM tiles this CTA has finished (parity of the TMEM-full barrier)
+  const uint32_t txA = (uint32_t)C_::kABytes, txB = (uint32_t)C_::kBBytes;
+
+  // A (weight) tile of k-block `kb` of GEMM g into slot s, unless the slot still holds it.  `arrive_with_b`: the call
+  // that follows the grid barrier also posts the arrival and the B bytes; the prefetch posts the A bytes only.
+  auto load_a = [&](const PGemm& g, int m0, int kb, int s, bool two, uint64_t pol_w) {
+    const unsigned long long tag = a_tag(g.map_a, m0, kb);
+    if (tags[s] == tag && !(flags & 2)) return false;
+    const CUtensorMap* tAh = maps + g.map_a;
+    tma_load_2d_hint(slot_a(s), tAh, full_bar(s), kb * BK, m0, pol_w);
+    if (two) tma_load_2d_hint(slot_a(s) + A_PLANE_BYTES, tAh + 1, full_bar(s), kb * BK, m0, pol_w);
+    tags[s] = tag;
+    return true;
+  };
 
   for (int c = 0; c < ncmds; c++) {
-    const PCmd& cmd = cmds[c];
+    const PCmd& cmd = *cbuf(c);
     const int type = cmd.type;
+    // fetch the next command into the other buffer while this one runs (its last reader finished before the barrier)
+    if (warp == 7 && lane < kCmdChunks && c + 1 < ncmds)
+      cp_async16(cbuf0 + (uint32_t)((c + 1) & 1) * (uint32_t)sizeof(PCmd) + lane * 16,
+                 reinterpret_cast<const uint8_t*>(cmds + (c + 1)) + lane * 16);
     unsigned long long t_begin = 0;
     if (trace && threadIdx.x == 0) {
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
@@ -193,22 +303,29 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
     if (is(P_GEMM) || is(P_GEMM_ENC_FWD) || is(P_GEMM_CELL_FWD)) {
       // P_GEMM: tile (mt, z) = (bid % m_tiles, bid / m_tiles), raw split-K partial -> global workspace.
       // Fused commands: the cluster is the M tile and the rank in the cluster is the split; the partial goes to this
-      // CTA's shared memory (the idle TMA ring), the cluster reduces through DSMEM and applies the cell right away.
+      // CTA's shared memory (the idle B ring), the cluster reduces through DSMEM and applies the cell right away.
       const bool fused = (kSet & (bit(P_GEMM_ENC_FWD) | bit(P_GEMM_CELL_FWD))) != 0 && (type != P_GEMM);
       const PGemm g = payload<PGemm>(cmd);
-      const int ntiles = g.m_tiles * g.splits;
-      const int z = fused ? (int)(bid % g.splits) : bid / g.m_tiles;
-      const int mt = fused ? (int)(bid / g.splits) : bid % g.m_tiles;
-      float* stage = reinterpret_cast<float*>(smem_raw + (base - raw));   // [BN columns][128 rows] fp32
-      if (bid < ntiles) {
-        const int kb_begin = z * g.kb_per;
-        const int kb_end = min(g.num_kb, kb_begin + g.kb_per);
-        const int nkb = kb_end - kb_begin;
+      const TileOf tl = tile_of(g, fused, bid);
+      const int z = tl.z, mt = tl.mt;
+      float* stage = scratch;                                  // [BN columns][128 rows] fp32
+      CellPre pre;
+      if (fused && tl.has) {
+        if constexpr ((kSet & bit(P_GEMM_ENC_FWD)) != 0) {
+          if (type == P_GEMM_ENC_FWD)
+            enc_cell_preload<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), mt, z, g.splits, pre);
+        }
+        if constexpr ((kSet & bit(P_GEMM_CELL_FWD)) != 0) {
+          if (type == P_GEMM_CELL_FWD)
+            cell_preload<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), mt, z, g.splits, pre);
+        }
+      }
+      if (tl.has) {
+        const int kb_begin = tl.kb_begin, nkb = tl.nkb;
         const int m0 = mt * BM;
+        const bool two = g.terms == 3;
         if (warp == 0) {
           if (lane == 0) {
-            const uint32_t tx = (uint32_t)(g.terms == 3 ? 2 : 1) * (A_PLANE_BYTES + C_::kBPlane);
-            const CUtensorMap* tAh = maps + g.map_a;
             const CUtensorMap* tBh = maps + g.map_b;
             const uint64_t pol_w = l2_policy_evict_last_frac();   // weights: re-read every timestep
             for (int i = 0; i < nkb; i++) {
@@ -216,16 +333,12 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
               const int s = n % C_::kStages;
               const uint32_t ph = (n / C_::kStages) & 1u;
               mbar_wait(empty_bar(s), ph ^ 1u);
-              const uint32_t sa = base + s * C_::kStageBytes;
-              const uint32_t sb = sa + 2 * A_PLANE_BYTES;
-              mbar_expect_tx(full_bar(s), tx);
+              const bool need_a = (flags & 2) || tags[s] != a_tag(g.map_a, m0, kb_begin + i);
+              mbar_expect_tx(full_bar(s), (need_a ? (two ? txA : txA / 2) : 0u) + (two ? txB : txB / 2));
+              if (need_a) load_a(g, m0, kb_begin + i, s, two, pol_w);
               const int kc = (kb_begin + i) * BK;
-              tma_load_2d_hint(sa, tAh, full_bar(s), kc, m0, pol_w);
-              tma_load_2d(sb, tBh, full_bar(s), g.b_k0 + kc, g.b_row0);
-              if (g.terms == 3) {
-                tma_load_2d_hint(sa + A_PLANE_BYTES, tAh + 1, full_bar(s), kc, m0, pol_w);
-                tma_load_2d(sb + C_::kBPlane, tBh + 1, full_bar(s), g.b_k0 + kc, g.b_row0);
-              }
+              tma_load_2d(slot_b(s), tBh, full_bar(s), g.b_k0 + kc, g.b_row0);
+              if (two) tma_load_2d(slot_b(s) + C_::kBPlane, tBh + 1, full_bar(s), g.b_k0 + kc, g.b_row0);
             }
           }
         } else if (warp == 1) {
@@ -237,15 +350,14 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
             if (lane == 0) {
-              const uint32_t sa = base + s * C_::kStageBytes;
-              const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+              const uint32_t sa = slot_a(s), sb = slot_b(s);
               const uint64_t dah = make_desc_kmajor_sw128(sa), dal = make_desc_kmajor_sw128(sa + A_PLANE_BYTES);
               const uint64_t dbh = make_desc_kmajor_sw128(sb), dbl = make_desc_kmajor_sw128(sb + C_::kBPlane);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; k++) {
                 const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
                 tc_mma(tmem_base, dah + adv, dbh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                if (g.terms == 3) {
+                if (two) {
                   tc_mma(tmem_base, dah + adv, dbl + adv, idesc, 1u);
                   tc_mma(tmem_base, dal + adv, dbh + adv, idesc, 1u);
                 }
@@ -272,7 +384,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (fused) {
-              // all of this CTA's MMAs have retired (tmem_full), so the ring is free: stage[column][tile row]
+              // all of this CTA's MMAs have retired (tmem_full), so the B ring is free: stage[column][tile row]
 #pragma unroll
               for (int j = 0; j < 16; j++) stage[(c0 + j) * BM + q * 32 + lane] = __uint_as_float(r[j]);
             } else if (row < g.M) {
@@ -291,19 +403,20 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       if (fused) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();                                       // every rank's partial tile is in its shared memory
-        if (bid < ntiles) {
+        if (tl.has) {
           if constexpr ((kSet & bit(P_GEMM_ENC_FWD)) != 0) {
             if (type == P_GEMM_ENC_FWD)
               fused_enc_cell_fwd<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z,
-                                     g.splits);
+                                     g.splits, pre);
           }
           if constexpr ((kSet & bit(P_GEMM_CELL_FWD)) != 0) {
             if (type == P_GEMM_CELL_FWD)
-              fused_cell_fwd<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z, g.splits);
+              fused_cell_fwd<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z, g.splits,
+                                 pre);
           }
         }
         // no second cluster barrier: the grid barrier that ends the command orders the peers' reads of this CTA's
-        // partial before anything reuses the ring
+        // partial before anything reuses the B ring
       }
     } else if (is(P_CELL_FWD)) {
       if constexpr ((kSet & bit(P_CELL_FWD)) != 0) decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);
@@ -361,7 +474,44 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         trace[2 * (ncmds + 1) + (size_t)c * nblk + bid] = t - t_begin;
       }
     }
-    grid_sync(barrier, (unsigned)nblk, epoch);
+    // ---- grid barrier (one global counter, release arrive / acquire poll) with the weight prefetch of the next command
+    // folded in: between this CTA's arrival and the last CTA's, thread 0 issues the A-tile loads of command c+1
+    if (warp == 7) cp_async_wait_all();                        // the next command is in its buffer
+    asm volatile("fence.proxy.async;" ::: "memory");          // this thread's stores -> visible to the async proxy (TMA)
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+      // arrive: a release reduction (no return value, so no round trip before the polling starts); the release is
+      // cumulative over the CTA's writes ordered before it by the bar.sync above
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(barrier), "r"(1u) : "memory");
+      if (c + 1 < ncmds && !(flags & 1)) {
+        const PCmd& nx = *cbuf(c + 1);
+        if ((kGemmTypes >> nx.type) & 1u) {
+          const PGemm& g = payload<PGemm>(nx);
+          const TileOf tl = tile_of(g, nx.type != P_GEMM, bid);
+          if (tl.has) {
+            const bool two = g.terms == 3;
+            const uint64_t pol_w = l2_policy_evict_last_frac();
+            const int npre = tl.nkb < C_::kStages ? tl.nkb : C_::kStages;
+            for (int i = 0; i < npre; i++) {
+              const uint32_t n = it + i;
+              const int s = n % C_::kStages;
+              const uint32_t ph = (n / C_::kStages) & 1u;
+              if (tags[s] == a_tag(g.map_a, tl.mt * BM, tl.kb_begin + i)) continue;     // resident
+              mbar_wait(empty_bar(s), ph ^ 1u);             // the slot's last readers have retired (this CTA is idle)
+              mbar_expect_tx_only(full_bar(s), two ? txA : txA / 2);
+              load_a(g, tl.mt * BM, tl.kb_begin + i, s, two, pol_w);
+            }
+          }
+        }
+      }
+      const unsigned target = epoch * (unsigned)nblk;
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(barrier) : "memory");
+      } while (v < target);
+    }
+    __syncthreads();
   }
 
   tc_fence_before();
@@ -372,19 +522,29 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
   }
 }
 
+// function attributes are per device: set once for every device a handle of this process launches on
+template <int BN, unsigned kSet>
+void ensure_attrs() {
+  static std::mutex mu;
+  static std::set<int> done;
+  int dev = 0;
+  AOCR_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(dev)) return;
+  AOCR_CUDA(cudaFuncSetAttribute(persist_kernel<BN, kSet>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes));
+  done.insert(dev);
+}
+
 template <int BN, unsigned kSet>
 void launch_bn(Ctx& ctx, PersistProgram& prog) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AOCR_CUDA(cudaFuncSetAttribute(persist_kernel<BN, kSet>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes));
-    attr_set = true;
-  }
+  ensure_attrs<BN, kSet>();
   const PCmd* cmds = prog.d_cmds;
   int ncmds = (int)prog.cmds.size();
   const CUtensorMap* maps = prog.d_maps;
   unsigned* bar = prog.d_barrier;
   unsigned long long* trace = prog.d_trace;
-  void* args[] = {(void*)&cmds, (void*)&ncmds, (void*)&maps, (void*)&bar, (void*)&trace};
+  static const int flags = getenv("AOCR_PERSIST_FLAGS") ? atoi(getenv("AOCR_PERSIST_FLAGS")) : 0;   // A/B: 1 no weight prefetch, 2 no resident tiles
+  void* args[] = {(void*)&cmds, (void*)&ncmds, (void*)&maps, (void*)&bar, (void*)&trace, (void*)&flags};
   AOCR_CUDA(cudaMemsetAsync(prog.d_barrier, 0, sizeof(unsigned), ctx.st));
   // cooperative (all CTAs co-resident: the grid barrier spins) + thread-block clusters of kCluster CTAs (the fused
   // GEMM -> cell commands reduce their split-K partials through distributed shared memory inside a cluster)
@@ -392,10 +552,14 @@ void launch_bn(Ctx& ctx, PersistProgram& prog) {
   cfgl.gridDim = dim3(prog.grid); cfgl.blockDim = dim3(256);
   cfgl.dynamicSmemBytes = (size_t)PCfg<BN>::kSmemBytes; cfgl.stream = ctx.st;
   cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
-  attrs[1].id = cudaLaunchAttributeClusterDimension;
-  attrs[1].val.clusterDim.x = prog.cluster; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
-  cfgl.attrs = attrs; cfgl.numAttrs = prog.cluster > 1 ? 2 : 1;
+  int na = 0;
+  if (prog.cluster > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = prog.cluster; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+    na++;
+  }
+  if (ctx.persist_coop) { attrs[na].id = cudaLaunchAttributeCooperative; attrs[na].val.cooperative = 1; na++; }
+  cfgl.attrs = attrs; cfgl.numAttrs = na;
   AOCR_CUDA(cudaLaunchKernelExC(&cfgl, (const void*)persist_kernel<BN, kSet>, args));
   ctx.launches++;
 }
@@ -464,6 +628,7 @@ int max_cluster_ctas_bn(int cluster) {
 int persist_max_cluster_ctas(int bn, int cluster) {
   if (cluster <= 1) return persist_max_ctas(bn);
   switch (bn) {
+    case 256: return max_cluster_ctas_bn<256>(cluster);
     case 128: return max_cluster_ctas_bn<128>(cluster);
     case 64: return max_cluster_ctas_bn<64>(cluster);
     case 32: return max_cluster_ctas_bn<32>(cluster);
@@ -471,8 +636,37 @@ int persist_max_cluster_ctas(int bn, int cluster) {
   }
 }
 
+// Launch-mode probe: an EMPTY program (no commands: TMEM alloc / dealloc only) launched the way the executor will be.
+// Returns cudaSuccess or the launch / execution error, with the error state cleared.  Tools that intercept launches
+// (Nsight Compute) reject the cooperative + thread-block-cluster combination; the engine then picks another mode.
+cudaError_t persist_probe(cudaStream_t st, int grid, int cluster, bool coop) {
+  constexpr int BN = 64;
+  cudaFuncSetAttribute(persist_kernel<BN, kSetEncFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::kSmemBytes);
+  const PCmd* cmds = nullptr; int ncmds = 0; const CUtensorMap* maps = nullptr; unsigned* bar = nullptr;
+  unsigned long long* trace = nullptr;
+  int flags = 0;
+  void* args[] = {(void*)&cmds, (void*)&ncmds, (void*)&maps, (void*)&bar, (void*)&trace, (void*)&flags};
+  cudaLaunchConfig_t cfgl = {};
+  cfgl.gridDim = dim3(grid); cfgl.blockDim = dim3(256);
+  cfgl.dynamicSmemBytes = (size_t)PCfg<BN>::kSmemBytes; cfgl.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (cluster > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = cluster; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1;
+    na++;
+  }
+  if (coop) { attrs[na].id = cudaLaunchAttributeCooperative; attrs[na].val.cooperative = 1; na++; }
+  cfgl.attrs = attrs; cfgl.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelExC(&cfgl, (const void*)persist_kernel<BN, kSetEncFwd>, args);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaGetLastError();
+  return e;
+}
+
 int persist_max_ctas(int bn) {
   switch (bn) {
+    case 256: return max_ctas_bn<256>();
     case 128: return max_ctas_bn<128>();
     case 64: return max_ctas_bn<64>();
     case 32: return max_ctas_bn<32>();
@@ -505,6 +699,7 @@ void persist_launch(Ctx& ctx, PersistProgram& prog) {
   auto go = [&](auto set) {
     constexpr unsigned S = decltype(set)::value;
     switch (prog.bn) {
+      case 256: launch_bn<256, S>(ctx, prog); break;
       case 128: launch_bn<128, S>(ctx, prog); break;
       case 64: launch_bn<64, S>(ctx, prog); break;
       case 32: launch_bn<32, S>(ctx, prog); break;

@@ -91,6 +91,7 @@ PGemmPlan persist_plan_gemm_fused(int M, int N, int K, int cluster);
 void persist_upload(Ctx& ctx, PersistProgram& prog);     // allocates + copies (once)
 void persist_launch(Ctx& ctx, PersistProgram& prog);     // cooperative launch on ctx.st
 void persist_free(PersistProgram& prog);
+cudaError_t persist_probe(cudaStream_t st, int grid, int cluster, bool coop);   // launch-mode probe (empty program)
 int persist_max_ctas(int bn);                            // co-resident CTAs of the executor on this device
 int persist_max_cluster_ctas(int bn, int cluster);       // the same when launched with thread-block clusters
 

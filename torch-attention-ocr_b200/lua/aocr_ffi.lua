@@ -15,6 +15,7 @@ int aocr_create(const aocr_config* cfg, int device, aocr_handle** out);
 void aocr_destroy(aocr_handle* h);
 const char* aocr_last_error(const aocr_handle* h);
 int aocr_param_groups(const aocr_handle* h, int32_t* n_groups, int64_t sizes[5]);
+int aocr_init_params(aocr_handle* h, uint64_t seed);
 int aocr_set_params(aocr_handle* h, int group, const float* host, int64_t n);
 int aocr_get_params(aocr_handle* h, int group, float* host, int64_t n);
 int aocr_get_grads(aocr_handle* h, int group, float* host, int64_t n);
@@ -48,6 +49,8 @@ typedef void (*aocr_allreduce_fn)(void* user, void* dev_ptr, int64_t n_floats, i
 int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user);
 int aocr_dp_unique_id(void* out128);
 int aocr_dp_init(aocr_handle* h, const void* id128);
+const char* aocr_last_global_error(void);
+int aocr_set_global_batch(aocr_handle* h, int32_t global_batch);
 int aocr_synchronize(aocr_handle* h);
 int64_t aocr_launch_count(const aocr_handle* h);
 int aocr_prof_enable(aocr_handle* h, int on);
