@@ -96,6 +96,25 @@ int aocr_decode_greedy(aocr_handle* h, const float* images, int b, int W,
                        const int32_t* targets, const int32_t* targets_eval, int T,
                        int32_t* labels, double* pred_scores, double* gold_scores,
                        double* loss_sum, int32_t* num_correct);
+/* model:step(batch, true, beam_size, trie) with beam_size > 1 and / or a dictionary — src/model/model.lua:226-251,
+ * 321-536 (beam search: first step on the un-replicated rows, sticky PAD, top-k over beam x vocabulary totals or the
+ * sorted walk over trie-valid continuations, parent re-gather of the state), :573-585 (backtrack from the best final
+ * beam), :589-627 (gold pass).  trie_table: (trie_nodes, target_vocab_size + 1) child table from aocr_trie_load /
+ * aocr_trie_from_words (column = 1-based vocabulary id, -1 = no child, node 0 = the start symbol), or NULL for an
+ * unconstrained search.  beam_size is clipped to the vocabulary (model.lua:229); beam_size 1 without a trie equals
+ * aocr_decode_greedy.  Outputs as aocr_decode_greedy (pred_scores = score of the best beam). */
+int aocr_decode_beam(aocr_handle* h, const float* images, int b, int W,
+                     const int32_t* targets, const int32_t* targets_eval, int T,
+                     int beam_size, const int32_t* trie_table, int32_t trie_nodes,
+                     int32_t* labels, double* pred_scores, double* gold_scores,
+                     double* loss_sum, int32_t* num_correct);
+/* loadDictionary(dictionary_path, allow_digit_prefix) — src/utils/utils.lua:177-218: one word per line over [0-9a-z];
+ * every word ends in an EOS child; allow_digit_prefix lets the root loop on EOS and digits.  The table is malloc'ed by
+ * the library and released with aocr_trie_free.  aocr_trie_from_words takes the words '\n'-separated in memory. */
+int aocr_trie_load(const char* path, int allow_digit_prefix, int32_t** table, int32_t* num_nodes);
+int aocr_trie_from_words(const char* words, int allow_digit_prefix, int32_t** table, int32_t* num_nodes);
+void aocr_trie_free(int32_t* table);
+
 /* parity tap: log-probs of the last call. which=0: train (T,b,V); 1: greedy pass (L,b,V) after the
  * sticky-PAD edit; 2: gold pass (L,b,V). */
 int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n);

@@ -15,3 +15,4 @@ checks of its own hand-written backward and (ii) the committed fixtures under
 from .layout import Config, GROUPS, param_specs, group_sizes, init_params, init_bn_stats, unflatten, flatten  # noqa: F401
 from .model import Oracle  # noqa: F401
 from .synth import make_batch, str2numlist, numlist2str  # noqa: F401
+from .trie import load_dictionary, flatten as flatten_trie  # noqa: F401

@@ -323,11 +323,22 @@ class Oracle:
             d["a"] = d["a"] + dz @ self.P["proj"]["W"]                # model.lua:648-649
             d = self.dec_step_bwd(dcaches[t], ctx, d, G, D_ctx)
         dsrc = self.enc_backward(src, ecache, D_ctx, d["c1"], d["h1"], G)
+        self.last_dsrc = dsrc.numpy().copy()                          # (S,B,512): the gradient handed to the CNN
+        self._last_ccache = ccache
+        self._last_cnn_out = cnn_out.detach()                         # (B,S,512)
         self.cnn_backward(dsrc.transpose(0, 1), ccache, G)            # model.lua:692
         out = (loss * Bn, self._flat_grads(G), torch.stack(logps).numpy())
         if return_named:
             return out + (G,)
         return out
+
+    def cnn_grads_given(self, dsrc):
+        """CNN parameter gradients (flat, group layout) for a GIVEN gradient at the CNN output, dsrc (S,B,512), through the
+        cache of the last forward_backward.  Lets a test check the CNN backward in isolation from the rounding of what
+        feeds it (model.lua:692)."""
+        G = self.zero_grads()
+        self.cnn_backward(_t(dsrc, self.dtype).transpose(0, 1), self._last_ccache, G)
+        return self._flat_grads(G)["cnn"]
 
     # ------------------------------------------------------------------ optimiser (optim_sgd.lua:40-95)
     def sgd_update(self, grads, lr, clip=5.0):
@@ -406,6 +417,117 @@ class Oracle:
         return {"labels": labels.numpy().astype(np.int32), "pred_scores": score.numpy(),
                 "gold_scores": gold.numpy(), "loss_sum": loss * B, "num_correct": num_correct,
                 "gaps": gaps.numpy(), "greedy_logp": np.stack(greedy_logp), "gold_logp": np.stack(gold_logp)}
+
+    # ------------------------------------------------------------------ beam search (model.lua:321-536,570-588)
+    def decode_beam(self, images, targets, targets_eval, beam_size, trie=None):
+        """forward_only step with beam_size > 1 and / or a dictionary trie (nested dicts, oracle/trie.py).
+        Follows the reference step by step: first step on the B un-replicated rows (model.lua:376-445), then beam*B rows
+        with sticky PAD (:448-449), top-k over beam*V totals (:451-459) or the sorted walk over trie-valid continuations
+        (:460-514), parent re-gather of every state (:516-534), backtrack from the best final beam (:573-585), then the
+        teacher-forced gold pass (:589-627).  Row order of the replicated state is the reference's b*beam + k.
+        Q4 (t = 1 parent computed from the un-decremented id) only matters for beam 1 (every replica of an image holds
+        the same state at t = 1); parent = 1 is used.  `tie_gaps` (B, L): margin between the last continuation taken
+        and the best one left out; `final_gap` (B): margin between the best and the second-best final beam."""
+        cfg = self.cfg
+        L, V = cfg.max_decoder_l, cfg.target_vocab_size
+        K = min(int(beam_size), V)                                    # model.lua:229
+        img = _t(images, self.dtype)
+        B = img.shape[0]
+        tg = np.ones((B, L), np.int64)
+        te = np.ones((B, L), np.int64)
+        T0 = np.asarray(targets).shape[1]
+        assert T0 <= L, f"max_decoder_l ({L}) < target_l ({T0})!"
+        tg[:, :T0] = np.asarray(targets)
+        te[:, :T0] = np.asarray(targets_eval)
+        tgt, tev = torch.as_tensor(tg).T, torch.as_tensor(te).T
+        NEG = float("-inf")
+        with torch.no_grad():
+            cnn_out, _ = self.cnn_forward(img, train=False)
+            ctx, _, finals = self.enc_forward(cnn_out.transpose(0, 1))
+            st = self.dec_init(finals, B)
+            beam_scores = torch.zeros(B, K, dtype=self.dtype)
+            cur_hist, par_hist = [], []
+            tie_gaps = torch.full((B, L), float("inf"), dtype=self.dtype)
+            locs = [None] * B                                           # trie node per (b, beam)
+            ctxK = ctx[:, None].expand(B, K, *ctx.shape[1:]).reshape(B * K, *ctx.shape[1:])
+            beam_input = tgt[0].clone()
+            for t in range(L):
+                st, _ = self.dec_step(beam_input, ctx if t == 0 else ctxK, st)
+                logp = self.generator(st["a"]).clone()
+                if t == 0:
+                    total = logp                                       # (B, V)
+                    nb = 1
+                else:
+                    stick = (beam_input == 1) | (beam_input == 3)      # model.lua:448-449
+                    logp[stick, 0] = 0.0
+                    total = (logp.view(B, K, V) + beam_scores[:, :, None]).reshape(B, K * V)
+                    nb = K
+                raw = torch.zeros(B, K, dtype=torch.long)
+                new_scores = torch.zeros(B, K, dtype=self.dtype)
+                if trie is None:
+                    vals, idx = total.topk(min(K + 1, total.shape[1]), dim=1)      # sorted; Torch's topk order is unspecified
+                    raw, new_scores = idx[:, :K].clone(), vals[:, :K].clone()
+                    if vals.shape[1] > K:
+                        tie_gaps[:, t] = vals[:, K - 1] - vals[:, K]
+                else:
+                    order = torch.argsort(total, dim=1, descending=True)
+                    for b in range(B):
+                        picked = []
+                        first_rejected = None
+                        for j in order[b].tolist():
+                            vid, beam = j % V + 1, j // V
+                            node = trie if t == 0 else locs[b][beam]
+                            ok = (vid in node) if t == 0 else (vid == 1 or vid in node)   # model.lua:417,472
+                            if ok and len(picked) < K:
+                                picked.append(j)
+                            elif ok and first_rejected is None:
+                                first_rejected = j
+                            if len(picked) == K and first_rejected is not None:
+                                break
+                        assert picked, "dictionary admits no first character"
+                        if first_rejected is not None and len(picked) == K:
+                            tie_gaps[b, t] = total[b, picked[-1]] - total[b, first_rejected]
+                        while len(picked) < K:                          # model.lua:424-436: pad with the best valid one
+                            picked.append(picked[0])
+                        raw[b] = torch.as_tensor(picked)
+                        new_scores[b] = total[b, raw[b]]
+                        nl = []
+                        for j in picked:                                 # model.lua:437-442,498-511
+                            vid, beam = j % V + 1, j // V
+                            node = trie if t == 0 else locs[b][beam]
+                            nl.append(node if (t > 0 and vid == 1) else node[vid])
+                        locs[b] = nl
+                beam_scores = new_scores
+                cur = raw % V + 1                                      # model.lua:455-458
+                par = raw // V if t > 0 else torch.zeros_like(raw)
+                cur_hist.append(cur.clone())
+                par_hist.append(par.clone())
+                rows = (par + torch.arange(B)[:, None] * nb).reshape(-1)   # model.lua:522-531
+                st = {k: v[rows] for k, v in st.items()}
+                beam_input = cur.reshape(-1)
+            srt = beam_scores.sort(dim=1, descending=True)
+            scores, idx = srt.values[:, 0], srt.indices[:, 0]          # model.lua:574-576 (first maximum)
+            final_gap = srt.values[:, 0] - srt.values[:, 1] if K > 1 else torch.full((B,), float("inf"), dtype=self.dtype)
+            labels = torch.ones(B, L, dtype=torch.long)
+            ar = torch.arange(B)
+            for t in range(L - 1, -1, -1):                             # model.lua:577-585
+                labels[:, t] = cur_hist[t][ar, idx]
+                idx = par_hist[t][ar, idx]
+            num_correct = 0
+            for b in range(B):
+                num_correct += int(_cut(labels[b].tolist()) == _cut(te[b].tolist()))
+            st = self.dec_init(finals, B)                               # gold pass, model.lua:589-627
+            loss = 0.0
+            gold = torch.zeros(B, dtype=self.dtype)
+            for t in range(L):
+                st, _ = self.dec_step(tgt[t], ctx, st)
+                logp = self.generator(st["a"])
+                y = tev[t]
+                loss += float(self.nll(logp, y)) / B
+                w = (y != 1).to(self.dtype)
+                gold = gold + w * logp.gather(1, (y - 1)[:, None])[:, 0]
+        return {"labels": labels.numpy().astype(np.int32), "pred_scores": scores.numpy(), "gold_scores": gold.numpy(),
+                "loss_sum": loss * B, "num_correct": num_correct, "tie_gaps": tie_gaps.numpy(), "final_gap": final_gap.numpy()}
 
 
 def _cut(ids):

@@ -151,3 +151,41 @@ def test_bn_running_stats_update():
     orc.forward_backward(batch["images"], batch["targets"], batch["targets_eval"])
     rm, rv = orc.bn["bn3"]
     assert float(rm.abs().max()) > 0 and float((rv - 1).abs().max()) > 0
+
+
+# ---- beam search / dictionary trie (model.lua:380-387,405-536,573-585; utils.lua:177-218)
+def test_beam_one_is_greedy_and_wider_beams_never_score_lower():
+    from oracle import Config, Oracle, init_params, init_bn_stats, make_batch
+    cfg = Config(batch_size=3, max_encoder_l=30, max_decoder_l=7)
+    b = make_batch(3, 100, 5, seed=21)
+    o = Oracle(cfg, init_params(cfg), init_bn_stats(cfg))
+    g = o.decode_greedy(b["images"], b["targets"], b["targets_eval"])
+    r1 = o.decode_beam(b["images"], b["targets"], b["targets_eval"], 1)
+    assert np.array_equal(g["labels"], r1["labels"]) and np.allclose(g["pred_scores"], r1["pred_scores"], atol=1e-12)
+    assert r1["num_correct"] == g["num_correct"] and abs(r1["loss_sum"] - g["loss_sum"]) < 1e-9
+    prev = r1["pred_scores"]
+    for k in (2, 4):
+        rk = o.decode_beam(b["images"], b["targets"], b["targets_eval"], k)
+        assert np.all(rk["pred_scores"] >= prev - 1e-9)        # the best hypothesis of a wider beam is at least as good
+        prev = rk["pred_scores"]
+
+
+def test_trie_decode_emits_dictionary_words_and_c_trie_matches():
+    from oracle import Config, Oracle, init_params, init_bn_stats, make_batch, load_dictionary, flatten_trie
+    from oracle.synth import numlist2str
+    words = ["hello", "help", "h3", "abc", "a", "zz9", "0", "42"]
+    cfg = Config(batch_size=3, max_encoder_l=30, max_decoder_l=8)
+    b = make_batch(3, 100, 5, seed=22)
+    o = Oracle(cfg, init_params(cfg), init_bn_stats(cfg))
+    r = o.decode_beam(b["images"], b["targets"], b["targets_eval"], 3, trie=load_dictionary(words))
+    for row in r["labels"]:
+        ids = []
+        for v in row.tolist():
+            if v == 3:
+                break
+            ids.append(v)
+        assert numlist2str(ids) in words
+    # the library's loadDictionary restatement (host code, no GPU needed) numbers the same trie the same way
+    from aocr import Trie
+    for adp in (False, True):
+        assert np.array_equal(Trie(words=words, allow_digit_prefix=adp).numpy(), flatten_trie(load_dictionary(words, adp)))

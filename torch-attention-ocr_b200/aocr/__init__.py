@@ -7,7 +7,7 @@ reference maintainer would drop in lives in `../lua/`.
 
 There is NO CPU fallback: importing this package without a built libaocr.so raises.
 """
-from .capi import Lib, AocrError, AocrConfig, GROUPS, lib_path  # noqa: F401
+from .capi import Lib, AocrError, AocrConfig, GROUPS, Trie, lib_path  # noqa: F401
 from .model import Model  # noqa: F401
 from .optim import sgd_list  # noqa: F401
 from .data import SyntheticDataGen, str2numlist, numlist2str  # noqa: F401

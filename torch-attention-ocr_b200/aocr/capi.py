@@ -50,6 +50,12 @@ _SYMBOLS = {
     "aocr_decode_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
                                      C.POINTER(C.c_int32)]),
+    "aocr_decode_beam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int32)]),
+    "aocr_trie_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]),
+    "aocr_trie_from_words": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]),
+    "aocr_trie_free": (None, [C.POINTER(C.c_int32)]),
     "aocr_get_logprobs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "aocr_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "aocr_stage_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
@@ -134,6 +140,36 @@ class Lib:
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class Trie:
+    """Dictionary trie of the constrained decode: loadDictionary (src/utils/utils.lua:177-218) as the flat child table the
+    library consumes.  Trie(path=...) reads one word per line; Trie(words=[...]) takes them from memory."""
+
+    def __init__(self, path=None, words=None, allow_digit_prefix=False):
+        lib = Lib.get()
+        self.lib = lib
+        self.table = C.POINTER(C.c_int32)()
+        n = C.c_int32()
+        if path is not None:
+            rc = lib.dll.aocr_trie_load(os.fsencode(path), int(bool(allow_digit_prefix)), C.byref(self.table), C.byref(n))
+        else:
+            rc = lib.dll.aocr_trie_from_words("\n".join(words).encode(), int(bool(allow_digit_prefix)), C.byref(self.table),
+                                              C.byref(n))
+        if rc != 0:
+            raise AocrError(rc, "dictionary could not be read" if path else "bad dictionary word")
+        self.num_nodes = n.value
+
+    def numpy(self, V=39):
+        return np.ctypeslib.as_array(self.table, shape=(self.num_nodes, V + 1)).copy()
+
+    def __del__(self):
+        try:
+            if self.table:
+                self.lib.dll.aocr_trie_free(self.table)
+                self.table = C.POINTER(C.c_int32)()
+        except Exception:
+            pass
 
 
 class Handle:
@@ -243,6 +279,20 @@ class Handle:
         loss, nc = C.c_double(), C.c_int32()
         self._ck(self.lib.dll.aocr_decode_greedy(self.h, _ptr(img), b, W, _ptr(tg), _ptr(te), T, _ptr(labels),
                                                  _ptr(pred), _ptr(gold), C.byref(loss), C.byref(nc)))
+        return {"labels": labels, "pred_scores": pred, "gold_scores": gold, "loss_sum": loss.value,
+                "num_correct": nc.value}
+
+    def decode_beam(self, images, targets, targets_eval, beam_size, trie=None):
+        """beam search, optionally constrained to a dictionary (`trie`: a Trie)"""
+        img, tg, te, b, W, T = self._batch(images, targets, targets_eval)
+        Ld = self.cfg.max_decoder_l
+        labels = np.empty((b, Ld), np.int32)
+        pred, gold = np.empty(b, np.float64), np.empty(b, np.float64)
+        loss, nc = C.c_double(), C.c_int32()
+        self._ck(self.lib.dll.aocr_decode_beam(self.h, _ptr(img), b, W, _ptr(tg), _ptr(te), T, int(beam_size),
+                                               C.cast(trie.table, C.c_void_p) if trie is not None else None,
+                                               trie.num_nodes if trie is not None else 0, _ptr(labels), _ptr(pred),
+                                               _ptr(gold), C.byref(loss), C.byref(nc)))
         return {"labels": labels, "pred_scores": pred, "gold_scores": gold, "loss_sum": loss.value,
                 "num_correct": nc.value}
 

@@ -102,9 +102,7 @@ class Model:
     def step(self, batch, forward_only, beam_size=1, trie=None, use_lua_optim=False):
         images, targets, targets_eval, num_nonzeros = batch[0], batch[1], batch[2], batch[3]
         if forward_only:
-            beam_size = min(beam_size or 1, self.config["target_vocab_size"])
-            if beam_size != 1 or trie is not None:
-                raise NotImplementedError("beam search / dictionary-constrained decode are out of scope (SURVEY §8f)")
+            beam_size = min(beam_size or 1, self.config["target_vocab_size"])        # model.lua:228-229
         try:
             if not forward_only:
                 if use_lua_optim:   # unmodified optim.sgd_list semantics over the proxies (optim_sgd.lua)
@@ -115,7 +113,10 @@ class Model:
                     return loss[0] * images.shape[0], stats                      # model.lua:700-701
                 loss_sum = self.handle.train_step(images, targets, targets_eval, self.optim_state["learningRate"])
                 return loss_sum, [num_nonzeros, 0.0]
-            out = self.handle.decode_greedy(images, targets, targets_eval)
+            if beam_size == 1 and trie is None:
+                out = self.handle.decode_greedy(images, targets, targets_eval)
+            else:   # beam search / dictionary-constrained decode (model.lua:380-387,405-445,460-514); trie: aocr.Trie
+                out = self.handle.decode_beam(images, targets, targets_eval, beam_size, trie)
         except AocrError as e:
             if e.code == -1:
                 raise AssertionError(e.msg) from e   # the reference raises Lua asserts (model.lua:264,287)
@@ -150,11 +151,13 @@ class Model:
     def save(self, model_path):
         p = self.get_parameters()
         bn = [self.handle.get_bn_stats(i) for i in range(3)]
-        np.savez(model_path if model_path.endswith(".npz") else model_path + ".npz",
+        path = model_path if model_path.endswith(".npz") else model_path + ".npz"
+        np.savez(path,
                  **{"param_" + g: p[g] for g in GROUPS},
                  **{"bn%d_mean" % i: bn[i][0] for i in range(3)}, **{"bn%d_var" % i: bn[i][1] for i in range(3)},
                  config=json.dumps(self.config), global_step=self.global_step,
                  optim_state=json.dumps(self.optim_state))
+        return path
 
     # model:load(model_path, config) — model.lua:45-80
     def load(self, model_path, config=None):

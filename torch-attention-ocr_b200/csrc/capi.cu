@@ -125,6 +125,16 @@ int aocr_decode_greedy(aocr_handle* h, const float* images, int b, int W, const 
   AOCR_API_END(h)
 }
 
+int aocr_decode_beam(aocr_handle* h, const float* images, int b, int W, const int32_t* targets, const int32_t* targets_eval,
+                     int T, int beam_size, const int32_t* trie_table, int32_t trie_nodes, int32_t* labels,
+                     double* pred_scores, double* gold_scores, double* loss_sum, int32_t* num_correct) {
+  AOCR_API_BEGIN(h)
+  h->eng->stage_batch(images, b, W, targets, targets_eval, T);
+  h->eng->decode_beam_enqueue(beam_size, trie_table, trie_nodes);
+  h->eng->decode_collect(labels, pred_scores, gold_scores, loss_sum, num_correct);
+  AOCR_API_END(h)
+}
+
 int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n) {
   AOCR_API_BEGIN(h) h->eng->get_logprobs(which, out, n); AOCR_API_END(h)
 }

@@ -5,6 +5,11 @@
 #pragma once
 #include "kernels_dec.h"
 
+// AOCR_BT(i): optional phase time stamps inside the bodies (persist.cu defines it under AOCR_PERSIST_TRACE builds)
+#ifndef AOCR_BT
+#define AOCR_BT(i)
+#endif
+
 namespace aocr {
 namespace decb {
 
@@ -84,28 +89,46 @@ __device__ __forceinline__ void cell_fwd_tc_body(CellFwdTc p, int bid, int nblk,
 __device__ __forceinline__ void cell_bwd_tc_body(CellBwdTc p, int bid, int nblk, float* sm) {
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
-  for (int64_t e = (int64_t)bid * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
-    const int u = (int)(e % H);
-    const int64_t b = e / H;
-    float dh = 0.f;
-    if (p.dh_a.p) dh += part_load(p.dh_a, b, u);
-    if (p.dh_b.p) dh += part_load(p.dh_b, b, u);
-    if (p.dh_c.p) dh += part_load(p.dh_c, b, u);
-    const float* a = p.acts + b * 4 * H + u;
-    const float i_ = a[0], f_ = a[H], o_ = a[2 * H], g_ = a[3 * H];
-    const float tc = tanhf(p.c_new[e]);
-    const float dc = p.dc[e] + dh * o_ * (1.f - tc * tc);
-    const float d0 = dc * g_ * i_ * (1.f - i_);
-    const float d1 = dc * p.c_prev[e] * f_ * (1.f - f_);
-    const float d2 = dh * tc * o_ * (1.f - o_);
-    const float d3 = dc * i_ * (1.f - g_ * g_);
-    float* dg = p.dG + b * 4 * H + u;
-    dg[0] = d0; dg[H] = d1; dg[2 * H] = d2; dg[3 * H] = d3;
-    pack_store(p.pk, b, u, d0);
-    pack_store(p.pk, b, H + u, d1);
-    pack_store(p.pk, b, 2 * H + u, d2);
-    pack_store(p.pk, b, 3 * H + u, d3);
-    p.dc[e] = dc * f_;
+  const int64_t stride = (int64_t)nblk * blockDim.x;
+  constexpr int U = 2;      // elements per thread and pass: their loads are issued together (one L2 round trip, not U)
+  for (int64_t e0 = (int64_t)bid * blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
+    float dh[U], ai[U], af[U], ao[U], ag[U], cn[U], cp[U], dcv[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int64_t e = e0 + k * stride;
+      if (e >= total) continue;
+      const int u = (int)(e % H);
+      const int64_t b = e / H;
+      float d = 0.f;
+      if (p.dh_a.p) d += part_load(p.dh_a, b, u);
+      if (p.dh_b.p) d += part_load(p.dh_b, b, u);
+      if (p.dh_c.p) d += part_load(p.dh_c, b, u);
+      dh[k] = d;
+      const float* a = p.acts + b * 4 * H + u;
+      ai[k] = __ldcg(a); af[k] = __ldcg(a + H); ao[k] = __ldcg(a + 2 * H); ag[k] = __ldcg(a + 3 * H);
+      cn[k] = __ldcg(p.c_new + e); cp[k] = __ldcg(p.c_prev + e); dcv[k] = __ldcg(p.dc + e);
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int64_t e = e0 + k * stride;
+      if (e >= total) continue;
+      const int u = (int)(e % H);
+      const int64_t b = e / H;
+      const float i_ = ai[k], f_ = af[k], o_ = ao[k], g_ = ag[k];
+      const float tc = tanhf(cn[k]);
+      const float dc = dcv[k] + dh[k] * o_ * (1.f - tc * tc);
+      const float d0 = dc * g_ * i_ * (1.f - i_);
+      const float d1 = dc * cp[k] * f_ * (1.f - f_);
+      const float d2 = dh[k] * tc * o_ * (1.f - o_);
+      const float d3 = dc * i_ * (1.f - g_ * g_);
+      float* dg = p.dG + b * 4 * H + u;
+      dg[0] = d0; dg[H] = d1; dg[2 * H] = d2; dg[3 * H] = d3;
+      pack_store(p.pk, b, u, d0);
+      pack_store(p.pk, b, H + u, d1);
+      pack_store(p.pk, b, 2 * H + u, d2);
+      pack_store(p.pk, b, 3 * H + u, d3);
+      p.dc[e] = dc * f_;
+    }
   }
 }
 
@@ -126,6 +149,17 @@ __device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, floa
   const float* cb = p.ctx + (int64_t)bsrc * S * H;
   const float* wb = p.ctxwc + (int64_t)bsrc * S * H;
   float* qs = accs + ATT_WARPS * H;               // the summed query, shared by the 8 warps
+  // the first source row of this warp does not depend on the query: its loads are issued before the partial sums and
+  // the barrier below, so that L2 round trip overlaps them
+  float4 row[ATT_MAXV], vrow[ATT_MAXV];
+  if (warp < S) {
+#pragma unroll
+    for (int i = 0; i < ATT_MAXV; i++)
+      if (i < nv) {
+        row[i] = __ldcg(reinterpret_cast<const float4*>(cb + (int64_t)warp * H + lane * 4 + 128 * i));
+        vrow[i] = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)warp * H + lane * 4 + 128 * i));
+      }
+  }
   // split-K partials of [q | v] are summed ONCE per CTA (4 consecutive columns per thread), not once per warp
   const int e4 = threadIdx.x * 4;
   float4 vpre = make_float4(0.f, 0.f, 0.f, 0.f);  // W_c2 h2 for the 4 outputs this thread finishes
@@ -144,13 +178,14 @@ __device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, floa
   }
   float m = -INFINITY, l = 0.f;
   for (int s = warp; s < S; s += ATT_WARPS) {
-    float4 row[ATT_MAXV], vrow[ATT_MAXV];
+    if (s != warp) {
 #pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++)
-      if (i < nv) {
-        row[i] = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
-        vrow[i] = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)s * H + lane * 4 + 128 * i));
-      }
+      for (int i = 0; i < ATT_MAXV; i++)
+        if (i < nv) {
+          row[i] = __ldcg(reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i));
+          vrow[i] = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)s * H + lane * 4 + 128 * i));
+        }
+    }
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < ATT_MAXV; i++)
@@ -218,6 +253,18 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
   const float* wb = p.ctxwc + (int64_t)b * S * H;
   const float* alpha = p.alpha + (int64_t)b * S;
   float* gs = accs + ATT_WARPS * H;               // du, shared by the 8 warps
+  // this warp's first ctx*W_c1^T row and first ctx row do not depend on du: loaded up front (one L2 round trip each,
+  // overlapped with the phases in front of their use)
+  float4 wrow[ATT_MAXV], crow[ATT_MAXV];
+  if (warp < S) {
+#pragma unroll
+    for (int i = 0; i < ATT_MAXV; i++)
+      if (i < nv) {
+        wrow[i] = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)warp * H + lane * 4 + 128 * i));
+        crow[i] = __ldcg(reinterpret_cast<const float4*>(cb + (int64_t)warp * H + lane * 4 + 128 * i));
+      }
+  }
+  AOCR_BT(0);
   const int e4 = threadIdx.x * 4;
   if (e4 < H) {   // du once per CTA: kept for the time-batched weight gradients + first half of the next GEMM's operand
     const int64_t e = (int64_t)b * H + e4;
@@ -233,6 +280,7 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
     pack_store4(p.pk, b, e4, g);
   }
   __syncthreads();
+  AOCR_BT(1);
   float4 gv[ATT_MAXV];
 #pragma unroll
   for (int i = 0; i < ATT_MAXV; i++)
@@ -242,7 +290,7 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
 #pragma unroll
     for (int i = 0; i < ATT_MAXV; i++) {
       if (i < nv) {
-        const float4 r = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)s * H + lane * 4 + 128 * i));
+        const float4 r = s == warp ? wrow[i] : __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)s * H + lane * 4 + 128 * i));
         dot += r.x * gv[i].x + r.y * gv[i].y + r.z * gv[i].z + r.w * gv[i].w;
       }
     }
@@ -250,6 +298,7 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
     if (lane == 0) das[s] = dot;
   }
   __syncthreads();
+  AOCR_BT(2);
   if (warp == 0) {
     float s_ = 0.f;
     for (int s = lane; s < S; s += 32) s_ += alpha[s] * das[s];
@@ -257,6 +306,7 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
     if (lane == 0) red[0] = s_;
   }
   __syncthreads();
+  AOCR_BT(3);
   const float tot = red[0];
   for (int s = threadIdx.x; s < S; s += blockDim.x) p.de[(int64_t)b * S + s] = alpha[s] * (das[s] - tot);
   float4 acc[ATT_MAXV];
@@ -267,7 +317,7 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
 #pragma unroll
     for (int i = 0; i < ATT_MAXV; i++) {
       if (i < nv) {
-        const float4 r = *reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i);
+        const float4 r = s == warp ? crow[i] : __ldcg(reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i));
         acc[i].x = fmaf(w, r.x, acc[i].x); acc[i].y = fmaf(w, r.y, acc[i].y);
         acc[i].z = fmaf(w, r.z, acc[i].z); acc[i].w = fmaf(w, r.w, acc[i].w);
       }
@@ -277,6 +327,7 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
   for (int i = 0; i < ATT_MAXV; i++)
     if (i < nv) *reinterpret_cast<float4*>(accs + warp * H + lane * 4 + 128 * i) = acc[i];
   __syncthreads();
+  AOCR_BT(4);
   if (e4 < H) {
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -287,6 +338,7 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
     *reinterpret_cast<float4*>(p.dq + (int64_t)b * H + e4) = u;
     pack_store4(p.pk, b, H + e4, u);
   }
+  AOCR_BT(5);
 }
 
 // encoder cell, both directions (grid-stride over dir x batch x unit); slot convention of engine.cu
@@ -320,30 +372,55 @@ __device__ __forceinline__ void enc_cell_fwd_tc_body(EncCellFwdTc p, int bid, in
 __device__ __forceinline__ void enc_cell_bwd_tc_body(EncCellBwdTc p, int bid, int nblk, float* sm) {
   const int He = p.He, B = p.B, S = p.S;
   const int64_t total = (int64_t)(p.d_only < 0 ? 2 : 1) * B * He;
-  for (int64_t e = (int64_t)bid * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
-    const int unit = (int)(e % He);
-    const int64_t b = (e / He) % B;
-    const int d = p.d_only < 0 ? (int)(e / ((int64_t)He * B)) : p.d_only;
-    const int t = d == 0 ? S - 1 - p.step : p.step;
-    const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
-    const float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
-    const float i_ = a[0], f_ = a[He], o_ = a[2 * He], g_ = a[3 * He];
-    const float cp = p.Cst[((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit];
-    const float tc = tanhf(p.Cst[((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit]);
-    const float dh = part_load(p.dh[d], b, unit) + p.Dctx[((int64_t)b * S + t) * (2 * He) + d * He + unit];
-    const int64_t ce = ((int64_t)d * B + b) * He + unit;
-    const float dc = p.dc[ce] + dh * o_ * (1.f - tc * tc);
-    const float d0 = dc * g_ * i_ * (1.f - i_);
-    const float d1 = dc * cp * f_ * (1.f - f_);
-    const float d2 = dh * tc * o_ * (1.f - o_);
-    const float d3 = dc * i_ * (1.f - g_ * g_);
-    float* dg = p.dG + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
-    dg[0] = d0; dg[He] = d1; dg[2 * He] = d2; dg[3 * He] = d3;
-    pack_store(p.dgp[d], b, unit, d0);
-    pack_store(p.dgp[d], b, He + unit, d1);
-    pack_store(p.dgp[d], b, 2 * He + unit, d2);
-    pack_store(p.dgp[d], b, 3 * He + unit, d3);
-    p.dc[ce] = dc * f_;
+  const int64_t stride = (int64_t)nblk * blockDim.x;
+  constexpr int U = 4;      // elements per thread and pass, loads of all U in front (32 CTAs serve 64 x 512 elements)
+  AOCR_BT(8);
+  for (int64_t e0 = (int64_t)bid * blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
+    float dhv[U], ai[U], af[U], ao[U], ag[U], cpv[U], cnv[U], dcv[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int64_t e = e0 + k * stride;
+      if (e >= total) continue;
+      const int unit = (int)(e % He);
+      const int64_t b = (e / He) % B;
+      const int d = p.d_only < 0 ? (int)(e / ((int64_t)He * B)) : p.d_only;
+      const int t = d == 0 ? S - 1 - p.step : p.step;
+      const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
+      const float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
+      ai[k] = __ldcg(a); af[k] = __ldcg(a + He); ao[k] = __ldcg(a + 2 * He); ag[k] = __ldcg(a + 3 * He);
+      cpv[k] = __ldcg(p.Cst + ((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit);
+      cnv[k] = __ldcg(p.Cst + ((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit);
+      dhv[k] = part_load(p.dh[d], b, unit) + __ldcg(p.Dctx + ((int64_t)b * S + t) * (2 * He) + d * He + unit);
+      dcv[k] = __ldcg(p.dc + ((int64_t)d * B + b) * He + unit);
+    }
+    if (dhv[0] == 12345.678f) AOCR_BT(15);     // (forces the loads to complete before the next stamp)
+    AOCR_BT(9);
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int64_t e = e0 + k * stride;
+      if (e >= total) continue;
+      const int unit = (int)(e % He);
+      const int64_t b = (e / He) % B;
+      const int d = p.d_only < 0 ? (int)(e / ((int64_t)He * B)) : p.d_only;
+      const int t = d == 0 ? S - 1 - p.step : p.step;
+      const float i_ = ai[k], f_ = af[k], o_ = ao[k], g_ = ag[k];
+      const float tc = tanhf(cnv[k]);
+      const float dh = dhv[k];
+      const int64_t ce = ((int64_t)d * B + b) * He + unit;
+      const float dc = dcv[k] + dh * o_ * (1.f - tc * tc);
+      const float d0 = dc * g_ * i_ * (1.f - i_);
+      const float d1 = dc * cpv[k] * f_ * (1.f - f_);
+      const float d2 = dh * tc * o_ * (1.f - o_);
+      const float d3 = dc * i_ * (1.f - g_ * g_);
+      float* dg = p.dG + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
+      dg[0] = d0; dg[He] = d1; dg[2 * He] = d2; dg[3 * He] = d3;
+      pack_store(p.dgp[d], b, unit, d0);
+      pack_store(p.dgp[d], b, He + unit, d1);
+      pack_store(p.dgp[d], b, 2 * He + unit, d2);
+      pack_store(p.dgp[d], b, 3 * He + unit, d3);
+      p.dc[ce] = dc * f_;
+    }
+    AOCR_BT(10);
   }
 }
 

@@ -133,22 +133,21 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   }
   if (c.batch_size > 256 || c.gemm_mode == 2) persist_on_ = false;   // one UMMA N tile (<= 256 rows) per command
   AOCR_CUDA(cudaStreamCreateWithFlags(&ctx_.st, cudaStreamNonBlocking));
-  // Launch mode of the executor.  Preferred: cooperative (co-residency of the spinning CTAs is checked by the driver) +
-  // clusters.  A launch interceptor may refuse that combination (Nsight Compute: LaunchFailed): then clusters without
-  // the cooperative attribute (the grids are <= 128 CTAs of one CTA per SM, co-resident on this part - checked above
-  // through the occupancy query), and as the last resort cooperative without clusters (no fused GEMM -> cell commands).
-  // Decided here, before any weight plane is built (their row order depends on it).
+  // Launch mode of the executor.  With thread-block clusters the launch does NOT carry the cooperative attribute:
+  // Nsight Compute rejects cooperative launches whose kernels use cluster barriers / distributed shared memory
+  // (LaunchFailed; measured: cooperative + cluster attribute alone is accepted, the fused commands are not), and the
+  // attribute only makes the driver check what is checked above - that the grid (<= 128 CTAs, one per SM) is
+  // co-resident as clusters.  Kernels of the other lanes that occupy SMs at launch time always finish, so the spinning
+  // CTAs of a partially resident grid cannot deadlock.  Without clusters the launch stays cooperative.
+  // AOCR_COOP=1 forces the attribute.  Decided here, before any weight plane is built (their row order depends on it).
+  ctx_.persist_coop = cluster_ <= 1;
   if (const char* e = getenv("AOCR_COOP")) ctx_.persist_coop = atoi(e) != 0;
-  if (persist_on_ && cluster_ > 1 && ctx_.persist_coop && !getenv("AOCR_NO_PROBE")) {
-    if (persist_probe(ctx_.st, 128, cluster_, true) != cudaSuccess) {
-      if (persist_probe(ctx_.st, 128, cluster_, false) == cudaSuccess) {
-        ctx_.persist_coop = false;
-        fprintf(stderr, "[aocr] cooperative + cluster launch refused: executor launches with clusters, without the cooperative attribute\n");
-      } else {
-        cluster_ = 1;
-        fprintf(stderr, "[aocr] cluster launches refused: executor runs without clusters\n");
-        AOCR_CHECK(persist_probe(ctx_.st, 128, 1, true) == cudaSuccess, "the persistent executor cannot be launched on this device");
-      }
+  if (persist_on_ && cluster_ > 1 && !getenv("AOCR_NO_PROBE")) {
+    if (persist_probe(ctx_.st, 128, cluster_, ctx_.persist_coop) != cudaSuccess) {
+      cluster_ = 1;
+      ctx_.persist_coop = true;
+      fprintf(stderr, "[aocr] cluster launches refused: executor runs without clusters\n");
+      AOCR_CHECK(persist_probe(ctx_.st, 128, 1, true) == cudaSuccess, "the persistent executor cannot be launched on this device");
     }
   }
   AOCR_CUDA(cudaEventCreate(&ev0_));
@@ -281,6 +280,7 @@ Engine::~Engine() {
     if (lanes_on_ && lanes_[i].st) { cudaStreamSynchronize(lanes_[i].st); cudaStreamDestroy(lanes_[i].st); }
   for (int i = 0; i < 8; i++) if (lane_ev_[i]) cudaEventDestroy(lane_ev_[i]);
   for (void* p : allocs_) cudaFree(p);
+  if (d_trie_) cudaFree(d_trie_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
@@ -591,6 +591,18 @@ void Engine::cnn_forward(bool train) {
     }
   }
   taps_["cnn_out"] = {src, (int64_t)S_ * B * 512};
+  // per-layer taps: activations (NHWC; act7 = cnn_out, time-major) and the pooling choices (0..3 = dy*2+dx)
+  {
+    static const char* an[8] = {"", "act1", "act2", "act3", "act4", "act5", "act6", "act7"};
+    static const char* pn[8] = {"", "pidx1", "pidx2", "", "pidx4", "", "pidx6", ""};
+    const int64_t n_act[8] = {0, (int64_t)B * 16 * W1_ * 64, (int64_t)B * 8 * W2_ * 128, (int64_t)B * 8 * W2_ * 256,
+                              (int64_t)B * 4 * W2_ * 256, (int64_t)B * 4 * W2_ * 512, (int64_t)B * 2 * W2_ * 512,
+                              (int64_t)S_ * B * 512};
+    for (int l = 1; l <= 7; l++) {
+      taps_[an[l]] = {act[l], n_act[l]};
+      if (pidx[l]) taps_[pn[l]] = {pidx[l], n_act[l], true};
+    }
+  }
 }
 
 // CNN backward (model.lua:692)

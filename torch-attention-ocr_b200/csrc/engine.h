@@ -39,7 +39,7 @@ struct ParamLayout {
   int64_t wo, bo;
 };
 
-struct Tap { const float* ptr; int64_t n; };
+struct Tap { const void* ptr; int64_t n; bool bytes = false; };   // bytes: uint8 on the device, widened to float on read
 
 class Engine {
  public:
@@ -62,6 +62,7 @@ class Engine {
   void set_global_batch(int n) { AOCR_CHECK(n >= 0, "global batch must be >= 0"); cfg.global_batch = n; }
   int global_b() const { return cfg.global_batch > 0 ? cfg.global_batch : b_; }
   void decode_enqueue();
+  void decode_beam_enqueue(int beam, const int32_t* trie_host, int32_t trie_nodes);   // engine_beam.cu
   void decode_collect(int32_t* labels, double* pred, double* gold, double* loss_sum, int32_t* num_correct);
   void get_logprobs(int which, float* out, int64_t n);
   void debug_read(const char* name, float* out, int64_t n);
@@ -145,6 +146,11 @@ class Engine {
   struct StepTail { GenTc gen; GreedyTc sel; };
   const StepTail* tail_ = nullptr;   // set while recording a dual decode step: generator + selection ride on the attention command
   int dual_rows_ = 0;   // > 0 while the dual decode pass is recorded / initialised: the number of real batch rows
+  int ctx_row0_ = 0;    // first context row of the state rows (beam search works on chunks of the batch)
+  // beam search (engine_beam.cu)
+  uint8_t* beam_tmp_ = nullptr; float* beam_logp_ = nullptr; double* beam_scores_[2] = {}; int32_t* beam_tok_[2] = {};
+  int32_t *beam_parent_ = nullptr, *beam_loc_[2] = {}, *beam_hist_tok_ = nullptr, *beam_hist_par_ = nullptr;
+  int32_t* d_trie_ = nullptr; const int32_t* trie_src_ = nullptr; int32_t trie_nodes_ = 0;
   struct ProgKey { int kind, b, S, nsteps, variant; bool operator<(const ProgKey& o) const {
     return std::tie(kind, b, S, nsteps, variant) < std::tie(o.kind, o.b, o.S, o.nsteps, o.variant); } };
   std::map<ProgKey, PersistProgram> programs_;

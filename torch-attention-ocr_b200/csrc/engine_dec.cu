@@ -656,6 +656,12 @@ void Engine::debug_read(const char* name, float* out, int64_t n) {
   AOCR_CHECK(it != taps_.end(), std::string("unknown debug tap: ") + name);
   AOCR_CHECK(n == it->second.n, "debug tap length mismatch");
   AOCR_CUDA(cudaStreamSynchronize(ctx_.st));
+  if (it->second.bytes) {
+    std::vector<uint8_t> tmp((size_t)n);
+    AOCR_CUDA(cudaMemcpy(tmp.data(), it->second.ptr, (size_t)n, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; i++) out[i] = (float)tmp[i];
+    return;
+  }
   AOCR_CUDA(cudaMemcpy(out, it->second.ptr, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
 }
 

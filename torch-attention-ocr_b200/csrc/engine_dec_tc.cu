@@ -179,7 +179,7 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   // ---- [q ; v] = [W_a ; W_c2] h2, then scores / softmax / alpha-weighted ctxwc + v / tanh in one body
   TcOut g3 = emit_gemm(W3p, 2 * Hd, H2p, r0, 0, Hd, dec_ws[2]);
   AttnOutTc ao;
-  ao.ctx = ctx; ao.ctxwc = CtxWc; ao.g3 = part_in(g3, 2 * Hd);
+  ao.ctx = ctx + (int64_t)ctx_row0_ * S * Hd; ao.ctxwc = CtxWc + (int64_t)ctx_row0_ * S * Hd; ao.g3 = part_in(g3, 2 * Hd);
   ao.alpha = ALPHA + (int64_t)t * B * S; ao.q_out = Q + (int64_t)t * B * Hd; ao.a_out = A_all + (int64_t)t * B * Hd;
   ao.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; ao.ld_next = K1;
   ao.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();

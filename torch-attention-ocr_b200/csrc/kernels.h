@@ -125,6 +125,28 @@ struct SgdGroups { int64_t off[5]; int64_t n[5]; int nb[5]; };
 // lrclip: device pointer to {lr, clip} (the step size is data, not a launch parameter: a captured step is replayed with any lr)
 void sgd_groups(Ctx&, float* params, float* grads, const SgdGroups& G, double* partial, double* sumsq, const double* lrclip);
 void scale_vec(Ctx&, float* v, int64_t n, float s);
+
+// ---- beam search / dictionary-constrained decode (kernels_beam.cu; model.lua:380-387,405-536,573-585)
+// state rows are beam-major: row = k*Bc + b (k < K beams, b < Bc images of the chunk)
+struct BeamSelect {
+  const float* logp;          // (K*Bc, V) log-probs of this step (first step: only the rows of beam 0 are read)
+  const int32_t* tok;         // (K*Bc) input tokens of this step (sticky PAD test)
+  const double* scores;       // (Bc, K) beam scores so far
+  double* new_scores;         // (Bc, K)
+  int32_t* tok_out;           // (K*Bc) tokens chosen = inputs of the next step
+  int32_t* parent_row;        // (K*Bc) state row each new beam continues
+  int32_t* hist_tok; int32_t* hist_par;   // (L, Bc, K) history for the backtrack
+  const int32_t* trie;        // (nodes, V+1) child table or nullptr; column = 1-based vocabulary id, root = node 0
+  const int32_t* loc; int32_t* new_loc;   // (Bc, K) trie node per beam
+  int t, Bc, K, V;
+};
+void beam_select(Ctx&, const BeamSelect&);
+struct BeamGatherTensor { uint8_t* ptr; int64_t pitch_bytes, row_bytes, tmp_off; };
+struct BeamGather { BeamGatherTensor t[10]; int n; int rows; const int32_t* parent_row; uint8_t* tmp; };
+void beam_gather(Ctx&, const BeamGather&);
+struct BeamBacktrack { const double* scores; const int32_t* hist_tok; const int32_t* hist_par; int32_t* labels; int64_t ldl;
+                       double* score_out; int Bc, K, L; };
+void beam_backtrack(Ctx&, const BeamBacktrack&);
 void axpy_vec(Ctx&, float* y, const float* x, int64_t n, float a);
 
 }  // namespace aocr

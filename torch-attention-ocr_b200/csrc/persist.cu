@@ -14,6 +14,17 @@
 
 #include "persist.h"
 
+// phase time stamps inside the bodies (diagnostic; CTA 0, thread 0; printed by persist_free under AOCR_PERSIST_TRACE)
+namespace aocr { __device__ unsigned long long g_bt[16]; __device__ int g_bt_on = 0; }
+#define AOCR_BT(i)                                                                          \
+  do {                                                                                      \
+    if (aocr::g_bt_on && blockIdx.x == 0 && threadIdx.x == 0) {                             \
+      unsigned long long _t;                                                                \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t));                                 \
+      aocr::g_bt[i] = _t;                                                                   \
+    }                                                                                       \
+  } while (0)
+
 #include "dec_bodies.cuh"
 #include "tc_ptx.cuh"
 
@@ -288,8 +299,12 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
   };
 
   for (int c = 0; c < ncmds; c++) {
-    const PCmd& cmd = *cbuf(c);
-    const int type = cmd.type;
+    // GEMM-type commands are decoded from the shared-memory copy (no L2 round trip after the barrier); the bodies read
+    // their payload from global memory: a payload in shared memory aliases the bodies' scratch stores as far as the
+    // compiler can tell, which serialises their loads (measured: attention backward 11.6 -> 17.5 us)
+    const PCmd& scmd = *cbuf(c);
+    const int type = scmd.type;
+    const PCmd& gcmd = cmds[c];
     // fetch the next command into the other buffer while this one runs (its last reader finished before the barrier)
     if (warp == 7 && lane < kCmdChunks && c + 1 < ncmds)
       cp_async16(cbuf0 + (uint32_t)((c + 1) & 1) * (uint32_t)sizeof(PCmd) + lane * 16,
@@ -305,7 +320,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       // Fused commands: the cluster is the M tile and the rank in the cluster is the split; the partial goes to this
       // CTA's shared memory (the idle B ring), the cluster reduces through DSMEM and applies the cell right away.
       const bool fused = (kSet & (bit(P_GEMM_ENC_FWD) | bit(P_GEMM_CELL_FWD))) != 0 && (type != P_GEMM);
-      const PGemm g = payload<PGemm>(cmd);
+      const PGemm g = payload<PGemm>(scmd);
       const TileOf tl = tile_of(g, fused, bid);
       const int z = tl.z, mt = tl.mt;
       float* stage = scratch;                                  // [BN columns][128 rows] fp32
@@ -313,11 +328,11 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       if (fused && tl.has) {
         if constexpr ((kSet & bit(P_GEMM_ENC_FWD)) != 0) {
           if (type == P_GEMM_ENC_FWD)
-            enc_cell_preload<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), mt, z, g.splits, pre);
+            enc_cell_preload<BN>(*reinterpret_cast<const EncCellFwdTc*>(scmd.payload + sizeof(PGemm)), mt, z, g.splits, pre);
         }
         if constexpr ((kSet & bit(P_GEMM_CELL_FWD)) != 0) {
           if (type == P_GEMM_CELL_FWD)
-            cell_preload<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), mt, z, g.splits, pre);
+            cell_preload<BN>(*reinterpret_cast<const CellFwdTc*>(scmd.payload + sizeof(PGemm)), mt, z, g.splits, pre);
         }
       }
       if (tl.has) {
@@ -406,12 +421,12 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         if (tl.has) {
           if constexpr ((kSet & bit(P_GEMM_ENC_FWD)) != 0) {
             if (type == P_GEMM_ENC_FWD)
-              fused_enc_cell_fwd<BN>(*reinterpret_cast<const EncCellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z,
+              fused_enc_cell_fwd<BN>(*reinterpret_cast<const EncCellFwdTc*>(scmd.payload + sizeof(PGemm)), cluster, stage, mt, z,
                                      g.splits, pre);
           }
           if constexpr ((kSet & bit(P_GEMM_CELL_FWD)) != 0) {
             if (type == P_GEMM_CELL_FWD)
-              fused_cell_fwd<BN>(*reinterpret_cast<const CellFwdTc*>(cmd.payload + sizeof(PGemm)), cluster, stage, mt, z, g.splits,
+              fused_cell_fwd<BN>(*reinterpret_cast<const CellFwdTc*>(scmd.payload + sizeof(PGemm)), cluster, stage, mt, z, g.splits,
                                  pre);
           }
         }
@@ -419,25 +434,25 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
         // partial before anything reuses the B ring
       }
     } else if (is(P_CELL_FWD)) {
-      if constexpr ((kSet & bit(P_CELL_FWD)) != 0) decb::cell_fwd_tc_body(payload<CellFwdTc>(cmd), bid, nblk, scratch);
+      if constexpr ((kSet & bit(P_CELL_FWD)) != 0) decb::cell_fwd_tc_body(payload<CellFwdTc>(gcmd), bid, nblk, scratch);
     } else if (is(P_CELL_BWD)) {
-      if constexpr ((kSet & bit(P_CELL_BWD)) != 0) decb::cell_bwd_tc_body(payload<CellBwdTc>(cmd), bid, nblk, scratch);
+      if constexpr ((kSet & bit(P_CELL_BWD)) != 0) decb::cell_bwd_tc_body(payload<CellBwdTc>(gcmd), bid, nblk, scratch);
     } else if (is(P_ENC_CELL_FWD)) {
-      if constexpr ((kSet & bit(P_ENC_CELL_FWD)) != 0) decb::enc_cell_fwd_tc_body(payload<EncCellFwdTc>(cmd), bid, nblk, scratch);
+      if constexpr ((kSet & bit(P_ENC_CELL_FWD)) != 0) decb::enc_cell_fwd_tc_body(payload<EncCellFwdTc>(gcmd), bid, nblk, scratch);
     } else if (is(P_ENC_CELL_BWD)) {
-      if constexpr ((kSet & bit(P_ENC_CELL_BWD)) != 0) decb::enc_cell_bwd_tc_body(payload<EncCellBwdTc>(cmd), bid, nblk, scratch);
+      if constexpr ((kSet & bit(P_ENC_CELL_BWD)) != 0) decb::enc_cell_bwd_tc_body(payload<EncCellBwdTc>(gcmd), bid, nblk, scratch);
     } else if (is(P_TO_DENSE)) {
       if constexpr ((kSet & bit(P_TO_DENSE)) != 0) {
-        const PToDense p = payload<PToDense>(cmd);
+        const PToDense p = payload<PToDense>(gcmd);
         decb::part_to_dense_body(p.in, p.dst, p.ld, p.B, p.cols, bid, nblk, scratch);
       }
     } else if (is(P_GENERATOR)) {
-      if constexpr ((kSet & bit(P_GENERATOR)) != 0) decb::generator_body(payload<GenTc>(cmd), bid, nblk, scratch);
+      if constexpr ((kSet & bit(P_GENERATOR)) != 0) decb::generator_body(payload<GenTc>(gcmd), bid, nblk, scratch);
     } else if (is(P_GREEDY)) {
-      if constexpr ((kSet & bit(P_GREEDY)) != 0) decb::greedy_select_body(payload<GreedyTc>(cmd), bid, nblk, scratch);
+      if constexpr ((kSet & bit(P_GREEDY)) != 0) decb::greedy_select_body(payload<GreedyTc>(gcmd), bid, nblk, scratch);
     } else if (is(P_ATTN_OUT)) {
       if constexpr ((kSet & bit(P_ATTN_OUT)) != 0) {
-        const AttnOutTc p = payload<AttnOutTc>(cmd);
+        const AttnOutTc p = payload<AttnOutTc>(gcmd);
         for (int b = bid; b < p.B; b += nblk) {
           decb::attn_out_tc_body(p, b, scratch);
           __syncthreads();
@@ -445,9 +460,9 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       }
     } else if (is(P_ATTN_OUT_GEN)) {
       if constexpr ((kSet & bit(P_ATTN_OUT_GEN)) != 0) {
-      const AttnOutTc p = payload<AttnOutTc>(cmd);
-      const GenTc& gp = *reinterpret_cast<const GenTc*>(cmd.payload + sizeof(AttnOutTc));
-      const GreedyTc& gs = *reinterpret_cast<const GreedyTc*>(cmd.payload + sizeof(AttnOutTc) + sizeof(GenTc));
+      const AttnOutTc p = payload<AttnOutTc>(gcmd);
+      const GenTc& gp = *reinterpret_cast<const GenTc*>(gcmd.payload + sizeof(AttnOutTc));
+      const GreedyTc& gs = *reinterpret_cast<const GreedyTc*>(gcmd.payload + sizeof(AttnOutTc) + sizeof(GenTc));
       float* as = scratch + ((p.S + 3) & ~3) + 16 + 8 * p.H;     // = the `qs` region of the attention body
       float* zs = as + p.H;
       for (int b = bid; b < p.B; b += nblk) {
@@ -458,7 +473,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       }
     } else if (is(P_ATTN_DU)) {
       if constexpr ((kSet & bit(P_ATTN_DU)) != 0) {
-        const AttnDuTc p = payload<AttnDuTc>(cmd);
+        const AttnDuTc p = payload<AttnDuTc>(gcmd);
         for (int b = bid; b < p.B; b += nblk) {
           decb::attn_du_tc_body(p, b, scratch);
           __syncthreads();
@@ -681,6 +696,8 @@ void persist_upload(Ctx& ctx, PersistProgram& prog) {
   AOCR_CUDA(cudaMalloc(&prog.d_maps, (prog.maps.size() + 1) * sizeof(CUtensorMap)));
   AOCR_CUDA(cudaMalloc(&prog.d_barrier, 256));
   if (getenv("AOCR_PERSIST_TRACE")) {
+    int on = 1;
+    cudaMemcpyToSymbol(g_bt_on, &on, sizeof(int));
     const size_t nt = (prog.cmds.size() + 1) * 2 + prog.cmds.size() * (size_t)prog.grid;
     AOCR_CUDA(cudaMalloc(&prog.d_trace, nt * sizeof(unsigned long long)));
     AOCR_CUDA(cudaMemset(prog.d_trace, 0, nt * sizeof(unsigned long long)));
@@ -743,6 +760,12 @@ void persist_free(PersistProgram& prog) {
               ty, cnt[ty], work[ty] / cnt[ty] / 1e3, wait[ty] / cnt[ty] / 1e3, wmed[ty] / cnt[ty] / 1e3, wmax[ty] / cnt[ty] / 1e3, top, slow[ty * ng + top]);
     }
     fprintf(stderr, "\n");
+    unsigned long long bt[16];
+    if (cudaMemcpyFromSymbol(bt, g_bt, sizeof(bt)) == cudaSuccess) {
+      fprintf(stderr, "[body stamps, last call, CTA 0] attn_du:");
+      for (int i = 1; i <= 5; i++) fprintf(stderr, " %d->%d %.2fus", i - 1, i, (double)(bt[i] - bt[i - 1]) / 1e3);
+      fprintf(stderr, " | enc_cell_bwd: loads %.2fus compute+stores %.2fus\n", (double)(bt[9] - bt[8]) / 1e3, (double)(bt[10] - bt[9]) / 1e3);
+    }
     cudaFree(prog.d_trace); prog.d_trace = nullptr;
   }
   prog.d_cmds = nullptr; prog.d_maps = nullptr; prog.d_barrier = nullptr; prog.uploaded = false;

@@ -32,6 +32,12 @@ int aocr_train_step(aocr_handle* h, const float* images, int b, int W, const int
 int aocr_decode_greedy(aocr_handle* h, const float* images, int b, int W, const int32_t* targets,
                        const int32_t* targets_eval, int T, int32_t* labels, double* pred_scores,
                        double* gold_scores, double* loss_sum, int32_t* num_correct);
+int aocr_decode_beam(aocr_handle* h, const float* images, int b, int W, const int32_t* targets,
+                     const int32_t* targets_eval, int T, int beam_size, const int32_t* trie_table, int32_t trie_nodes,
+                     int32_t* labels, double* pred_scores, double* gold_scores, double* loss_sum, int32_t* num_correct);
+int aocr_trie_load(const char* path, int allow_digit_prefix, int32_t** table, int32_t* num_nodes);
+int aocr_trie_from_words(const char* words, int allow_digit_prefix, int32_t** table, int32_t* num_nodes);
+void aocr_trie_free(int32_t* table);
 int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n);
 int aocr_debug_read(aocr_handle* h, const char* name, float* out, int64_t n);
 /* device-resident entry points and the data-parallel plumbing (no reference counterpart: train.lua is single-device) */
@@ -59,6 +65,16 @@ int aocr_prof_read(aocr_handle* h, int cls, double* ms, int64_t* launches, doubl
 
 local lib = ffi.load(os.getenv('AOCR_LIB') or 'torch-attention-ocr_b200/lib/libaocr.so')
 local M = { lib = lib, ffi = ffi }
+
+-- loadDictionary(dictionary_path, allow_digit_prefix) of src/utils/utils.lua:177-218, as the flat child table the
+-- library consumes: returns {table = int32_t*, nodes = n} (pass it as the `trie` argument of model:step)
+function M.loadDictionary(path, allow_digit_prefix)
+  local t, n = ffi.new('int32_t*[1]'), ffi.new('int32_t[1]')
+  if lib.aocr_trie_load(path, allow_digit_prefix and 1 or 0, t, n) ~= 0 then
+    error(string.format('Error: Data file %s not found ', path))
+  end
+  return { table = ffi.gc(t[0], lib.aocr_trie_free), nodes = n[0] }
+end
 
 function M.check(h, rc)
   if rc ~= 0 then error(ffi.string(lib.aocr_last_error(h)), 2) end   -- same texts as the reference's asserts

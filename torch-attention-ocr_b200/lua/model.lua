@@ -145,10 +145,11 @@ function model:step(batch, forward_only, beam_size, trie)   -- model.lua:226-706
     A.check(self.h, lib.aocr_decode_greedy(self.h, images:data(), b, W, targets:data(), targets_eval:data(), T,
                                            labels:data(), pred:data(), gold:data(), loss, nc))
   else
-    -- beam search, optionally constrained to a dictionary trie (model.lua:380-387,405-445,460-514): `trie` is the
-    -- flattened trie built by aocr_trie_build from the word list of utils.lua:177-218 (loadDictionary)
+    -- beam search, optionally constrained to a dictionary trie (model.lua:380-387,405-445,460-514): `trie` is what
+    -- aocr_ffi.loadDictionary returns (utils.lua:177-218 as a flat child table)
     A.check(self.h, lib.aocr_decode_beam(self.h, images:data(), b, W, targets:data(), targets_eval:data(), T,
-                                         beam_size, trie, labels:data(), pred:data(), gold:data(), loss, nc))
+                                         beam_size, trie and trie.table or nil, trie and trie.nodes or 0,
+                                         labels:data(), pred:data(), gold:data(), loss, nc))
   end
   if self.visualize and self.visualize_file then                                               -- model.lua:628-633
     local img_paths = batch[5]
