@@ -6,6 +6,9 @@
 #include "kernels_dec.h"
 
 // AOCR_BT(i): optional phase time stamps inside the bodies (persist.cu defines it under AOCR_PERSIST_TRACE builds)
+#ifndef AOCR_VARIANT
+#define AOCR_VARIANT 0
+#endif
 #ifndef AOCR_BT
 #define AOCR_BT(i)
 #endif
@@ -135,6 +138,22 @@ __device__ __forceinline__ void cell_bwd_tc_body(CellBwdTc p, int bid, int nblk,
 // ------------------------------------------------------------------ attention (see kernels_rnn.cu for the layout notes)
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_MAXV = 8;
+constexpr int ATT_RIF = 2;      // source rows in flight per warp and pass (3 spills registers in the executor)
+
+// a 16-byte load of a time-invariant operand that is re-read every timestep (ctx, ctx W_c1^T): L2 evict_last, so the
+// weight stream of the GEMM commands does not push it out to DRAM between two steps
+__device__ __forceinline__ float4 ld_keep4(const float* p, uint64_t pol) {
+  float4 v;
+  asm("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint64_t l2_keep_policy(bool keep = true) {
+  uint64_t pol;
+  if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 
 // attention + output projection of batch row b (see AttnOutTc)
 __device__ __forceinline__ void attn_out_tc_body(const AttnOutTc& p, int b, float* sm, bool keep_a = false) {
@@ -253,17 +272,8 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
   const float* wb = p.ctxwc + (int64_t)b * S * H;
   const float* alpha = p.alpha + (int64_t)b * S;
   float* gs = accs + ATT_WARPS * H;               // du, shared by the 8 warps
-  // this warp's first ctx*W_c1^T row and first ctx row do not depend on du: loaded up front (one L2 round trip each,
-  // overlapped with the phases in front of their use)
-  float4 wrow[ATT_MAXV], crow[ATT_MAXV];
-  if (warp < S) {
-#pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++)
-      if (i < nv) {
-        wrow[i] = __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)warp * H + lane * 4 + 128 * i));
-        crow[i] = __ldcg(reinterpret_cast<const float4*>(cb + (int64_t)warp * H + lane * 4 + 128 * i));
-      }
-  }
+  const int var = AOCR_VARIANT;
+  const uint64_t pol = l2_keep_policy(!(var & 4));
   AOCR_BT(0);
   const int e4 = threadIdx.x * 4;
   if (e4 < H) {   // du once per CTA: kept for the time-batched weight gradients + first half of the next GEMM's operand
@@ -285,17 +295,28 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
 #pragma unroll
   for (int i = 0; i < ATT_MAXV; i++)
     gv[i] = (i < nv) ? *reinterpret_cast<const float4*>(gs + lane * 4 + 128 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = warp; s < S; s += ATT_WARPS) {
-    float dot = 0.f;
+  // each warp takes ATT_RIF consecutive source rows per pass, all of their loads in flight before the first use
+  for (int s0 = warp * ATT_RIF; s0 < S; s0 += ATT_WARPS * ATT_RIF) {
+    float4 r[ATT_RIF][ATT_MAXV];
 #pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++) {
-      if (i < nv) {
-        const float4 r = s == warp ? wrow[i] : __ldcg(reinterpret_cast<const float4*>(wb + (int64_t)s * H + lane * 4 + 128 * i));
-        dot += r.x * gv[i].x + r.y * gv[i].y + r.z * gv[i].z + r.w * gv[i].w;
-      }
+    for (int k = 0; k < ATT_RIF; k++) {
+      const int s = min(s0 + k, S - 1);
+#pragma unroll
+      for (int i = 0; i < ATT_MAXV; i++)
+        if (i < nv) {
+          const float* src = wb + (int64_t)s * H + lane * 4 + 128 * i;
+          r[k][i] = ld_keep4(src, pol);
+        }
     }
-    dot = warp_sum(dot);
-    if (lane == 0) das[s] = dot;
+#pragma unroll
+    for (int k = 0; k < ATT_RIF; k++) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < ATT_MAXV; i++)
+        if (i < nv) dot += r[k][i].x * gv[i].x + r[k][i].y * gv[i].y + r[k][i].z * gv[i].z + r[k][i].w * gv[i].w;
+      dot = warp_sum(dot);
+      if (lane == 0 && s0 + k < S) das[s0 + k] = dot;
+    }
   }
   __syncthreads();
   AOCR_BT(2);
@@ -312,16 +333,28 @@ __device__ __forceinline__ void attn_du_tc_body(const AttnDuTc& p, int b, float*
   float4 acc[ATT_MAXV];
 #pragma unroll
   for (int i = 0; i < ATT_MAXV; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = warp; s < S; s += ATT_WARPS) {
-    const float w = alpha[s] * (das[s] - tot);
+  for (int s0 = warp * ATT_RIF; s0 < S; s0 += ATT_WARPS * ATT_RIF) {
+    float4 r[ATT_RIF][ATT_MAXV];
+    float w[ATT_RIF];
 #pragma unroll
-    for (int i = 0; i < ATT_MAXV; i++) {
-      if (i < nv) {
-        const float4 r = s == warp ? crow[i] : __ldcg(reinterpret_cast<const float4*>(cb + (int64_t)s * H + lane * 4 + 128 * i));
-        acc[i].x = fmaf(w, r.x, acc[i].x); acc[i].y = fmaf(w, r.y, acc[i].y);
-        acc[i].z = fmaf(w, r.z, acc[i].z); acc[i].w = fmaf(w, r.w, acc[i].w);
-      }
+    for (int k = 0; k < ATT_RIF; k++) {
+      const int s = min(s0 + k, S - 1);
+      w[k] = s0 + k < S ? alpha[s] * (das[s] - tot) : 0.f;
+#pragma unroll
+      for (int i = 0; i < ATT_MAXV; i++)
+        if (i < nv) {
+          const float* src = cb + (int64_t)s * H + lane * 4 + 128 * i;
+          r[k][i] = ld_keep4(src, pol);
+        }
     }
+#pragma unroll
+    for (int k = 0; k < ATT_RIF; k++)
+#pragma unroll
+      for (int i = 0; i < ATT_MAXV; i++)
+        if (i < nv) {
+          acc[i].x = fmaf(w[k], r[k][i].x, acc[i].x); acc[i].y = fmaf(w[k], r[k][i].y, acc[i].y);
+          acc[i].z = fmaf(w[k], r[k][i].z, acc[i].z); acc[i].w = fmaf(w[k], r[k][i].w, acc[i].w);
+        }
   }
 #pragma unroll
   for (int i = 0; i < ATT_MAXV; i++)

@@ -15,7 +15,8 @@
 #include "persist.h"
 
 // phase time stamps inside the bodies (diagnostic; CTA 0, thread 0; printed by persist_free under AOCR_PERSIST_TRACE)
-namespace aocr { __device__ unsigned long long g_bt[16]; __device__ int g_bt_on = 0; }
+namespace aocr { __device__ unsigned long long g_bt[16]; __device__ int g_bt_on = 0; __device__ int g_variant = 0; }
+#define AOCR_VARIANT (aocr::g_variant)
 #define AOCR_BT(i)                                                                          \
   do {                                                                                      \
     if (aocr::g_bt_on && blockIdx.x == 0 && threadIdx.x == 0) {                             \
@@ -695,6 +696,10 @@ void persist_upload(Ctx& ctx, PersistProgram& prog) {
   AOCR_CUDA(cudaMalloc(&prog.d_cmds, prog.cmds.size() * sizeof(PCmd)));
   AOCR_CUDA(cudaMalloc(&prog.d_maps, (prog.maps.size() + 1) * sizeof(CUtensorMap)));
   AOCR_CUDA(cudaMalloc(&prog.d_barrier, 256));
+  if (getenv("AOCR_VARIANT")) {          // development A/B switch read by the bodies (dec_bodies.cuh)
+    int v = atoi(getenv("AOCR_VARIANT"));
+    cudaMemcpyToSymbol(g_variant, &v, sizeof(int));
+  }
   if (getenv("AOCR_PERSIST_TRACE")) {
     int on = 1;
     cudaMemcpyToSymbol(g_bt_on, &on, sizeof(int));
