@@ -89,7 +89,7 @@ __device__ __forceinline__ void cell_fwd_tc_body(CellFwdTc p, int bid, int nblk,
   }
 }
 
-__device__ __forceinline__ void cell_bwd_tc_body(CellBwdTc p, int bid, int nblk, float* sm) {
+__device__ __forceinline__ void cell_bwd_tc_scalar(const CellBwdTc& p, int bid, int nblk) {
   const int H = p.H;
   const int64_t total = (int64_t)p.B * H;
   const int64_t stride = (int64_t)nblk * blockDim.x;
@@ -402,12 +402,11 @@ __device__ __forceinline__ void enc_cell_fwd_tc_body(EncCellFwdTc p, int bid, in
   }
 }
 
-__device__ __forceinline__ void enc_cell_bwd_tc_body(EncCellBwdTc p, int bid, int nblk, float* sm) {
+__device__ __forceinline__ void enc_cell_bwd_tc_scalar(const EncCellBwdTc& p, int bid, int nblk) {
   const int He = p.He, B = p.B, S = p.S;
   const int64_t total = (int64_t)(p.d_only < 0 ? 2 : 1) * B * He;
   const int64_t stride = (int64_t)nblk * blockDim.x;
   constexpr int U = 4;      // elements per thread and pass, loads of all U in front (32 CTAs serve 64 x 512 elements)
-  AOCR_BT(8);
   for (int64_t e0 = (int64_t)bid * blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
     float dhv[U], ai[U], af[U], ao[U], ag[U], cpv[U], cnv[U], dcv[U];
 #pragma unroll
@@ -426,8 +425,6 @@ __device__ __forceinline__ void enc_cell_bwd_tc_body(EncCellBwdTc p, int bid, in
       dhv[k] = part_load(p.dh[d], b, unit) + __ldcg(p.Dctx + ((int64_t)b * S + t) * (2 * He) + d * He + unit);
       dcv[k] = __ldcg(p.dc + ((int64_t)d * B + b) * He + unit);
     }
-    if (dhv[0] == 12345.678f) AOCR_BT(15);     // (forces the loads to complete before the next stamp)
-    AOCR_BT(9);
 #pragma unroll
     for (int k = 0; k < U; k++) {
       const int64_t e = e0 + k * stride;
@@ -453,6 +450,96 @@ __device__ __forceinline__ void enc_cell_bwd_tc_body(EncCellBwdTc p, int bid, in
       pack_store(p.dgp[d], b, 3 * He + unit, d3);
       p.dc[ce] = dc * f_;
     }
+  }
+}
+
+// ---- vector forms of the two cell-backward bodies: one thread = 4 consecutive hidden units of one batch row, every
+// operand as one 16-byte access (a quarter of the memory instructions of the scalar form; these bodies are bound by the
+// number of outstanding requests, not by bytes).  Used when every base pointer / pitch keeps 16-byte alignment.
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ bool part_al16(const PartIn& a) { return !a.p || (al16(a.p) && (a.ld & 3) == 0 && (a.stride & 3) == 0); }
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+struct GateGrads { float4 d0, d1, d2, d3, dcn; };
+__device__ __forceinline__ GateGrads lstm_cell_bwd4(float4 i_, float4 f_, float4 o_, float4 g_, float4 cn, float4 cp, float4 dcin,
+                                                    float4 dh) {
+  GateGrads r;
+  const float iv[4] = {i_.x, i_.y, i_.z, i_.w}, fv[4] = {f_.x, f_.y, f_.z, f_.w}, ov[4] = {o_.x, o_.y, o_.z, o_.w};
+  const float gv[4] = {g_.x, g_.y, g_.z, g_.w}, cnv[4] = {cn.x, cn.y, cn.z, cn.w}, cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+  const float dcv[4] = {dcin.x, dcin.y, dcin.z, dcin.w}, dhv[4] = {dh.x, dh.y, dh.z, dh.w};
+  float d0[4], d1[4], d2[4], d3[4], dn[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float tc = tanhf(cnv[k]);
+    const float dc = dcv[k] + dhv[k] * ov[k] * (1.f - tc * tc);
+    d0[k] = dc * gv[k] * iv[k] * (1.f - iv[k]);
+    d1[k] = dc * cpv[k] * fv[k] * (1.f - fv[k]);
+    d2[k] = dhv[k] * tc * ov[k] * (1.f - ov[k]);
+    d3[k] = dc * iv[k] * (1.f - gv[k] * gv[k]);
+    dn[k] = dc * fv[k];
+  }
+  r.d0 = make_float4(d0[0], d0[1], d0[2], d0[3]); r.d1 = make_float4(d1[0], d1[1], d1[2], d1[3]);
+  r.d2 = make_float4(d2[0], d2[1], d2[2], d2[3]); r.d3 = make_float4(d3[0], d3[1], d3[2], d3[3]);
+  r.dcn = make_float4(dn[0], dn[1], dn[2], dn[3]);
+  return r;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__device__ __forceinline__ void cell_bwd_tc_body(CellBwdTc p, int bid, int nblk, float* sm) {
+  const int H = p.H;
+  const bool vec = (H & 3) == 0 && part_al16(p.dh_a) && part_al16(p.dh_b) && part_al16(p.dh_c) && al16(p.dc) && al16(p.c_prev) &&
+                   al16(p.c_new) && al16(p.acts) && al16(p.dG) && (!p.pk.hi || ((p.pk.ld & 3) == 0));
+  if (!vec) { cell_bwd_tc_scalar(p, bid, nblk); return; }
+  const int H4 = H / 4;
+  const int64_t total = (int64_t)p.B * H4;
+  for (int64_t q = (int64_t)bid * blockDim.x + threadIdx.x; q < total; q += (int64_t)nblk * blockDim.x) {
+    const int u = (int)(q % H4) * 4;
+    const int64_t b = q / H4, e = b * H + u;
+    const float* a = p.acts + b * 4 * H + u;
+    const float4 ai = ldcg4(a), af = ldcg4(a + H), ao = ldcg4(a + 2 * H), ag = ldcg4(a + 3 * H);
+    const float4 cn = ldcg4(p.c_new + e), cp = ldcg4(p.c_prev + e), dcin = ldcg4(p.dc + e);
+    float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dh_a.p) dh = add4(dh, part_load4(p.dh_a, b, u));
+    if (p.dh_b.p) dh = add4(dh, part_load4(p.dh_b, b, u));
+    if (p.dh_c.p) dh = add4(dh, part_load4(p.dh_c, b, u));
+    const GateGrads g = lstm_cell_bwd4(ai, af, ao, ag, cn, cp, dcin, dh);
+    float* dg = p.dG + b * 4 * H + u;
+    *reinterpret_cast<float4*>(dg) = g.d0; *reinterpret_cast<float4*>(dg + H) = g.d1;
+    *reinterpret_cast<float4*>(dg + 2 * H) = g.d2; *reinterpret_cast<float4*>(dg + 3 * H) = g.d3;
+    pack_store4(p.pk, b, u, g.d0); pack_store4(p.pk, b, H + u, g.d1);
+    pack_store4(p.pk, b, 2 * H + u, g.d2); pack_store4(p.pk, b, 3 * H + u, g.d3);
+    *reinterpret_cast<float4*>(p.dc + e) = g.dcn;
+  }
+}
+
+__device__ __forceinline__ void enc_cell_bwd_tc_body(EncCellBwdTc p, int bid, int nblk, float* sm) {
+  const int He = p.He, B = p.B, S = p.S;
+  const bool vec = (He & 3) == 0 && part_al16(p.dh[0]) && part_al16(p.dh[1]) && al16(p.Cst) && al16(p.acts) && al16(p.Dctx) &&
+                   al16(p.dc) && al16(p.dG) && (!p.dgp[0].hi || (p.dgp[0].ld & 3) == 0) && (!p.dgp[1].hi || (p.dgp[1].ld & 3) == 0);
+  if (!vec) { enc_cell_bwd_tc_scalar(p, bid, nblk); return; }
+  const int H4 = He / 4;
+  const int64_t total = (int64_t)(p.d_only < 0 ? 2 : 1) * B * H4;
+  AOCR_BT(8);
+  for (int64_t q = (int64_t)bid * blockDim.x + threadIdx.x; q < total; q += (int64_t)nblk * blockDim.x) {
+    const int unit = (int)(q % H4) * 4;
+    const int64_t b = (q / H4) % B;
+    const int d = p.d_only < 0 ? (int)(q / ((int64_t)H4 * B)) : p.d_only;
+    const int t = d == 0 ? S - 1 - p.step : p.step;
+    const int prev_slot = d == 0 ? t : t + 1, out_slot = d == 0 ? t + 1 : t;
+    const float* a = p.acts + (((int64_t)(d * S + t) * B + b) * 4) * He + unit;
+    const float4 ai = ldcg4(a), af = ldcg4(a + He), ao = ldcg4(a + 2 * He), ag = ldcg4(a + 3 * He);
+    const float4 cp = ldcg4(p.Cst + ((int64_t)(d * (S + 1) + prev_slot) * B + b) * He + unit);
+    const float4 cn = ldcg4(p.Cst + ((int64_t)(d * (S + 1) + out_slot) * B + b) * He + unit);
+    const int64_t ce = ((int64_t)d * B + b) * He + unit;
+    const float4 dcin = ldcg4(p.dc + ce);
+    const float4 dh = add4(part_load4(p.dh[d], b, unit), ldcg4(p.Dctx + ((int64_t)b * S + t) * (2 * He) + d * He + unit));
+    AOCR_BT(9);
+    const GateGrads g = lstm_cell_bwd4(ai, af, ao, ag, cn, cp, dcin, dh);
+    float* dg = p.dG + ((int64_t)t * B + b) * (8 * He) + (int64_t)d * 4 * He + unit;
+    *reinterpret_cast<float4*>(dg) = g.d0; *reinterpret_cast<float4*>(dg + He) = g.d1;
+    *reinterpret_cast<float4*>(dg + 2 * He) = g.d2; *reinterpret_cast<float4*>(dg + 3 * He) = g.d3;
+    pack_store4(p.dgp[d], b, unit, g.d0); pack_store4(p.dgp[d], b, He + unit, g.d1);
+    pack_store4(p.dgp[d], b, 2 * He + unit, g.d2); pack_store4(p.dgp[d], b, 3 * He + unit, g.d3);
+    *reinterpret_cast<float4*>(p.dc + ce) = g.dcn;
     AOCR_BT(10);
   }
 }

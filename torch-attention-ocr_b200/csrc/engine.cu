@@ -177,7 +177,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
     const int64_t n_act[7] = {0, B * 16 * W1 * 64, B * 8 * W2 * 128, B * 8 * W2 * 256, B * 4 * W2 * 256, B * 4 * W2 * 512, B * 2 * W2 * 512};
     for (int l = 1; l <= 6; l++) actp_[l] = alloc_pack(1, n_act[l]);
     const int64_t n_z[7] = {0, B * 16 * W1 * 128, B * 8 * W2 * 256, B * 8 * W2 * 256, B * 4 * W2 * 512, B * 4 * W2 * 512, B * S * 512};
-    for (int l = 1; l <= 6; l++) dzp_[l] = alloc_pack(1, n_z[l]);
+    for (int l = 1; l <= 6; l++) { dzp_[l] = alloc_pack(1, n_z[l]); dzf_[l] = alloc<float>(n_z[l]); }
     srcP_ = alloc_pack(S * B, 512);
     WiCatP = alloc_pack(8 * c.encoder_num_hidden, 512);   // dz of conv_{l+1} has the shape of zb[l+1]
   }
@@ -615,9 +615,9 @@ void Engine::cnn_backward() {
     conv_dims(l, Hin, Win, Hout, Wout);
     const int64_t rows = (int64_t)B * Hout * Wout;
     const int Kc = c.k * c.k * c.cin;
-    float* dz = gA;
     // dz as bf16 planes, written by the kernel that produces dz: shared by the weight- and the data-gradient GEMM
     const bool tc = cfg.gemm_mode != 2;
+    float* dz = tc ? dzf_[l] : gA;      // per layer in tensor-core mode: read by the side lane after lane 0 has moved on
     Pack dzp;
     dzp.rows = rows; dzp.kp = c.cout; dzp.hi = tc ? dzp_[l].hi : nullptr; dzp.lo = tc ? dzp_[l].lo : nullptr;
     if (c.bn >= 0) {
@@ -630,18 +630,18 @@ void Engine::cnn_backward() {
     } else {
       relu_pool_bwd(ctx_, dcur, act[l + 1], pidx[l + 1], dz, B, Hout, Wout, c.cout, c.pool_kw, dzp.hi, dzp.lo);
     }
-    // bias grad
-    col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);
     // weight grad: dW[co][tap,ci] = sum_rows dz[row][co] * col[row][tap,ci]
     if (cfg.gemm_mode != 2) {
-      // the weight gradient feeds nothing downstream: lane 2 (idle since the encoder backward), so it fills the
-      // partial waves of the data-gradient chain that continues on lane 0; operands are per-layer packs (no reuse race)
+      // the weight and bias gradients feed nothing downstream: lane 2 (idle since the encoder backward), so they fill the
+      // partial waves of the data-gradient chain that continues on lane 0; operands are per-layer buffers (no reuse race)
       fork_to(2);
       use_lane(2);
+      col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);     // bias grad (this lane's partial buffer)
       conv_wgrad_tc(dz, act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, c.cout, d_grads + L.conv_w[l], &dzp, &actp_[l]);
       if (l == 4 && cnn_bucket_split_ >= 0) grad_range(cnn_bucket_split_, L.goff[G_CNN] + L.gphys[G_CNN]);
       use_lane(0);
     } else {
+      col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);     // bias grad
       im2col(ctx_, act[l], col, B, Hin, Win, c.cin, c.k, c.pad);
       Gemm gw;
       gw.M = c.cout; gw.N = Kc; gw.K = (int)rows;
@@ -668,7 +668,7 @@ void Engine::cnn_backward() {
     dcur = gB;
     // next iteration writes dz into gA again and reads dcur=gB: fine (distinct buffers)
   }
-  const int nblk = 256;
+  const int nblk = 8 * 148;      // ~43 pooled pixels per block at batch 64: the per-thread loop is a chain of dependent loads
   conv1_bwd(ctx_, x0, act[1], pidx[1], dcur, d_grads + L.conv_w[0], d_grads + L.conv_b[0], partial, nblk, B, W_);
   join_from(2);
 }

@@ -224,6 +224,7 @@ class Engine {
   // tensor-core decoder path: concatenated weight packs, per-step operand packs, split-K partial regions
   Pack Wcat1p, Wcat2p, W3p, Wcat1Tp, Wcat2Tp, W3Tp;   // W3 = [W_a ; W_c[:, H:]] (rows), W3T = its transpose
   Pack X1p, X2p, H2p, dUQp, dG2p, dG1p;
+  float* dzf_[8] = {};   // dz of conv layer l in fp32, per layer: its bias-gradient column sum runs on the side lane too
   Pack dzp_[8];    // dz of conv layer l as bf16 planes (per layer: the weight-gradient GEMM runs on a side lane)
   Pack actp_[8];   // act[l] (input of conv l+1) as bf16 planes, written by the producing kernel; reused by the weight gradient
   Pack Whp[2], WhTp[2], HencP[2], dGeP[2];

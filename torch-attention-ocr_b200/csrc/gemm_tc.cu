@@ -44,6 +44,7 @@ struct TcParams {
   int wg_cin;      // mn == 2: input channels (N index = tap*Cin + ci)
   int cin_blocks, ksz, pad;
   int bw, bh, bn, tiles_w, tiles_h;
+  int a_rows;      // conv mode: pixels per A box = bw*bh*bn (<= 128; the remaining tile rows are never written nor stored)
   int Nimg, Ho, Wo;
   // epilogue
   float* C;
@@ -115,7 +116,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0 && !(p.dbg & 1)) {
-      const uint32_t tx = (uint32_t)(p.terms == 3 ? 2 : 1) * (A_PLANE_BYTES + C_::kBPlane);
+      const uint32_t a_bytes = p.conv ? (uint32_t)p.a_rows * (BK * 2) : (uint32_t)A_PLANE_BYTES;
+      const uint32_t tx = (uint32_t)(p.terms == 3 ? 2 : 1) * (a_bytes + C_::kBPlane);
       for (int i = 0; i < nkb; i++) {
         const int kb = kb_begin + i;
         const int s = i % C_::kStages;
@@ -211,7 +213,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (p.conv) {
       const int wl = ml % p.bw, hl = (ml / p.bw) % p.bh, nl = ml / (p.bw * p.bh);
       const int n = cn0 + nl, h = ch0 + hl, w = cw0 + wl;
-      row_ok = (n < p.Nimg) && (h < p.Ho) && (w < p.Wo);
+      row_ok = (nl < p.bn) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo);
       row = ((long long)n * p.Ho + h) * p.Wo + w;
     }
     const float bm = (p.bias_m && row_ok) ? p.bias_m[row] : 0.f;
@@ -286,6 +288,244 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 1 && !(p.dbg & 4)) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// One cluster of two CTAs per 256 x BN output tile (two consecutive 128-row M tiles).  Each CTA loads its own A tile and
+// HALF of the B tile (BN/2 rows), so the operand bytes per MMA flop are 2/3 (BN = 128) or 1/2 (BN = 256) of the
+// single-CTA kernel's: under bf16x3 (two planes per operand, three MMAs per k-step) the single-CTA 128 x 128 tile needs
+// 85 B/clk of shared-memory fill per SM, about twice what L2 delivers per SM; the pair's 256 x 256 tile needs 42.
+template <int BN> struct Cfg2 {
+  static constexpr int BNH = BN / 2;                       // B rows this CTA loads
+  static constexpr int kBPlane = BNH * BK * 2;
+  static constexpr int kStageBytes = 2 * A_PLANE_BYTES + 2 * kBPlane;
+  static constexpr int kStages = (BN == 256) ? 3 : 4;
+  static constexpr int kTmemCols = BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                const TcParams p) {
+  using C_ = Cfg2<BN>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + C_::kStages * C_::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C_::kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * C_::kStages);
+  const uint32_t tmem_slot = bars + 8u * (2 * C_::kStages + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int kb_begin = blockIdx.z * p.kb_per;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per);
+  const int nkb = kb_end - kb_begin;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
+  const int n0 = blockIdx.y * BN;                          // first output column of the pair's tile
+  const int nb0 = n0 + (int)rank * C_::BNH;                // first B row this CTA loads
+  int m0 = blockIdx.x * BM;                                // this CTA's 128 rows (cluster = a blockIdx.x pair: cta_group::2 pairs lie along x)
+  int cn0 = 0, ch0 = 0, cw0 = 0;
+  if (p.conv) {
+    int id = blockIdx.x;
+    int wb = id % p.tiles_w; id /= p.tiles_w;
+    int hb = id % p.tiles_h; id /= p.tiles_h;
+    cn0 = id * p.bn; ch0 = hb * p.bh; cw0 = wb * p.bw;
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_::kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+  }
+  if (warp == 1) {   // TMEM allocation of the pair (the MMA warp of each CTA)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C_::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; completion bytes go to the leader's full barrier) ==========
+    if (lane == 0) {
+      const int planes = p.terms == 3 ? 2 : 1;
+      const uint32_t a_bytes = p.conv ? (uint32_t)p.a_rows * (BK * 2) : (uint32_t)A_PLANE_BYTES;
+      const uint32_t tx_pair = 2u * (uint32_t)planes * (a_bytes + C_::kBPlane);
+      for (int i = 0; i < nkb; i++) {
+        const int kb = kb_begin + i;
+        const int s = i % C_::kStages;
+        const uint32_t ph = (uint32_t)(i / C_::kStages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t sa = base + s * C_::kStageBytes;
+        const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+        const uint32_t fb = mapa_rank(full_bar(s), 0);
+        if (rank == 0) mbar_expect_tx(full_bar(s), tx_pair);
+        if (p.mn) {
+          int kc1 = kb * BK, kc2 = 0, kc3 = 0;
+          int bs1 = 0, bs2 = 0, bco = nb0;
+          if (p.mn == 2) {
+            int id = kb;
+            const int wb = id % p.tiles_w; id /= p.tiles_w;
+            const int hb = id % p.tiles_h; id /= p.tiles_h;
+            kc1 = wb * p.bw; kc2 = hb * p.bh; kc3 = id * p.bn;
+            const int tap = n0 / p.wg_cin;
+            bco = nb0 % p.wg_cin;
+            bs1 = tap % p.ksz - p.pad; bs2 = tap / p.ksz - p.pad;
+          }
+          for (int pl = 0; pl < planes; pl++) {
+            const CUtensorMap* ta = pl ? &tmAl : &tmAh;
+            const CUtensorMap* tb = pl ? &tmBl : &tmBh;
+#pragma unroll
+            for (int j = 0; j < BM / 64; j++) {
+              const uint32_t dst = sa + pl * A_PLANE_BYTES + j * 8192;
+              if (p.mn == 2) tma2_load_4d(dst, ta, fb, m0 + 64 * j, kc1, kc2, kc3);
+              else tma2_load_2d(dst, ta, fb, m0 + 64 * j, kc1);
+            }
+#pragma unroll
+            for (int j = 0; j < C_::BNH / 64; j++) {
+              const uint32_t dst = sb + pl * C_::kBPlane + j * 8192;
+              if (p.mn == 2) tma2_load_4d(dst, tb, fb, bco + 64 * j, kc1 + bs1, kc2 + bs2, kc3);
+              else tma2_load_2d(dst, tb, fb, nb0 + 64 * j, kc1);
+            }
+          }
+        } else {
+          if (p.conv) {
+            const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+            const int kh = tap / p.ksz, kw = tap % p.ksz;
+            tma2_load_4d(sa, &tmAh, fb, cb * BK, cw0 + kw - p.pad, ch0 + kh - p.pad, cn0);
+            if (planes == 2) tma2_load_4d(sa + A_PLANE_BYTES, &tmAl, fb, cb * BK, cw0 + kw - p.pad, ch0 + kh - p.pad, cn0);
+          } else {
+            tma2_load_2d(sa, &tmAh, fb, kb * BK, m0);
+            if (planes == 2) tma2_load_2d(sa + A_PLANE_BYTES, &tmAl, fb, kb * BK, m0);
+          }
+          tma2_load_2d(sb, &tmBh, fb, kb * BK, nb0);
+          if (planes == 2) tma2_load_2d(sb + C_::kBPlane, &tmBl, fb, kb * BK, nb0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the leader CTA only =====================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc2(BN, p.mn);
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % C_::kStages;
+        const uint32_t ph = (uint32_t)(i / C_::kStages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * C_::kStageBytes;
+          const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+          const uint64_t dah = p.mn ? make_desc_mnmajor_sw128(sa) : make_desc_kmajor_sw128(sa);
+          const uint64_t dal = p.mn ? make_desc_mnmajor_sw128(sa + A_PLANE_BYTES) : make_desc_kmajor_sw128(sa + A_PLANE_BYTES);
+          const uint64_t dbh = p.mn ? make_desc_mnmajor_sw128(sb) : make_desc_kmajor_sw128(sb);
+          const uint64_t dbl = p.mn ? make_desc_mnmajor_sw128(sb + C_::kBPlane) : make_desc_kmajor_sw128(sb + C_::kBPlane);
+          const uint64_t kstep = p.mn ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            const uint64_t adv = kstep * k;
+            tc2_mma(tmem_base, dah + adv, dbh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (p.terms == 3) {
+              tc2_mma(tmem_base, dah + adv, dbl + adv, idesc, 1u);
+              tc2_mma(tmem_base, dal + adv, dbh + adv, idesc, 1u);
+            }
+          }
+          tc2_commit(empty_bar(s));                      // frees the slot in BOTH CTAs when these MMAs retire
+          if (i == nkb - 1) tc2_commit(tmem_full_bar);   // both epilogues
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: this CTA's 128 accumulator rows, TMEM -> registers -> global ===============
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int ml = q * 32 + lane;
+    long long row = (long long)m0 + ml;
+    bool row_ok = row < p.M;
+    if (p.conv) {
+      const int wl = ml % p.bw, hl = (ml / p.bw) % p.bh, nl = ml / (p.bw * p.bh);
+      const int n = cn0 + nl, h = ch0 + hl, w = cw0 + wl;
+      row_ok = (nl < p.bn) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo);
+      row = ((long long)n * p.Ho + h) * p.Wo + w;
+    }
+    const float bm = (p.bias_m && row_ok) ? p.bias_m[row] : 0.f;
+    float* __restrict__ outp = p.splits > 1 ? p.ws + (long long)blockIdx.z * p.part_stride : p.C;
+    const bool plain = (p.splits > 1);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!row_ok) continue;
+      const int nb = n0 + c0;
+      if (nb >= p.N) continue;
+      float bias[16], old[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) { bias[j] = 0.f; old[j] = 0.f; }
+      if (!plain) {
+        if (p.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (nb + j < p.N)
+              old[j] = p.transpose_out ? p.C[(long long)(nb + j) * p.ldc + row] : p.C[row * p.ldc + nb + j];
+        }
+        if (p.bias_n) {
+#pragma unroll
+          for (int j = 0; j < 16; j++)
+            if (nb + j < p.N) bias[j] = p.bias_n[nb + j];
+        }
+      }
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        v[j] = __uint_as_float(r[j]);
+        if (!plain) {
+          v[j] += bm + bias[j];
+          if (p.act == ACT_TANH) v[j] = tanhf(v[j]);
+          v[j] += old[j];
+        }
+      }
+      if (!p.transpose_out && nb + 16 <= p.N && (p.ldc & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(outp + row * p.ldc + nb) & 15) == 0) {
+        float4* dst = reinterpret_cast<float4*>(outp + row * p.ldc + nb);
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          const int n = nb + j;
+          if (n < p.N) {
+            float* dst = p.transpose_out ? outp + (long long)n * p.ldc + row : outp + row * p.ldc + n;
+            *dst = v[j];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();        // both CTAs are done with the pair's shared memory and TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::kTmemCols) : "memory");
   }
 }
 
@@ -455,6 +695,41 @@ void launch(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtens
   AOCR_CUDA(cudaGetLastError());
 }
 
+template <int BN>
+void launch2(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+             const TcParams& p, dim3 grid) {
+  {
+    static std::mutex mu;
+    static std::set<int> done;
+    int dev = 0;
+    AOCR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done.count(dev)) {
+      AOCR_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmemBytes));
+      done.insert(dev);
+    }
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid.y, grid.x, grid.z);      // M tiles along x: the CTA pair is a pair of consecutive blockIdx.x
+  cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = (size_t)Cfg2<BN>::kSmemBytes; cfg.stream = ctx.st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ctx.pdl ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<BN>, ah, al, bh, bl, p);
+  if (e != cudaSuccess) {
+    int ncl = -1;
+    cudaGetLastError();
+    cudaError_t e2 = cudaOccupancyMaxActiveClusters(&ncl, (const void*)tc_gemm2_kernel<BN>, &cfg);
+    fprintf(stderr, "[aocr] pair-kernel launch failed: %s; grid (%u,%u,%u) smem %zu; max active clusters %d (%s)\n",
+            cudaGetErrorString(e), grid.x, grid.y, grid.z, cfg.dynamicSmemBytes, ncl, cudaGetErrorString(e2));
+    AOCR_CUDA(e);
+  }
+  ctx.launches++;
+}
+
 }  // namespace
 
 const CUtensorMap& tc_map_2d(const __nv_bfloat16* ptr, int64_t rows, int64_t kp, int box_rows) {
@@ -497,6 +772,12 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   int BN = g.N > 64 ? 128 : (g.N > 32 ? 64 : (g.N > 16 ? 32 : 16));
   if (g.mn && BN < 64) BN = 64;                     // MN-major boxes are 64 elements wide
   if (g.mn == 2 && g.conv && g.conv->C < 128) BN = 64;   // an N tile must not straddle two filter taps
+  // CTA-pair kernel (256 x BN tiles, cta_group::2): whenever there are at least two M tiles and N fills a 128-wide tile
+  static const bool pair_on = !(getenv("AOCR_CG2") && atoi(getenv("AOCR_CG2")) == 0);
+  static const int pair_maxbn = getenv("AOCR_CG2_BN") ? atoi(getenv("AOCR_CG2_BN")) : 256;
+  bool pair = pair_on && BN == 128 && g.M > BM && !(g.dbg);
+  if (pair && pair_maxbn >= 256 && g.N >= 256 && (g.mn != 2 || g.conv->C % 256 == 0)) BN = 256;
+  const int BNB = pair ? BN / 2 : BN;               // B rows one CTA loads
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.terms = g.terms; p.mn = g.mn;
   p.C = g.C; p.ldc = g.ldc; p.transpose_out = g.transpose_out ? 1 : 0;
@@ -509,11 +790,28 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     const ConvView& c = *g.conv;
     AOCR_CHECK(c.C % 64 == 0 && g.B.kp == c.C && g.A.kp >= g.M && g.M % 64 == 0, "conv wgrad: channels must be multiples of 64");
     AOCR_CHECK(g.N == c.k * c.k * c.C && c.C % BN == 0, "conv wgrad: N must be k*k*Cin");
+    AOCR_CHECK(!pair || BNB % 64 == 0, "pair kernel: MN-major B half must be whole 64-column boxes");
+    // contraction block = 64 output pixels as a (bw x bh x bn) box.  Rows of the block that the box does not cover would
+    // have to be zero, so only EXACT covers (bw*bh*bn == 64, every dimension divided evenly) replace the power-of-two
+    // box: a 25-wide map takes 1 x 8 x 8 boxes (no padded pixels) instead of 32 x 2 x 1 (22 % zero-filled pixels).
     int bw = 8;
     while (bw < c.Wo && bw < 64) bw *= 2;
     int bh = 1;
     while (bh * 2 * bw <= 64 && bh < c.Ho) bh *= 2;
-    const int bn = 64 / (bw * bh);
+    int bn = 64 / (bw * bh);
+    if (!(getenv("AOCR_BOX_POW2") && atoi(getenv("AOCR_BOX_POW2")))) {
+      long long best = (long long)((c.Wo + bw - 1) / bw) * ((c.Ho + bh - 1) / bh) * ((c.N + bn - 1) / bn);
+      for (int w = 1; w <= 64 && w <= c.Wo; w++) {
+        if (c.Wo % w) continue;
+        for (int h = 1; w * h <= 64 && h <= c.Ho; h++) {
+          if (c.Ho % h || 64 % (w * h)) continue;
+          const int n = 64 / (w * h);
+          if (c.N % n) continue;
+          const long long blocks = (long long)(c.Wo / w) * (c.Ho / h) * (c.N / n);
+          if (blocks < best || (blocks == best && w > bw)) { best = blocks; bw = w; bh = h; bn = n; }
+        }
+      }
+    }
     p.bw = bw; p.bh = bh; p.bn = bn; p.ksz = c.k; p.pad = c.pad; p.wg_cin = c.C;
     p.tiles_w = (c.Wo + bw - 1) / bw; p.tiles_h = (c.Ho + bh - 1) / bh;
     p.num_kb = p.tiles_w * p.tiles_h * ((c.N + bn - 1) / bn);
@@ -536,13 +834,32 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     const ConvView& c = *g.conv;
     AOCR_CHECK(c.C % BK == 0 && g.A.kp == c.C, "conv A pack must be NHWC with C a multiple of 64");
     AOCR_CHECK(g.K == c.k * c.k * c.C && g.B.kp == pad64(g.K), "conv weight pack must be [Cout][k*k*C]");
-    int bw = 8;
-    while (bw < c.Wo && bw < 128) bw *= 2;
-    int bh = 1;
-    while (bh * 2 * bw <= 128 && bh < c.Ho) bh *= 2;
-    int bn = 128 / (bw * bh);
+    // pixel box (bw x bh x bn <= 128 rows of the M tile): the one that covers the output with the fewest tiles.  TMA
+    // boxes need not be powers of two: a 25-wide map takes 25 x 1 x 5 boxes (125 of 128 rows live) instead of 32 x 4 x 1
+    // (100 of 128); rows past the box are never written by TMA and never stored by the epilogue.
+    int bw = 1, bh = 1, bn = 1;
+    {
+      static const bool pow2 = getenv("AOCR_BOX_POW2") && atoi(getenv("AOCR_BOX_POW2"));
+      long long best = -1;
+      for (int w = 1; w <= (c.Wo < 128 ? c.Wo : 128); w++) {
+        if (pow2 && (w & (w - 1)) && w != c.Wo) continue;
+        for (int h = 1; h <= c.Ho && w * h <= 128; h++) {
+          int n = 128 / (w * h);
+          if (n > c.N) n = c.N;
+          const long long tiles = (long long)((c.Wo + w - 1) / w) * ((c.Ho + h - 1) / h) * ((c.N + n - 1) / n);
+          if (best < 0 || tiles < best || (tiles == best && w * h * n > bw * bh * bn)) { best = tiles; bw = w; bh = h; bn = n; }
+        }
+      }
+      if (pow2) {
+        bw = 8;
+        while (bw < c.Wo && bw < 128) bw *= 2;
+        bh = 1;
+        while (bh * 2 * bw <= 128 && bh < c.Ho) bh *= 2;
+        bn = 128 / (bw * bh);
+      }
+    }
     p.conv = 1; p.cin_blocks = c.C / BK; p.ksz = c.k; p.pad = c.pad;
-    p.bw = bw; p.bh = bh; p.bn = bn;
+    p.bw = bw; p.bh = bh; p.bn = bn; p.a_rows = bw * bh * bn;
     p.tiles_w = (c.Wo + bw - 1) / bw; p.tiles_h = (c.Ho + bh - 1) / bh;
     p.Nimg = c.N; p.Ho = c.Ho; p.Wo = c.Wo;
     p.num_kb = c.k * c.k * p.cin_blocks;
@@ -556,9 +873,10 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     ah = &map_2d(g.A.hi, g.A.rows, g.A.kp, BM);
     al = &map_2d(g.A.lo, g.A.rows, g.A.kp, BM);
   }
-  bhp = &map_2d(g.B.hi, g.B.rows, g.B.kp, BN);
-  blp = &map_2d(g.B.lo, g.B.rows, g.B.kp, BN);
+  bhp = &map_2d(g.B.hi, g.B.rows, g.B.kp, BNB);
+  blp = &map_2d(g.B.lo, g.B.rows, g.B.kp, BNB);
   }
+  if (pair) grid.y = (grid.y + 1) & ~1u;            // whole pairs: a padding CTA loads zero-filled tiles and stores nothing
   const CUtensorMap& bh_ = *bhp;
   const CUtensorMap& bl_ = *blp;
   // split-K when the output tiles alone cannot fill the machine (per-timestep decoder GEMMs, weight gradients)
@@ -569,7 +887,9 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   if (ctx.tc_ws && tiles * 2 <= ctx.num_sms && p.num_kb >= 4) {
     splits = (int)(ctx.num_sms / tiles);
     if (splits > p.num_kb / 2) splits = p.num_kb / 2;
-    if (splits > 8) splits = 8;     // consumers of deferred partials sum at most 8 (decb::kMaxSplits)
+    // consumers of deferred partials sum at most 8 (decb::kMaxSplits); the stand-alone reduction takes any number
+    const int cap = g.defer_reduce ? 8 : 16;
+    if (splits > cap) splits = cap;
   }
   if (g.force_splits > 0 && ctx.tc_ws) splits = g.force_splits < p.num_kb ? g.force_splits : p.num_kb;
   float* wsbase = g.ws ? g.ws : ctx.tc_ws;
@@ -585,6 +905,10 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     p.C = wsbase;        // splits == 1 writes the single partial straight into the workspace
   }
   grid.z = p.splits;
+  if (pair) {
+    if (BN == 256) launch2<256>(ctx, *ah, *al, bh_, bl_, p, grid);
+    else launch2<128>(ctx, *ah, *al, bh_, bl_, p, grid);
+  } else
   switch (BN) {
     case 128: launch<128>(ctx, *ah, *al, bh_, bl_, p, grid); break;
     case 64: launch<64>(ctx, *ah, *al, bh_, bl_, p, grid); break;
