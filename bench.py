@@ -109,10 +109,15 @@ def per_gpu_batch(c, world):
 
 def make_inputs(c, rank, world):
     """one synthetic batch per width bucket of the config (all rows of a batch share W, as in the reference)"""
-    from oracle import make_batch
+    # aocr/data.py is plain numpy; it is loaded as a stand-alone module so that the reference arm never imports the
+    # package (and with it the ctypes binding of libaocr.so)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("aocr_data_standalone", os.path.join(ROOT, "torch-attention-ocr_b200", "aocr", "data.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    synthetic_batch = mod.synthetic_batch
     B = per_gpu_batch(c, world)
-    return [make_batch(B, W, c["T"] - 1, seed=SEED + rank + 1000 * i, force_T=c["T"], kind="noise")
-            for i, W in enumerate(c["widths"])]
+    return [synthetic_batch(B, W, c["T"] - 1, seed=SEED + rank + 1000 * i, force_T=c["T"]) for i, W in enumerate(c["widths"])]
 
 
 def oracle_config(c, B):

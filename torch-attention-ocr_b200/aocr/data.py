@@ -39,6 +39,21 @@ def make_batch_from_labels(images, labels, img_paths=None):
             img_paths or [f"synthetic/{i}.png" for i in range(b)]]
 
 
+def synthetic_batch(b, W, max_label_len, seed=910820, force_T=None):
+    """One seeded synthetic batch of the benchmark workloads: i.i.d. uniform gray levels 0..255, labels of
+    1..max_label_len characters over [0-9a-z]; `force_T` pins the target length (the longest label gets force_T - 1
+    characters).  Returns a dict with the arrays of the reference batch tuple."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    images = rng.integers(0, 256, size=(b, 1, 32, W)).astype(np.float32)
+    lens = rng.integers(1, max_label_len + 1, size=b)
+    if force_T is not None:
+        lens[0] = force_T - 1
+        lens = np.minimum(lens, force_T - 1)
+    labels = ["".join(ALPHABET[i] for i in rng.integers(0, 36, size=int(n))) for n in lens]
+    t = make_batch_from_labels(images, labels)
+    return {"images": t[0], "targets": t[1], "targets_eval": t[2], "num_nonzeros": int(t[3]), "labels": labels}
+
+
 class SyntheticDataGen:
     """Width-bucketed synthetic stand-in for DataGen (same nextBatch contract, incl. the final partial flush)."""
 

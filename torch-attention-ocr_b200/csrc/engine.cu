@@ -547,6 +547,7 @@ bool Engine::prep_weights() {
 // CNN forward (src/model/cnn.lua:9-45; called model.lua:285)
 void Engine::cnn_forward(bool train) {
   cnn_train_ = train;
+  mbox_slot_next_ = 0;        // the statistics exchanges of a step use mailbox slots 0, 1, ... in issue order
   const int B = b_;
   const bool tc = cfg.gemm_mode != 2;
   conv1_fwd(ctx_, x0, d_params + L.conv_w[0], d_params + L.conv_b[0], act[1], pidx[1], B, W_, tc ? actp_[1].hi : nullptr,
@@ -639,6 +640,9 @@ void Engine::cnn_backward() {
       col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);     // bias grad (this lane's partial buffer)
       conv_wgrad_tc(dz, act[l], B, Hin, Win, c.cin, c.k, c.pad, Hout, Wout, c.cout, d_grads + L.conv_w[l], &dzp, &actp_[l]);
       if (l == 4 && cnn_bucket_split_ >= 0) grad_range(cnn_bucket_split_, L.goff[G_CNN] + L.gphys[G_CNN]);
+      // conv2..conv4 (+bn3) are complete once this lane has run conv2's weight gradient: their bucket leaves now, so
+      // that only conv1's 640 gradients remain for after the last kernel of the backward
+      if (l == 1 && cnn_bucket_split_ >= 0) grad_range(L.conv_w[1], cnn_bucket_split_);
       use_lane(0);
     } else {
       col_sum(ctx_, dz, rows, c.cout, d_grads + L.conv_b[l], partial, 0);     // bias grad
@@ -670,6 +674,7 @@ void Engine::cnn_backward() {
   }
   const int nblk = 8 * 148;      // ~43 pooled pixels per block at batch 64: the per-thread loop is a chain of dependent loads
   conv1_bwd(ctx_, x0, act[1], pidx[1], dcur, d_grads + L.conv_w[0], d_grads + L.conv_b[0], partial, nblk, B, W_);
+  if (cnn_bucket_split_ >= 0) grad_small(L.goff[G_CNN], L.conv_w[1]);     // conv1: the tail of the gradient exchange
   join_from(2);
 }
 

@@ -212,8 +212,18 @@ class Engine {
   cudaEvent_t comm_ev_[4] = {};
   int comm_ev_next_ = 0;
   bool comm_pending_ = false;
+  // one-shot exchange of the batch-norm statistics through NVLink peer memory (engine_nccl.cu): every rank owns a
+  // mailbox that its peers write into; nullptr = not set up (NCCL all-reduce is used instead)
+  float* mbox_ = nullptr;            // this rank's mailbox (cudaMalloc, exported with cudaIpcGetMemHandle)
+  float** d_peer_mbox_ = nullptr;    // device array [world]: every rank's mailbox as mapped into this process
+  std::vector<void*> peer_mapped_;   // cudaIpcOpenMemHandle mappings to close
+  unsigned* d_mbox_seq_ = nullptr;   // device counters [kMboxSlots]: use count of a slot (its parity picks the buffer half)
+  int mbox_slot_next_ = 0;           // host: slot of the next exchange of the current step (reset at step start)
+  void dp_peer_setup();
+  bool dp_peer_allreduce(float* buf, int64_t n);   // false: mailboxes unavailable / vector too long (caller falls back to NCCL)
   int64_t cnn_bucket_split_ = -1;    // >= 0: cnn_backward issues [split, end of cnn group) as soon as conv5 is done
   void dp_allreduce(float* buf, int64_t n, int kind);
+  void grad_small(int64_t off, int64_t end);
  public:
   void exchange(float* buf, int64_t n, int kind);
  private:

@@ -347,6 +347,12 @@ void Engine::grad_bucket(int first_group, int last_group) {
 void Engine::grad_range(int64_t off, int64_t end) {
   if (cfg.dp_world > 1 && end > off) exchange(d_grads + off, end - off, 1);
 }
+// a short gradient range at the very end of backward: through the peer mailboxes when they exist (one small kernel on the
+// current stream, ~10 us) instead of an NCCL all-reduce queued behind the earlier buckets
+void Engine::grad_small(int64_t off, int64_t end) {
+  if (cfg.dp_world <= 1 || end <= off) return;
+  if (!dp_peer_allreduce(d_grads + off, end - off)) exchange(d_grads + off, end - off, 1);
+}
 void Engine::grad_join() {
   if (cfg.dp_world > 1) exchange(nullptr, 0, 2);
 }
@@ -404,7 +410,6 @@ void Engine::forward_backward_enqueue() {
   join_from(1);                    // encoder (and decoder) weight gradients
   phase_mark("lane_join");
   if (dp && !native) { grad_bucket(G_ENC_FW, G_ENC_BW); grad_bucket(G_CNN, G_CNN); }
-  if (native) grad_range(L.goff[G_CNN], cnn_bucket_split_);
   grad_join();
   phase_report();
   have_grads_ = true;
