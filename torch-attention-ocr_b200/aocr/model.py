@@ -146,11 +146,15 @@ class Model:
             self.log("Error: visualize file %s cannot be created" % self.visualize_path)
             self.visualize, self.visualize_file = False, None
 
-    # model:save(model_path) — model.lua:720-725.  Torch7 serialisation is out of scope (no Torch7 to read it);
-    # the same four items {layers, config, global_step, optim_state} go into one .npz.
+    # model:save(model_path) — model.lua:720-725.  A path ending in ".t7" is written in Torch7's container (the named
+    # tensors of every group, aocr/checkpoint.py; lua/t7_convert.lua rebuilds the reference's module trees from it);
+    # anything else goes into one .npz holding the same four items {layers, config, global_step, optim_state}.
     def save(self, model_path):
         p = self.get_parameters()
         bn = [self.handle.get_bn_stats(i) for i in range(3)]
+        if model_path.endswith(".t7"):
+            from .checkpoint import save_checkpoint
+            return save_checkpoint(model_path, self.config, p, bn, self.global_step, self.optim_state)
         path = model_path if model_path.endswith(".npz") else model_path + ".npz"
         np.savez(path,
                  **{"param_" + g: p[g] for g in GROUPS},
@@ -159,24 +163,35 @@ class Model:
                  optim_state=json.dumps(self.optim_state))
         return path
 
-    # model:load(model_path, config) — model.lua:45-80
+    # model:load(model_path, config) — model.lua:45-80.  ".t7": a reference checkpoint (its five module trees) or the
+    # named-tensor table written by save().
     def load(self, model_path, config=None):
-        path = model_path if model_path.endswith(".npz") else model_path + ".npz"
-        assert os.path.isfile(path), "Model %s does not exist!" % model_path      # model.lua:50
-        ck = np.load(path, allow_pickle=False)
+        if model_path.endswith(".t7"):
+            assert os.path.isfile(model_path), "Model %s does not exist!" % model_path    # model.lua:50
+            from .checkpoint import load_checkpoint
+            ck = load_checkpoint(model_path)
+            saved_cfg, params, bn = ck["config"], ck["params"], ck["bn_stats"]
+            step, opt = ck["global_step"], ck["optim_state"]
+        else:
+            path = model_path if model_path.endswith(".npz") else model_path + ".npz"
+            assert os.path.isfile(path), "Model %s does not exist!" % model_path      # model.lua:50
+            z = np.load(path, allow_pickle=False)
+            saved_cfg, step, opt = json.loads(str(z["config"])), int(z["global_step"]), json.loads(str(z["optim_state"]))
+            params = {g: z["param_" + g] for g in GROUPS}
+            bn = [(z["bn%d_mean" % i], z["bn%d_var" % i]) for i in range(3)]
         c = dict(_DEFAULTS)
-        c.update(json.loads(str(ck["config"])))
+        c.update(saved_cfg)
         for k in ("max_encoder_l", "max_decoder_l", "batch_size", "prealloc"):    # model.lua:71-74
             if config and k in config:
                 c[k] = config[k]
         self.config = c
-        self.global_step = int(ck["global_step"])
-        self.optim_state = json.loads(str(ck["optim_state"]))
+        self.global_step = int(step)
+        self.optim_state = dict(opt) if opt else {"learningRate": c.get("learning_rate", 0.1)}
         self._build()
         for i, g in enumerate(GROUPS):
-            self.handle.set_params(i, ck["param_" + g])
+            self.handle.set_params(i, params[g])
         for i in range(3):
-            self.handle.set_bn_stats(i, ck["bn%d_mean" % i], ck["bn%d_var" % i])
+            self.handle.set_bn_stats(i, bn[i][0], bn[i][1])
         return self
 
     # model:shutdown() — model.lua:727-731
