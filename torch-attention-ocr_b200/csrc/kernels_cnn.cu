@@ -133,16 +133,24 @@ __global__ void __launch_bounds__(256) conv1_bwd_partial_kernel(const float* __r
       partial[((int64_t)blockIdx.x * 10 + i) * 64 + c] = red[0][i][c] + red[1][i][c] + red[2][i][c] + red[3][i][c];
   }
 }
-__global__ void conv1_bwd_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw,
-                                       float* __restrict__ db) {
+// folds the per-block partials in a fixed order: block i (0..9: nine taps + bias), 64 channel lanes x 16 block lanes,
+// each thread sums every 16th partial (coalesced over channels), then the 16 lane sums are added in order
+__global__ void __launch_bounds__(1024) conv1_bwd_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ dw,
+                                                               float* __restrict__ db) {
   pdl_launch_dependents();
   pdl_wait();
-  int e = blockIdx.x * blockDim.x + threadIdx.x;   // 640 outputs
-  if (e >= 640) return;
-  int i = e / 64, c = e % 64;
+  __shared__ float red[16][64];
+  const int i = blockIdx.x, c = threadIdx.x % 64, lane = threadIdx.x / 64;
   float s = 0.f;
-  for (int b = 0; b < nblk; b++) s += partial[((int64_t)b * 10 + i) * 64 + c];
-  if (i < 9) dw[c * 9 + i] += s; else db[c] += s;
+  for (int b = lane; b < nblk; b += 16) s += partial[((int64_t)b * 10 + i) * 64 + c];
+  red[lane][c] = s;
+  __syncthreads();
+  if (lane == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; l++) t += red[l][c];
+    if (i < 9) dw[c * 9 + i] += t; else db[c] += t;
+  }
 }
 
 // ------------------------------------------------------------------ ReLU + max-pool
@@ -492,7 +500,7 @@ void conv1_bwd(Ctx& ctx, const float* x, const float* a1, const uint8_t* idx, co
   int64_t per = (npix + nblk - 1) / nblk;
   launch_pdl(ctx, conv1_bwd_partial_kernel, dim3(nblk), dim3(256), 0, x, a1, idx, da1, partial, B, W, per);
   AOCR_CUDA(cudaGetLastError());
-  launch_pdl(ctx, conv1_bwd_final_kernel, dim3(cdiv(640, 128)), dim3(128), 0, partial, nblk, dw, db);
+  launch_pdl(ctx, conv1_bwd_final_kernel, dim3(10), dim3(1024), 0, partial, nblk, dw, db);
   AOCR_CUDA(cudaGetLastError());
 }
 

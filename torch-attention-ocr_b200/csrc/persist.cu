@@ -26,6 +26,15 @@ namespace aocr { __device__ unsigned long long g_bt[16]; __device__ int g_bt_on 
     }                                                                                       \
   } while (0)
 
+#define AOCR_BT_T(i, t)                                                                     \
+  do {                                                                                      \
+    if (aocr::g_bt_on && blockIdx.x == 0 && threadIdx.x == (t)) {                           \
+      unsigned long long _t;                                                                \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(_t));                                 \
+      aocr::g_bt[i] = _t;                                                                   \
+    }                                                                                       \
+  } while (0)
+
 #include "dec_bodies.cuh"
 #include "tc_ptx.cuh"
 
@@ -336,6 +345,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
             cell_preload<BN>(*reinterpret_cast<const CellFwdTc*>(scmd.payload + sizeof(PGemm)), mt, z, g.splits, pre);
         }
       }
+      if (fused) AOCR_BT(11);
       if (tl.has) {
         const int kb_begin = tl.kb_begin, nkb = tl.nkb;
         const int m0 = mt * BM;
@@ -387,6 +397,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
           const int q = warp & 3;
           mbar_wait(tmem_full_bar, tiles & 1u);
           tc_fence_after();
+          if (fused) AOCR_BT_T(12, 64);
           const int row = m0 + q * 32 + lane;                 // weight row = output column of the (batch x M) result
           float* outp = g.ws + (long long)z * g.part_stride;
 #pragma unroll 1
@@ -412,6 +423,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
             }
           }
           tc_fence_before();
+          if (fused) AOCR_BT_T(13, 64);
         }
         it += (uint32_t)nkb;
         tiles += 1;
@@ -419,6 +431,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
       if (fused) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();                                       // every rank's partial tile is in its shared memory
+        AOCR_BT(14);
         if (tl.has) {
           if constexpr ((kSet & bit(P_GEMM_ENC_FWD)) != 0) {
             if (type == P_GEMM_ENC_FWD)
@@ -431,6 +444,7 @@ persist_kernel(const PCmd* __restrict__ cmds, int ncmds, const CUtensorMap* __re
                                  pre);
           }
         }
+        AOCR_BT(15);
         // no second cluster barrier: the grid barrier that ends the command orders the peers' reads of this CTA's
         // partial before anything reuses the B ring
       }
@@ -769,7 +783,9 @@ void persist_free(PersistProgram& prog) {
     if (cudaMemcpyFromSymbol(bt, g_bt, sizeof(bt)) == cudaSuccess) {
       fprintf(stderr, "[body stamps, last call, CTA 0] attn_du:");
       for (int i = 1; i <= 5; i++) fprintf(stderr, " %d->%d %.2fus", i - 1, i, (double)(bt[i] - bt[i - 1]) / 1e3);
-      fprintf(stderr, " | enc_cell_bwd: loads %.2fus compute+stores %.2fus\n", (double)(bt[9] - bt[8]) / 1e3, (double)(bt[10] - bt[9]) / 1e3);
+      fprintf(stderr, " | enc_cell_bwd: loads %.2fus compute+stores %.2fus", (double)(bt[9] - bt[8]) / 1e3, (double)(bt[10] - bt[9]) / 1e3);
+      fprintf(stderr, " | fused GEMM->cell: start->accumulator ready %.2fus, ->staged %.2fus, ->cluster barrier %.2fus, ->cell done %.2fus\n",
+              (double)(bt[12] - bt[11]) / 1e3, (double)(bt[13] - bt[12]) / 1e3, (double)(bt[14] - bt[13]) / 1e3, (double)(bt[15] - bt[14]) / 1e3);
     }
     cudaFree(prog.d_trace); prog.d_trace = nullptr;
   }
