@@ -225,6 +225,11 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   // side lanes (lane 0 = the members above)
   if (const char* e = getenv("AOCR_LANES")) lanes_on_ = atoi(e) != 0;
   for (int i = 0; i < 8; i++) AOCR_CUDA(cudaEventCreateWithFlags(&lane_ev_[i], cudaEventDisableTiming));
+  if (const char* e = getenv("AOCR_EARLY_UPDATE")) early_update_on_ = atoi(e) != 0;
+  if (lanes_on_) {
+    AOCR_CUDA(cudaStreamCreateWithFlags(&upd_st_, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) AOCR_CUDA(cudaEventCreateWithFlags(&upd_ev_[i], cudaEventDisableTiming));
+  }
   lanes_[0].st = ctx_.st; lanes_[0].tc_ws = ctx_.tc_ws; lanes_[0].scratch[0] = scratch_[0]; lanes_[0].scratch[1] = scratch_[1];
   lanes_[0].partial = partial; lanes_[0].tmpvec = tmpvec;
   for (int i = 1; i < 3; i++) {
@@ -279,6 +284,8 @@ Engine::~Engine() {
   for (int i = 1; i < 3; i++)
     if (lanes_on_ && lanes_[i].st) { cudaStreamSynchronize(lanes_[i].st); cudaStreamDestroy(lanes_[i].st); }
   for (int i = 0; i < 8; i++) if (lane_ev_[i]) cudaEventDestroy(lane_ev_[i]);
+  if (upd_st_) { cudaStreamSynchronize(upd_st_); cudaStreamDestroy(upd_st_); }
+  for (int i = 0; i < 4; i++) if (upd_ev_[i]) cudaEventDestroy(upd_ev_[i]);
   for (void* p : allocs_) cudaFree(p);
   if (d_trie_) cudaFree(d_trie_);
   if (ev0_) cudaEventDestroy(ev0_);

@@ -224,6 +224,18 @@ class Engine {
   int64_t cnn_bucket_split_ = -1;    // >= 0: cnn_backward issues [split, end of cnn group) as soon as conv5 is done
   void dp_allreduce(float* buf, int64_t n, int kind);
   void grad_small(int64_t off, int64_t end);
+  // optional: per-group clip + SGD as soon as a group's gradients are final (a training step only: aocr_train_step): the
+  // update of the decoder / projector / encoder groups (97 MB of the 119 MB) runs on its own stream under the CNN
+  // backward, so only the CNN group is left for after the last kernel
+  cudaStream_t upd_st_ = nullptr;
+  cudaEvent_t upd_ev_[4] = {};
+  int upd_ev_next_ = 0;
+  unsigned updated_mask_ = 0;        // groups already updated in this step
+  bool fused_update_ = false, upd_pending_ = false;
+  bool early_update_on_ = false;     // AOCR_EARLY_UPDATE=1 enables.  Measured at config 2 / 4: no gain (3.99 vs 3.98 ms, 9.27 vs 9.28): the
+                                     // update's 0.4 GB of HBM traffic slows the CNN backward it overlaps by what the tail saves
+  void early_update(int g_first, int g_last, cudaStream_t after);
+  void sgd_subset(Ctx& c, unsigned mask);
  public:
   void exchange(float* buf, int64_t n, int kind);
  private:

@@ -399,12 +399,22 @@ void Engine::forward_backward_enqueue() {
   // so lane 0 never waits for the time-batched weight gradients of lane 1; the CNN bucket is split so that only the
   // small conv1-4 tail is exposed after the last kernel.  Hook flavour: the host runtime orders on lane 0's stream.
   const bool dp = cfg.dp_world > 1, native = dp && dp_native();
+  // [proj | decoder] are adjacent in the flat buffer but not as group numbers (decoder 3, projector 4): two masks
   if (dp) {
-    if (native) { use_lane(1); grad_bucket(G_PROJ, G_DEC); use_lane(0); }
-    else { join_from(1); grad_bucket(G_PROJ, G_DEC); }
+    if (native) {
+      use_lane(1); grad_bucket(G_PROJ, G_DEC); use_lane(0);
+      early_update(G_DEC, G_PROJ, comm_st_);
+    } else { join_from(1); grad_bucket(G_PROJ, G_DEC); }
+  } else {
+    early_update(G_DEC, G_PROJ, lanes_[1].st);
   }
   cnn_bucket_split_ = native ? L.conv_w[4] : -1;      // conv5..conv7 (+BN) complete after the conv5 iteration
-  if (native) { use_lane(1); grad_bucket(G_ENC_FW, G_ENC_BW); use_lane(0); }   // all encoder gradients are lane-1 work
+  if (native) {                                       // all encoder gradients are lane-1 work
+    use_lane(1); grad_bucket(G_ENC_FW, G_ENC_BW); use_lane(0);
+    early_update(G_ENC_FW, G_ENC_BW, comm_st_);
+  } else if (!dp) {
+    early_update(G_ENC_FW, G_ENC_BW, lanes_[1].st);
+  }
   cnn_backward();
   phase_mark("cnn_bwd");
   join_from(1);                    // encoder (and decoder) weight gradients
@@ -455,14 +465,42 @@ void Engine::sgd_enqueue(double lr, double clip) {
   set_lr_clip(lr, clip);
   sgd_enqueue_kernels();
 }
-void Engine::sgd_enqueue_kernels() {
+void Engine::sgd_subset(Ctx& c, unsigned mask) {
   SgdGroups G;
   for (int g = 0; g < 5; g++) {
     G.off[g] = L.goff[g]; G.n[g] = L.gphys[g];
     int64_t nb = L.gphys[g] / 16384 + 1;          // ~16k floats per block and pass
-    G.nb[g] = (int)(nb < 1024 ? nb : 1024);
+    G.nb[g] = (mask >> g) & 1u ? (int)(nb < 1024 ? nb : 1024) : 0;      // 0 blocks: the group is not touched
   }
-  sgd_groups(ctx_, d_params, d_grads, G, d_sq_partial, d_sumsq, d_lrclip);
+  sgd_groups(c, d_params, d_grads, G, d_sq_partial, d_sumsq, d_lrclip);
+}
+// Groups [g_first, g_last] are final once everything enqueued so far on stream `after` has run (the lane that computed
+// their weight gradients, or the communication stream behind their all-reduce): clip + SGD of those groups on the update
+// stream, concurrently with the rest of backward.  Nothing downstream reads their fp32 master parameters any more (the
+// recurrences and their weight gradients run on operand planes built at the start of the step).
+void Engine::early_update(int g_first, int g_last, cudaStream_t after) {
+  if (!fused_update_ || !early_update_on_ || !lanes_on_ || !upd_st_) return;
+  cudaEvent_t ev = upd_ev_[upd_ev_next_++ % 3];
+  AOCR_CUDA(cudaEventRecord(ev, after));
+  AOCR_CUDA(cudaStreamWaitEvent(upd_st_, ev, 0));
+  unsigned mask = 0;
+  for (int g = g_first; g <= g_last; g++) mask |= 1u << g;
+  Ctx c = ctx_;
+  c.st = upd_st_;
+  sgd_subset(c, mask);
+  ctx_.launches = c.launches;
+  updated_mask_ |= mask;
+  upd_pending_ = true;
+}
+void Engine::sgd_enqueue_kernels() {
+  if (upd_pending_) {            // the early updates join the main stream
+    AOCR_CUDA(cudaEventRecord(upd_ev_[3], upd_st_));
+    AOCR_CUDA(cudaStreamWaitEvent(ctx_.st, upd_ev_[3], 0));
+    upd_pending_ = false;
+  }
+  const unsigned rest = 0x1fu & ~updated_mask_;
+  updated_mask_ = 0;
+  if (rest) sgd_subset(ctx_, rest);
   mark_weights_dirty();
 }
 
@@ -475,6 +513,7 @@ void Engine::sgd_enqueue_kernels() {
 void Engine::train_step_enqueue(double lr, double clip) {
   const bool eligible = graphs_on_ && (cfg.dp_world <= 1 || dp_native()) && !prof_on && !phases_on_;
   set_lr_clip(lr, clip);           // outside any capture: one graph per shape serves every learning rate
+  struct FusedScope { bool& f; FusedScope(bool& x) : f(x) { f = true; } ~FusedScope() { f = false; } } fused_scope(fused_update_);
   if (!eligible) {
     forward_backward_enqueue();
     sgd_enqueue_kernels();

@@ -773,8 +773,8 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   if (g.mn && BN < 64) BN = 64;                     // MN-major boxes are 64 elements wide
   if (g.mn == 2 && g.conv && g.conv->C < 128) BN = 64;   // an N tile must not straddle two filter taps
   // CTA-pair kernel (256 x BN tiles, cta_group::2): whenever there are at least two M tiles and N fills a 128-wide tile
-  static const bool pair_on = !(getenv("AOCR_CG2") && atoi(getenv("AOCR_CG2")) == 0);
-  static const int pair_maxbn = getenv("AOCR_CG2_BN") ? atoi(getenv("AOCR_CG2_BN")) : 256;
+  const bool pair_on = !(getenv("AOCR_CG2") && atoi(getenv("AOCR_CG2")) == 0);      // read per call: an A/B switch
+  const int pair_maxbn = getenv("AOCR_CG2_BN") ? atoi(getenv("AOCR_CG2_BN")) : 256;
   bool pair = pair_on && BN == 128 && g.M > BM && !(g.dbg);
   if (pair && pair_maxbn >= 256 && g.N >= 256 && (g.mn != 2 || g.conv->C % 256 == 0)) BN = 256;
   const int BNB = pair ? BN / 2 : BN;               // B rows one CTA loads
@@ -839,7 +839,7 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     // (100 of 128); rows past the box are never written by TMA and never stored by the epilogue.
     int bw = 1, bh = 1, bn = 1;
     {
-      static const bool pow2 = getenv("AOCR_BOX_POW2") && atoi(getenv("AOCR_BOX_POW2"));
+      const bool pow2 = getenv("AOCR_BOX_POW2") && atoi(getenv("AOCR_BOX_POW2"));
       long long best = -1;
       for (int w = 1; w <= (c.Wo < 128 ? c.Wo : 128); w++) {
         if (pow2 && (w & (w - 1)) && w != c.Wo) continue;

@@ -603,6 +603,7 @@ __global__ void __launch_bounds__(256) sumsq_final_groups_kernel(const double* _
   pdl_wait();
   __shared__ double red[256];
   const int g = blockIdx.x;
+  if (G.nb[g] == 0) return;          // group not part of this update: leave its sum alone
   double s = 0.0;
   for (int i = threadIdx.x; i < G.nb[g]; i += 256) s += partial[g * 1024 + i];
   red[threadIdx.x] = s;
