@@ -52,3 +52,16 @@ def test_target_as_long_as_max_decoder_l():
     batch = _with_labels(make_batch(2, 44, 5, seed=53), ["abcdef", "xy"])     # GO + 6 chars = 7 inputs
     assert batch["targets"].shape[1] == 7
     _check(cfg, batch)
+
+
+@pytest.mark.parametrize("B,W", [(5, 106), (7, 50), (3, 210), (66, 102)])
+def test_ragged_widths_and_batches(B, W):
+    """widths whose halves / quarters are odd (floor-mode pooling drops a column: W = 106 -> 53 -> 26, W = 50 -> 25 -> 12,
+    W = 102 -> 51 -> 25) and batch sizes that divide no pixel box evenly: the implicit-GEMM convolutions tile their output
+    with TMA boxes chosen per shape (partial boxes at the right / bottom / last-image edge, CTA pairs padded to even
+    counts, exact contraction covers falling back to power-of-two boxes), DESIGN.md 5.1"""
+    S = (W // 2) // 2 - 1
+    cfg = Config(batch_size=B, max_encoder_l=S + 2, max_decoder_l=8)
+    batch = make_batch(B, W, 5, seed=60 + B)
+    out, _ = train_parity(cfg, batch, gemm_mode=0)
+    check_train(out, gemm_mode=0)

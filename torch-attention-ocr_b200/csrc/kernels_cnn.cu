@@ -32,55 +32,71 @@ __device__ __forceinline__ void split_store4(__nv_bfloat16* phi, __nv_bfloat16* 
   *reinterpret_cast<uint2*>(plo + i) = *reinterpret_cast<uint2*>(l);
 }
 
+// One thread = one pooled pixel x 16 output channels: the 4 x 4 input patch is loaded once (not once per channel), the
+// four conv outputs of the pooling window are formed per channel from weights in shared memory, and the 16 results leave
+// as 16-byte stores (fp32, the two bf16 planes, the pooling choice).  The four threads of a pixel are adjacent.
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ a1,
                                                         uint8_t* __restrict__ idx, int B, int W, __nv_bfloat16* __restrict__ phi,
                                                         __nv_bfloat16* __restrict__ plo) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float ws[64 * 9];
+  __shared__ float ws[9][68];          // [tap][channel group * 17 + k]: the four groups of a warp hit distinct banks
   __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) ws[i % 9][((i / 9) >> 4) * 17 + ((i / 9) & 15)] = w[i];
   if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const int W1 = W / 2;
-  const int64_t total = (int64_t)B * 16 * W1 * 64;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(e % 64);
-    int64_t r = e / 64;
-    int pw = (int)(r % W1); r /= W1;
-    int ph = (int)(r % 16);
-    int n = (int)(r / 16);
+  const int64_t total = (int64_t)B * 16 * W1 * 4;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t & 3);
+    int64_t r = t >> 2;
+    const int pw = (int)(r % W1); r /= W1;
+    const int ph = (int)(r % 16);
+    const int n = (int)(r / 16);
     const float* xi = x + (int64_t)n * 32 * W;
     float p[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      int h = 2 * ph - 1 + i;
+      const int h = 2 * ph - 1 + i;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        int ww = 2 * pw - 1 + j;
+        const int ww = 2 * pw - 1 + j;
         float v = 0.f;
-        if (h >= 0 && h < 32 && ww >= 0 && ww < W) v = (xi[h * W + ww] - 128.0f) * (1.0f / 128.0f);
+        if (h >= 0 && h < 32 && ww >= 0 && ww < W) v = (__ldg(xi + h * W + ww) - 128.0f) * (1.0f / 128.0f);
         p[i][j] = v;
       }
     }
-    float best = -1.f;
-    int bi = 0;
+    const int64_t e0 = (t >> 2) * 64 + cg * 16;            // first of this thread's 16 consecutive output elements
+    float outv[16];
+    uint32_t packed_idx[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int dy = 0; dy < 2; dy++)
+    for (int k = 0; k < 16; k++) {
+      const int c = cg * 16 + k;
+      float best = -1.f;
+      int bi = 0;
 #pragma unroll
-      for (int dx = 0; dx < 2; dx++) {
-        float s = bs[c];
+      for (int dy = 0; dy < 2; dy++)
 #pragma unroll
-        for (int kh = 0; kh < 3; kh++)
+        for (int dx = 0; dx < 2; dx++) {
+          float sacc = bs[c];
 #pragma unroll
-          for (int kw = 0; kw < 3; kw++) s = fmaf(ws[c * 9 + kh * 3 + kw], p[dy + kh][dx + kw], s);
-        s = fmaxf(s, 0.f);
-        if (s > best) { best = s; bi = dy * 2 + dx; }
-      }
-    a1[e] = best;
-    idx[e] = (uint8_t)bi;
-    split_store1(phi, plo, e, best);
+          for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+            for (int kw = 0; kw < 3; kw++) sacc = fmaf(ws[kh * 3 + kw][cg * 17 + k], p[dy + kh][dx + kw], sacc);
+          sacc = fmaxf(sacc, 0.f);
+          if (sacc > best) { best = sacc; bi = dy * 2 + dx; }
+        }
+      outv[k] = best;
+      packed_idx[k >> 2] |= (uint32_t)bi << (8 * (k & 3));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const float4 v = make_float4(outv[4 * q], outv[4 * q + 1], outv[4 * q + 2], outv[4 * q + 3]);
+      *reinterpret_cast<float4*>(a1 + e0 + 4 * q) = v;
+      split_store4(phi, plo, e0 + 4 * q, v);
+    }
+    *reinterpret_cast<uint4*>(idx + e0) = make_uint4(packed_idx[0], packed_idx[1], packed_idx[2], packed_idx[3]);
   }
 }
 
@@ -489,7 +505,7 @@ void col_reduce(Ctx& ctx, const float* z, const float* z2, const float* mean, co
 
 void conv1_fwd(Ctx& ctx, const float* x, const float* w, const float* bias, float* a1, uint8_t* idx, int B, int W,
                __nv_bfloat16* phi, __nv_bfloat16* plo) {
-  int64_t total = (int64_t)B * 16 * (W / 2) * 64;
+  int64_t total = (int64_t)B * 16 * (W / 2) * 4;          // one thread per pooled pixel and 16 channels
   launch_pdl(ctx, conv1_fwd_kernel, dim3(grid_for(total, 256, ctx.num_sms)), dim3(256), 0, x, w, bias, a1, idx, B, W, phi, plo);
   AOCR_CUDA(cudaGetLastError());
 }
