@@ -87,7 +87,7 @@ constexpr size_t kMboxWords = (size_t)2 * kMboxSlots * kMboxMaxWorld * kMboxMaxN
 
 __global__ void __launch_bounds__(1024) peer_allreduce_kernel(float* __restrict__ buf, int n, int rank, int world,
                                                               float* const* __restrict__ peers, unsigned* __restrict__ seqctr,
-                                                              int slot) {
+                                                              int slot, unsigned long long timeout_ns) {
   __shared__ unsigned seq_s;
   const int tid = threadIdx.x;
   if (tid == 0) seq_s = ++seqctr[slot];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(1024) peer_allreduce_kernel(float* __restrict_
       if (v != seq) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) {     // 20 s: a peer is gone; fail the launch instead of hanging the device
+        if (t1 - t0 > timeout_ns) {         // a peer is gone: fail the launch instead of hanging the device for ever
           printf("[aocr] peer statistics exchange timed out (rank %d waits for rank %d, slot %d, seq %u, saw %u)\n", rank, tid, slot, seq, v);
           __trap();
         }
@@ -240,7 +240,12 @@ void Engine::dp_shutdown() {
 
 bool Engine::dp_peer_allreduce(float* buf, int64_t n) {
   if (!mbox_ || n > kMboxMaxN || mbox_slot_next_ >= kMboxSlots) return false;
-  peer_allreduce_kernel<<<1, 1024, 0, ctx_.st>>>(buf, (int)n, cfg.dp_rank, cfg.dp_world, d_peer_mbox_, d_mbox_seq_, mbox_slot_next_++);
+  // ranks may reach an exchange far apart (one of them saving a checkpoint, loading data): wait as long as a collective
+  // library's watchdog would (10 minutes; AOCR_DP_PEER_TIMEOUT_S overrides), then fail the launch
+  static const unsigned long long timeout_ns =
+      (unsigned long long)(getenv("AOCR_DP_PEER_TIMEOUT_S") ? atof(getenv("AOCR_DP_PEER_TIMEOUT_S")) : 600.0) * 1000000000ull;
+  peer_allreduce_kernel<<<1, 1024, 0, ctx_.st>>>(buf, (int)n, cfg.dp_rank, cfg.dp_world, d_peer_mbox_, d_mbox_seq_, mbox_slot_next_++,
+                                                 timeout_ns);
   AOCR_LAUNCH_CHECK(ctx_);
   return true;
 }
