@@ -42,7 +42,7 @@ struct PersistProgram {                 // host-side, then uploaded
   std::vector<PCmd> cmds;
   std::vector<CUtensorMap> maps;
   int grid = 1;                         // CTAs (>= the largest number of GEMM tiles of any command)
-  int bn = 64;                          // UMMA N = batch rounded up to {16,32,64,128}
+  int bn = 64;                          // UMMA N = batch rounded up to {16,32,64,128,256}
   int cluster = 1;                      // thread-block cluster size of the launch (grid is a multiple of it)
   // device copies
   PCmd* d_cmds = nullptr;
