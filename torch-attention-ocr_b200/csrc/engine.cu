@@ -192,7 +192,8 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   col = alloc<float>(B * W1 * 18432);
   gA = alloc<float>(B * 16 * W1 * 128);
   gB = alloc<float>(B * 16 * W1 * 128);
-  partial = alloc<float>((int64_t)256 * 8192);
+  partial = alloc<float>(kPartialFloats);
+  AOCR_CUDA(cudaMemset(partial, 0, (size_t)kPartialFloats * sizeof(float)));      // arrival counters in its tail start at 0
   tmpvec = alloc<float>(8192);
   if (cfg.gemm_mode != 2) {
     ctx_.tc_ws_floats = (int64_t)32 * 148 * 128 * 128;
@@ -235,7 +236,8 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   for (int i = 1; i < 3; i++) {
     if (!lanes_on_) { lanes_[i] = lanes_[0]; continue; }
     AOCR_CUDA(cudaStreamCreateWithFlags(&lanes_[i].st, cudaStreamNonBlocking));
-    lanes_[i].partial = alloc<float>((int64_t)256 * 8192);
+    lanes_[i].partial = alloc<float>(kPartialFloats);
+    AOCR_CUDA(cudaMemset(lanes_[i].partial, 0, (size_t)kPartialFloats * sizeof(float)));
     lanes_[i].tmpvec = alloc<float>(8192);
     if (cfg.gemm_mode != 2) {
       lanes_[i].tc_ws = alloc<float>(ctx_.tc_ws_floats);

@@ -23,6 +23,11 @@ void relu_pool_bwd(Ctx&, const float* da, const float* a, const uint8_t* idx, fl
 void im2col(Ctx&, const float* a, float* col, int B, int H, int Wi, int C, int k, int pad);
 // column statistics of z (R,C): sum and (two-pass) centred sum of squares; deterministic.
 void col_sum(Ctx&, const float* z, int64_t R, int C, float* out /*[C]*/, float* partial, int accumulate);
+// Scratch of the column reductions: `partial` buffers hold kPartialFloats floats; their last kSlabCounters words are the
+// arrival counters of the "last slab block finalises" reductions (one per block of 32 columns; zero at allocation,
+// self-resetting), one buffer per lane.
+constexpr int64_t kPartialFloats = (int64_t)256 * 8192;
+constexpr int kSlabCounters = 1024;
 // cross-rank summation hook for batch-norm statistics (data parallelism); world == 1: unused
 // grows: global rows / local rows of a batch-norm reduction (= global batch / this rank's batch; the shards need not be equal)
 struct StatSync { void (*fn)(void* user, float* buf, int64_t n) = nullptr; void* user = nullptr; int world = 1; double grows = 1.0; };

@@ -253,12 +253,33 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ a
 }
 
 // ------------------------------------------------------------------ column reductions over (R, C)
+// Two-stage reductions in ONE launch: every slab block writes its partial sums, the block that arrives LAST at the
+// counter of its column block (blockIdx.x) folds the partials in slab order 0..n-1 - the order, and therefore the bits,
+// of the former second kernel - and resets the counter for the next launch.
+__device__ __forceinline__ unsigned* slab_counters(float* partial) {
+  return reinterpret_cast<unsigned*>(partial + kPartialFloats - kSlabCounters);
+}
+__device__ __forceinline__ bool last_slab_block(float* partial) {
+  __shared__ int s_last;
+  __threadfence();                 // this block's partials are visible device-wide before it is counted
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ctr = slab_counters(partial) + blockIdx.x;
+    const unsigned t = atomicAdd(ctr, 1u);
+    s_last = (t == gridDim.y - 1);
+    if (s_last) *ctr = 0;          // everyone has passed: ready for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
 // mode 0: sum z ; mode 1: sum (z-mean)^2 ; mode 2: sum z*xhat where xhat=(z2-mean)*inv  (z = dy)
 // grid (C/32, nslab); block 32 x 8: each thread walks rows r = slab*rows_per + ty, += 8
 __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict__ z, const float* __restrict__ z2,
                                                          const float* __restrict__ mean, const float* __restrict__ var,
                                                          int64_t R, int C, int64_t rows_per, int mode,
-                                                         float* __restrict__ partial) {
+                                                         float* __restrict__ partial, float scale, int accumulate,
+                                                         float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
@@ -285,12 +306,24 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
     for (int i = 0; i < 8; i++) s += red[i][tx];
     partial[(int64_t)blockIdx.y * C + c] = s;
   }
+  if (!last_slab_block(partial)) return;
+  if (ty == 0 && c < C) {          // out[c] (op)= scale * sum over slabs, fixed order
+    float s = 0.f;
+    for (int i = 0; i < (int)gridDim.y; i++) s += __ldcg(partial + (int64_t)i * C + c);
+    s *= scale;
+    out[c] = accumulate ? out[c] + s : s;
+  }
 }
 // batch-norm forward statistics in ONE pass: s1 = sum (z - k), s2 = sum (z - k)^2 with the shift k = running mean
 // (identical on every data-parallel rank, and close to the batch mean after a few steps: no cancellation in
 // s2/R - (s1/R)^2).  partial: [2][nslab][C]
+// single device (fin != 0): the last block also forms mean / biased variance and updates the running statistics for its
+// columns (the work of bn_finalize_kernel); under data parallelism it writes the local sums for the exchange.
 __global__ void __launch_bounds__(256) col_reduce_bn_fwd_kernel(const float* __restrict__ z, const float* __restrict__ shift,
-                                                                int64_t R, int C, int64_t rows_per, float* __restrict__ partial) {
+                                                                int64_t R, int C, int64_t rows_per, float* __restrict__ partial,
+                                                                float* __restrict__ sums, int fin, float invR, float unbias,
+                                                                float* __restrict__ mean, float* __restrict__ var,
+                                                                float* __restrict__ rmean, float* __restrict__ rvar) {
   pdl_launch_dependents();
   pdl_wait();
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
@@ -315,6 +348,24 @@ __global__ void __launch_bounds__(256) col_reduce_bn_fwd_kernel(const float* __r
     for (int i = 0; i < 8; i++) s += red[ty][i][tx];
     partial[((int64_t)ty * gridDim.y + blockIdx.y) * C + c] = s;
   }
+  if (!last_slab_block(partial)) return;
+  if (ty < 2 && c < C) {
+    float s = 0.f;
+    for (int i = 0; i < (int)gridDim.y; i++) s += __ldcg(partial + ((int64_t)ty * gridDim.y + i) * C + c);
+    sums[ty * C + c] = s;
+    red[ty][0][tx] = s;
+  }
+  if (!fin) return;
+  __syncthreads();
+  if (ty == 0 && c < C) {          // bn_finalize_kernel, for this block's 32 columns
+    const float k = rmean[c];
+    const float m1 = red[0][0][tx] * invR, m2 = red[1][0][tx] * invR;
+    const float mu = k + m1;
+    const float v = fmaxf(m2 - m1 * m1, 0.f);
+    mean[c] = mu; var[c] = v;
+    rmean[c] = 0.9f * k + 0.1f * mu;
+    rvar[c] = 0.9f * rvar[c] + 0.1f * v * unbias;
+  }
 }
 // mean / biased variance from the (globally summed) shifted sums, and the running-statistics update (momentum 0.1,
 // unbiased variance) in the same kernel
@@ -335,7 +386,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float 
 // both batch-norm backward sums in one pass over dy and z: s1 = sum dy, s2 = sum dy * xhat.  partial: [2][nslab][C]
 __global__ void __launch_bounds__(256) col_reduce_bn_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                                 const float* __restrict__ mean, const float* __restrict__ var,
-                                                                int64_t R, int C, int64_t rows_per, float* __restrict__ partial) {
+                                                                int64_t R, int C, int64_t rows_per, float* __restrict__ partial,
+                                                                float* __restrict__ out1, float* __restrict__ out2) {
   pdl_launch_dependents();
   pdl_wait();
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
@@ -360,31 +412,13 @@ __global__ void __launch_bounds__(256) col_reduce_bn_bwd_kernel(const float* __r
     for (int i = 0; i < 8; i++) s += red[ty][i][tx];
     partial[((int64_t)ty * gridDim.y + blockIdx.y) * C + c] = s;
   }
+  if (!last_slab_block(partial)) return;
+  if (ty < 2 && c < C) {
+    float s = 0.f;
+    for (int i = 0; i < (int)gridDim.y; i++) s += __ldcg(partial + ((int64_t)ty * gridDim.y + i) * C + c);
+    (ty ? out2 : out1)[c] = s;
+  }
 }
-__global__ void col_reduce_final2_kernel(const float* __restrict__ partial, int nslab, int C, float* __restrict__ out1,
-                                         float* __restrict__ out2) {
-  pdl_launch_dependents();
-  pdl_wait();
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
-  const int which = c / C, cc = c % C;
-  float s = 0.f;
-  for (int i = 0; i < nslab; i++) s += partial[((int64_t)which * nslab + i) * C + cc];
-  (which ? out2 : out1)[cc] = s;
-}
-// out[c] (op)= scale * sum_slab partial ; op: 0 set, 1 add
-__global__ void col_reduce_final_kernel(const float* __restrict__ partial, int nslab, int C, float scale, int accumulate,
-                                        float* __restrict__ out) {
-  pdl_launch_dependents();
-  pdl_wait();
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int i = 0; i < nslab; i++) s += partial[(int64_t)i * C + c];
-  s *= scale;
-  out[c] = accumulate ? out[c] + s : s;
-}
-
 __global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var,
                                          float* __restrict__ rmean, float* __restrict__ rvar, int C, float unbias) {
   pdl_launch_dependents();
@@ -495,9 +529,8 @@ void col_reduce(Ctx& ctx, const float* z, const float* z2, const float* mean, co
   int ns = nslabs_for(R, ctx.num_sms, C);
   int64_t rows_per = (R + ns - 1) / ns;
   dim3 grid(cdiv(C, 32), ns);
-  launch_pdl(ctx, col_reduce_kernel, dim3(grid), dim3(256), 0, z, z2, mean, var, R, C, rows_per, mode, partial);
-  AOCR_CUDA(cudaGetLastError());
-  launch_pdl(ctx, col_reduce_final_kernel, dim3(cdiv(C, 128)), dim3(128), 0, partial, ns, C, scale, accumulate, out);
+  AOCR_CHECK(cdiv(C, 32) <= kSlabCounters && (int64_t)ns * C <= kPartialFloats - kSlabCounters, "col_reduce: scratch too small");
+  launch_pdl(ctx, col_reduce_kernel, dim3(grid), dim3(256), 0, z, z2, mean, var, R, C, rows_per, mode, partial, scale, accumulate, out);
   AOCR_CUDA(cudaGetLastError());
 }
 
@@ -557,14 +590,16 @@ void bn_stats(Ctx& ctx, const float* z, int64_t R, int C, float* mean, float* va
   int ns = nslabs_for(R, ctx.num_sms, C);
   if (ns > 128) ns = 128;
   const int64_t rows_per = (R + ns - 1) / ns;
-  launch_pdl(ctx, col_reduce_bn_fwd_kernel, dim3(cdiv(C, 32), ns), dim3(256), 0, z, (const float*)rmean, R, C, rows_per, partial);
-  AOCR_CUDA(cudaGetLastError());
-  launch_pdl(ctx, col_reduce_final2_kernel, dim3(cdiv(2 * C, 128)), dim3(128), 0, (const float*)partial, ns, C, sums, sums + C);
-  AOCR_CUDA(cudaGetLastError());
-  if (sync.world > 1) sync.fn(sync.user, sums, 2 * (int64_t)C);       // ONE all-reduce: [sum | sum of squares]
   const double Rg = (double)R * sync.grows;
-  launch_pdl(ctx, bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, (const float*)sums, C, (float)(1.0 / Rg),
-             Rg > 1 ? (float)(Rg / (Rg - 1)) : 1.f, mean, var, rmean, rvar);
+  const float invR = (float)(1.0 / Rg), unbias = Rg > 1 ? (float)(Rg / (Rg - 1)) : 1.f;
+  const int fin = sync.world > 1 ? 0 : 1;          // single device: one launch does sums, statistics and running update
+  AOCR_CHECK(cdiv(C, 32) <= kSlabCounters && (int64_t)2 * ns * C <= kPartialFloats - kSlabCounters, "bn_stats: scratch too small");
+  launch_pdl(ctx, col_reduce_bn_fwd_kernel, dim3(cdiv(C, 32), ns), dim3(256), 0, z, (const float*)rmean, R, C, rows_per, partial, sums,
+             fin, invR, unbias, mean, var, rmean, rvar);
+  AOCR_CUDA(cudaGetLastError());
+  if (fin) return;
+  sync.fn(sync.user, sums, 2 * (int64_t)C);        // ONE exchange: [sum | sum of squares]
+  launch_pdl(ctx, bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, (const float*)sums, C, invR, unbias, mean, var, rmean, rvar);
   AOCR_CUDA(cudaGetLastError());
 }
 
@@ -592,9 +627,7 @@ void bn_relu_bwd(Ctx& ctx, const float* da, const float* a, const float* z, cons
     if (ns > 128) ns = 128;                       // partial holds [2][ns][C]
     int64_t rows_per = (R + ns - 1) / ns;
     launch_pdl(ctx, col_reduce_bn_bwd_kernel, dim3(cdiv(C, 32), ns), dim3(256), 0, (const float*)dz, z, mean, var, R, C, rows_per,
-               partial);
-    AOCR_CUDA(cudaGetLastError());
-    launch_pdl(ctx, col_reduce_final2_kernel, dim3(cdiv(2 * C, 128)), dim3(128), 0, (const float*)partial, ns, C, dbeta, dgamma);
+               partial, dbeta, dgamma);
     AOCR_CUDA(cudaGetLastError());
   }
   if (sync.world > 1) {   // global sums of dy and dy*xhat (dgamma, dbeta are adjacent: one all-reduce when contiguous)
