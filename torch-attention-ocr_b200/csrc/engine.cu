@@ -227,6 +227,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (const char* e = getenv("AOCR_LANES")) lanes_on_ = atoi(e) != 0;
   for (int i = 0; i < 8; i++) AOCR_CUDA(cudaEventCreateWithFlags(&lane_ev_[i], cudaEventDisableTiming));
   if (const char* e = getenv("AOCR_EARLY_UPDATE")) early_update_on_ = atoi(e) != 0;
+  AOCR_CUDA(cudaEventCreateWithFlags(&conv_packs_ev_, cudaEventDisableTiming));
   if (lanes_on_) {
     AOCR_CUDA(cudaStreamCreateWithFlags(&upd_st_, cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) AOCR_CUDA(cudaEventCreateWithFlags(&upd_ev_[i], cudaEventDisableTiming));
@@ -286,6 +287,7 @@ Engine::~Engine() {
   for (int i = 1; i < 3; i++)
     if (lanes_on_ && lanes_[i].st) { cudaStreamSynchronize(lanes_[i].st); cudaStreamDestroy(lanes_[i].st); }
   for (int i = 0; i < 8; i++) if (lane_ev_[i]) cudaEventDestroy(lane_ev_[i]);
+  if (conv_packs_ev_) cudaEventDestroy(conv_packs_ev_);
   if (upd_st_) { cudaStreamSynchronize(upd_st_); cudaStreamDestroy(upd_st_); }
   for (int i = 0; i < 4; i++) if (upd_ev_[i]) cudaEventDestroy(upd_ev_[i]);
   for (void* p : allocs_) cudaFree(p);
@@ -527,6 +529,20 @@ bool Engine::prep_weights() {
   if (!weights_dirty_) return false;
   fork_to(1);
   use_lane(1);
+  static const bool prewarm = !(getenv("AOCR_PREWARM") && atoi(getenv("AOCR_PREWARM")) == 0);
+  const bool tcm = cfg.gemm_mode != 2 && prewarm;
+  if (tcm && lanes_on_) {
+    // the forward convolutions need their weight planes first (conv2 right after conv1): converted here, ahead of
+    // everything else on this lane, and lane 0 waits for exactly this point before its first convolution GEMM - not
+    // lazily in front of every GEMM on the critical path
+    for (int l = 1; l < 7; l++) {
+      const ConvSpec& c = kConv[l];
+      const int Kc = c.k * c.k * c.cin;
+      operand_pack(d_params + L.conv_w[l], c.cout, Kc, Kc, 1, 1);
+    }
+    AOCR_CUDA(cudaEventRecord(conv_packs_ev_, ctx_.st));
+    conv_packs_pending_ = true;
+  }
   for (int l = 1; l < 7; l++) {
     const ConvSpec& c = kConv[l];
     int64_t total = (int64_t)c.cout * c.k * c.k * c.cin;
@@ -547,6 +563,19 @@ bool Engine::prep_weights() {
   g.C = Ptab; g.ldc = 4 * Hd; g.bias_n = bsum1;
   gemm_simt(ctx_, g);
   if (cfg.gemm_mode != 2) build_decoder_packs();
+  if (tcm && lanes_on_) {
+    // every other parameter-derived operand of the step, so that no conversion launch sits in front of a GEMM on the
+    // critical path: encoder input projection and recurrent weights, W_c1 of the attention precompute, the flipped
+    // convolution weights of the data gradients (all joined before the encoder starts)
+    ensure_wicat_pack();
+    ensure_enc_packs();
+    operand_pack(d_params + L.wc, Hd, Hd, 2 * Hd, 1, 1);
+    for (int l = 1; l < 7; l++) {
+      const ConvSpec& c = kConv[l];
+      const int Kd = c.k * c.k * c.cout;
+      operand_pack(wt[l], c.cin, Kd, Kd, 1, 1);
+    }
+  }
   use_lane(0);
   weights_dirty_ = false;
   return true;      // lane 1 carries the work: join before the encoder
@@ -561,6 +590,10 @@ void Engine::cnn_forward(bool train) {
   const bool tc = cfg.gemm_mode != 2;
   conv1_fwd(ctx_, x0, d_params + L.conv_w[0], d_params + L.conv_b[0], act[1], pidx[1], B, W_, tc ? actp_[1].hi : nullptr,
             tc ? actp_[1].lo : nullptr);
+  if (conv_packs_pending_) {      // the weight planes of the forward convolutions are being written on lane 1 (prep_weights)
+    AOCR_CUDA(cudaStreamWaitEvent(ctx_.st, conv_packs_ev_, 0));
+    conv_packs_pending_ = false;
+  }
   for (int l = 1; l < 7; l++) {
     const ConvSpec& c = kConv[l];
     int Hin, Win, Hout, Wout;
@@ -687,6 +720,17 @@ void Engine::cnn_backward() {
   join_from(2);
 }
 
+// operand planes of [W_i fw ; W_i bw] (the encoder's time-batched input projection); refreshed once per weight update
+void Engine::ensure_wicat_pack() {
+  if (wicat_version_ == weights_version_) return;
+  for (int d = 0; d < 2; d++) {
+    Pack half = WiCatP;
+    half.hi += (int64_t)d * 4 * He * 512; half.lo += (int64_t)d * 4 * He * 512; half.rows = 4 * He;
+    split_to_pack(ctx_, d_params + L.enc_wi[d], 4 * He, 512, 512, 1, half);
+  }
+  wicat_version_ = weights_version_;
+}
+
 // ---------------------------------------------------------------------------------------------
 // encoder (model.lua:293-316).  Slot convention: fw slot t+1 = state after column t (slot 0 = zeros);
 // bw slot t = state after column t (slot S = zeros).
@@ -695,14 +739,7 @@ void Engine::encoder_forward() {
   if (cfg.gemm_mode != 2) {
     // time-batched input projection of BOTH directions as one GEMM: [W_i fw ; W_i bw] stacked on the UMMA M side,
     // the CNN output (operand planes written by the last batch-norm kernel) on the N side
-    if (wicat_version_ != weights_version_) {
-      for (int d = 0; d < 2; d++) {
-        Pack half = WiCatP;
-        half.hi += (int64_t)d * 4 * He * 512; half.lo += (int64_t)d * 4 * He * 512; half.rows = 4 * He;
-        split_to_pack(ctx_, d_params + L.enc_wi[d], 4 * He, 512, 512, 1, half);
-      }
-      wicat_version_ = weights_version_;
-    }
+    ensure_wicat_pack();
     prof_begin(0);
     TcGemm t;
     Pack sp = srcP_; sp.rows = (int64_t)S * B;

@@ -160,6 +160,10 @@ class Engine {
   bool persist_on_ = true;      // AOCR_PERSIST=0: per-kernel chains instead of the persistent executor
   void run_program(int kind, int nsteps, int variant);
   void encoder_forward_steps_tc();
+  void ensure_enc_packs();
+  void ensure_wicat_pack();
+  cudaEvent_t conv_packs_ev_ = nullptr;    // lane 1 has written the forward convolutions' weight planes (prep_weights)
+  bool conv_packs_pending_ = false;
   void encoder_backward_steps_tc();
   void conv_wgrad_tc(const float* dz, const float* x, int N, int H, int W, int Cin, int k, int pad, int Ho, int Wo,
                      int Cout, float* dW, const Pack* zpack = nullptr, const Pack* xpack = nullptr);

@@ -60,16 +60,20 @@ void Engine::encoder_dir_backward(int d) {
   }
 }
 
+// operand planes of the encoder's recurrent weights (forward, gate-interleaved forward, transposed for the backward)
+void Engine::ensure_enc_packs() {
+  if (enc_packs_version_ == weights_version_) return;
+  for (int d = 0; d < 2; d++) {
+    split_to_pack(ctx_, d_params + L.enc_wh[d], 4 * He, He, He, 1, Whp[d]);       // rows = gate units
+    if (He % 32 == 0) split_to_pack(ctx_, d_params + L.enc_wh[d], 4 * He, He, He, 1, WhpG[d], -1, He);   // gate-interleaved
+    split_to_pack(ctx_, d_params + L.enc_wh[d], He, 4 * He, 1, He, WhTp[d]);      // rows = input units (transpose)
+  }
+  enc_packs_version_ = weights_version_;
+}
+
 void Engine::encoder_forward_steps_tc() {
   const int B = b_, S = S_;
-  if (enc_packs_version_ != weights_version_) {
-    for (int d = 0; d < 2; d++) {
-      split_to_pack(ctx_, d_params + L.enc_wh[d], 4 * He, He, He, 1, Whp[d]);       // rows = gate units
-      if (He % 32 == 0) split_to_pack(ctx_, d_params + L.enc_wh[d], 4 * He, He, He, 1, WhpG[d], -1, He);   // gate-interleaved
-      split_to_pack(ctx_, d_params + L.enc_wh[d], He, 4 * He, 1, He, WhTp[d]);      // rows = input units (transpose)
-    }
-    enc_packs_version_ = weights_version_;
-  }
+  ensure_enc_packs();
   // zero initial states as operand planes: fw slot 0, bw slot S
   const size_t slot_bytes = (size_t)B * He * sizeof(__nv_bfloat16);
   fill_zero(ctx_, HencP[0].hi, slot_bytes); fill_zero(ctx_, HencP[0].lo, slot_bytes);
