@@ -11,7 +11,7 @@ data-parallel training step; the 32x800 / target 150 long-sequence stress, globa
   value : whole-job images/s with the batch already resident in HBM (CUDA events on the engine's stream)
   e2e   : the same step through the reference-facing call (Model.step) with HOST buffers: H2D of images+targets and
           D2H of the loss (train) or labels/scores (decode) inside the timed region
-  decode: the decode half of the metric (greedy pass + gold pass, max_decoder_l steps) with its own roofline block
+  decode: the decode half of the metric (greedy pass of max_decoder_l steps + gold pass) with its own roofline block
   roofline / cpu_baseline : see DESIGN.md §8
 
 `--impl reference` times the reference's CPU path instead: the float64 oracle restatement (the Torch7 stack cannot run
@@ -301,7 +301,7 @@ def main():
         if train_primary:
             sampler.stop_flag = True
             sampler.join(timeout=2)
-    # ---- greedy decode (greedy pass + gold pass, max_decoder_l steps each)
+    # ---- greedy decode (greedy pass of max_decoder_l steps + gold pass over the batch's target length)
     run_decode = c["flop_decode"] is not None and (world == 1 or not train_primary or args.config == 2)
     if run_decode:
         nd = steps if not train_primary else max(3, steps // 2)
@@ -404,7 +404,8 @@ def main():
         if run_decode:
             dec_blk = {"metric": "greedy_decode_images_per_sec", "value": total_imgs / (ms_dec / 1e3), "unit": "images/s",
                        "ms_per_batch": ms_dec,
-                       "workload": f"greedy decode + gold pass, batch {B}/GPU, {c['max_dec']} decoder steps each",
+                       "workload": f"greedy decode ({c['max_dec']} steps) + gold pass (the batch's target length, {c['T']} steps: "
+                                   f"the padded steps after it carry no loss / score), batch {B}/GPU",
                        "e2e": {"value": total_imgs / (ms_dec_e2e / 1e3), "unit": "images/s", "ms_per_batch": ms_dec_e2e,
                                "h2d_bytes_per_step": h2d_avg, "d2h_bytes_per_step": dec_d2h},
                        "roofline": roofline(prof_dec, ms_dec),

@@ -116,7 +116,8 @@ int aocr_trie_from_words(const char* words, int allow_digit_prefix, int32_t** ta
 void aocr_trie_free(int32_t* table);
 
 /* parity tap: log-probs of the last call. which=0: train (T,b,V); 1: greedy pass (L,b,V) after the
- * sticky-PAD edit; 2: gold pass (L,b,V). */
+ * sticky-PAD edit; 2: gold pass (L,b,V) - computed for the batch's own target length T; rows t >= T may be zero (their
+ * targets are padding: no loss, no score, src/model/criterion.lua:5, src/model/model.lua:614-618). */
 int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n);
 /* parity tap for intermediate tensors ("cnn_out" (S,b,512), "context" (b,S,1024), ...) */
 int aocr_debug_read(aocr_handle* h, const char* name, float* out, int64_t n);

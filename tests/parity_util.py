@@ -217,8 +217,12 @@ def decode_parity(cfg, batch, seed=910820, gemm_mode=0, tie_eps=1e-4):
         tie_rows += int(len(ties) > 0)
         compared += upto
         mism += int((g["labels"][b, :upto] != o["labels"][b, :upto]).sum())
+    # gold log-probs exist for the batch's own target length T: past it the padded targets carry neither loss nor score
+    # and the library does not run the gold rows (zeros there)
+    T = batch["targets"].shape[1]
+    assert not np.any(lp_gold[T:]) or rel_err(lp_gold[T:], o["gold_logp"][T:]) < TOL
     return {"token_mismatch": mism, "tokens_compared": compared, "tie_rows": tie_rows,
-            "gold_logp": rel_err(lp_gold, o["gold_logp"]),
+            "gold_logp": rel_err(lp_gold[:T], o["gold_logp"][:T]),
             "greedy_logp_t0": rel_err(lp_greedy[0], o["greedy_logp"][0]),
             "loss": abs(g["loss_sum"] - o["loss_sum"]) / abs(o["loss_sum"]),
             "gold_scores": rel_err(g["gold_scores"], o["gold_scores"]),

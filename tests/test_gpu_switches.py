@@ -17,6 +17,7 @@ CASES = [
     {"AOCR_FUSE": "0"},                                             # executor without the fused GEMM -> cell commands
     {"AOCR_CLUSTER": "1"},                                          # executor launched without thread-block clusters
     {"AOCR_DUAL": "0"},                                             # greedy and gold decode passes one after the other
+    {"AOCR_SHORT_GOLD": "0"},                                       # gold rows for all max_decoder_l steps
     {"AOCR_GRAPHS": "0", "AOCR_LANES": "0", "AOCR_PDL": "0"},       # plain serial launches
     {"AOCR_CG2": "0"},                                              # single-CTA GEMM kernel instead of the cta_group::2 pairs
     {"AOCR_CG2_BN": "128", "AOCR_BOX_POW2": "1"},                   # 256 x 128 pair tiles, power-of-two pixel boxes

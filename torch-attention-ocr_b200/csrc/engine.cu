@@ -227,6 +227,7 @@ Engine::Engine(const aocr_config& c, int device) : cfg(c), device_(device) {
   if (const char* e = getenv("AOCR_LANES")) lanes_on_ = atoi(e) != 0;
   for (int i = 0; i < 8; i++) AOCR_CUDA(cudaEventCreateWithFlags(&lane_ev_[i], cudaEventDisableTiming));
   if (const char* e = getenv("AOCR_EARLY_UPDATE")) early_update_on_ = atoi(e) != 0;
+  if (const char* e = getenv("AOCR_SHORT_GOLD")) short_gold_on_ = atoi(e) != 0;
   AOCR_CUDA(cudaEventCreateWithFlags(&conv_packs_ev_, cudaEventDisableTiming));
   if (lanes_on_) {
     AOCR_CUDA(cudaStreamCreateWithFlags(&upd_st_, cudaStreamNonBlocking));

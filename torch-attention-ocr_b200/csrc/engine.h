@@ -142,10 +142,13 @@ class Engine {
   void emit_to_dense(const PartIn& in, float* dst, int64_t ld, int B, int cols);
   void encoder_dir_forward(int d);
   void encoder_dir_backward(int d);
-  enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4, PK_DEC_GREEDY = 6, PK_DEC_DUAL = 7 };
+  enum ProgKind { PK_DEC_FWD = 0, PK_DEC_BWD = 1, PK_ENC_FWD0 = 2, PK_ENC_BWD0 = 4, PK_DEC_GREEDY = 6, PK_DEC_DUAL = 7, PK_DEC_DUAL_TAIL = 8 };
   struct StepTail { GenTc gen; GreedyTc sel; };
   const StepTail* tail_ = nullptr;   // set while recording a dual decode step: generator + selection ride on the attention command
   int dual_rows_ = 0;   // > 0 while the dual decode pass is recorded / initialised: the number of real batch rows
+  int slot_rows_ = 0;   // > 0: rows per time slot of the decoder state when it differs from the active rows b_ (the
+                        // greedy-only tail of the dual decode pass continues on the dual pass's 2B-row layout)
+  bool short_gold_on_ = true;   // AOCR_SHORT_GOLD=0: the gold rows ride along for all max_decoder_l steps
   int ctx_row0_ = 0;    // first context row of the state rows (beam search works on chunks of the batch)
   // beam search (engine_beam.cu)
   uint8_t* beam_tmp_ = nullptr; float* beam_logp_ = nullptr; double* beam_scores_[2] = {}; int32_t* beam_tok_[2] = {};

@@ -613,15 +613,27 @@ void Engine::decode_enqueue() {
     AOCR_CUDA(cudaMemcpy2DAsync(tokseq + B, (size_t)B2 * sizeof(int32_t), tgt_tb, (size_t)B * sizeof(int32_t),
                                 (size_t)B * sizeof(int32_t), (size_t)Ld, cudaMemcpyDeviceToDevice, ctx_.st));
     decoder_init(2);
+    // The gold rows are needed for the batch's own target length only: past it the padded targets carry no loss and no
+    // score (criterion.lua:5; model.lua:614-618), so nothing the step returns depends on those steps.  The dual pass
+    // runs T steps, then the greedy rows go on alone - half the rows per command - on the same state layout.
+    const int Tg = (short_gold_on_ && T + 4 <= Ld) ? T : Ld;
+    if (Tg < Ld) {
+      AOCR_CUDA(cudaMemsetAsync(rowloss + (int64_t)Tg * B, 0, (size_t)(Ld - Tg) * B * sizeof(float), ctx_.st));
+      AOCR_CUDA(cudaMemsetAsync(logp[2] + (int64_t)Tg * B * V, 0, (size_t)(Ld - Tg) * B * V * sizeof(float), ctx_.st));
+    }
     dual_rows_ = B;
     b_ = B2;
     try {
-      run_program(PK_DEC_DUAL, Ld, 0);
+      run_program(PK_DEC_DUAL, Tg, Tg < Ld ? Ld : 0);
+      if (Tg < Ld) {
+        b_ = B; dual_rows_ = 0; slot_rows_ = B2;
+        run_program(PK_DEC_DUAL_TAIL, Ld, Tg);
+      }
     } catch (...) {
-      b_ = B; dual_rows_ = 0;
+      b_ = B; dual_rows_ = 0; slot_rows_ = 0;
       throw;
     }
-    b_ = B; dual_rows_ = 0;
+    b_ = B; dual_rows_ = 0; slot_rows_ = 0;
     reduce_sum_double(ctx_, rowloss, (int64_t)Ld * B, d_loss);
     last_logp_rows_[1] = last_logp_rows_[2] = Ld * B;
     return;

@@ -135,20 +135,21 @@ void Engine::attention_precompute() {
 // Three GEMMs + three bodies per step: gates1 -> cell1 -> gates2 -> cell2 -> [q ; v] = [W_a ; W_c2] h2 -> attention+output.
 void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   const int B = b_, S = S_;
+  const int64_t RS = slot_rows_ > 0 ? slot_rows_ : b_;     // rows per time slot (>= the active rows B)
   const int nsteps = dec_steps_;
   const bool has_next = (t + 1 < nsteps);
-  float* x1 = X1 + (int64_t)t * B * K1;
-  float* x2 = X2 + (int64_t)t * B * 2 * Hd;
-  float* cat = CAT + (int64_t)t * B * 2 * Hd;
-  const int64_t r0 = (int64_t)t * B, r1 = (int64_t)(t + 1) * B;
+  float* x1 = X1 + (int64_t)t * RS * K1;
+  float* x2 = X2 + (int64_t)t * RS * 2 * Hd;
+  float* cat = CAT + (int64_t)t * RS * 2 * Hd;
+  const int64_t r0 = (int64_t)t * RS, r1 = (int64_t)(t + 1) * RS;
   // ---- layer 1
   const bool fuse = fused_rec() && dec_packs_inter_ && rec_->cluster == cluster_;
   CellFwdTc c1;
   c1.addrows = Ptab; c1.rowsel = tokens; c1.addld = 4 * Hd;
-  c1.c_prev = C1 + (int64_t)t * B * Hd; c1.c_new = C1 + (int64_t)(t + 1) * B * Hd;
-  c1.acts = ACT1 + (int64_t)t * B * 4 * Hd;
+  c1.c_prev = C1 + (int64_t)t * RS * Hd; c1.c_new = C1 + (int64_t)(t + 1) * RS * Hd;
+  c1.acts = ACT1 + (int64_t)t * RS * 4 * Hd;
   c1.h_out0 = x2; c1.ld0 = 2 * Hd;
-  c1.h_out1 = has_next ? x1 + (int64_t)B * K1 + h1off : nullptr; c1.ld1 = K1;
+  c1.h_out1 = has_next ? x1 + RS * K1 + h1off : nullptr; c1.ld1 = K1;
   c1.pk0 = pack_out(X2p, r0, 0);
   c1.pk1 = has_next ? pack_out(X1p, r1, h1off) : PackOut();
   c1.B = B; c1.H = Hd;
@@ -162,10 +163,10 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   // ---- layer 2
   CellFwdTc c2;
   c2.addrows = bsum2; c2.rowsel = nullptr; c2.addld = 0;
-  c2.c_prev = C2 + (int64_t)t * B * Hd; c2.c_new = C2 + (int64_t)(t + 1) * B * Hd;
-  c2.acts = ACT2 + (int64_t)t * B * 4 * Hd;
+  c2.c_prev = C2 + (int64_t)t * RS * Hd; c2.c_new = C2 + (int64_t)(t + 1) * RS * Hd;
+  c2.acts = ACT2 + (int64_t)t * RS * 4 * Hd;
   c2.h_out0 = cat + Hd; c2.ld0 = 2 * Hd;
-  c2.h_out1 = has_next ? x2 + (int64_t)B * 2 * Hd + Hd : nullptr; c2.ld1 = 2 * Hd;
+  c2.h_out1 = has_next ? x2 + RS * 2 * Hd + Hd : nullptr; c2.ld1 = 2 * Hd;
   c2.pk0 = pack_out(H2p, r0, 0);
   c2.pk1 = has_next ? pack_out(X2p, r1, Hd) : PackOut();
   c2.B = B; c2.H = Hd;
@@ -180,8 +181,8 @@ void Engine::decoder_step_tc(int t, const int32_t* tokens) {
   TcOut g3 = emit_gemm(W3p, 2 * Hd, H2p, r0, 0, Hd, dec_ws[2]);
   AttnOutTc ao;
   ao.ctx = ctx + (int64_t)ctx_row0_ * S * Hd; ao.ctxwc = CtxWc + (int64_t)ctx_row0_ * S * Hd; ao.g3 = part_in(g3, 2 * Hd);
-  ao.alpha = ALPHA + (int64_t)t * B * S; ao.q_out = Q + (int64_t)t * B * Hd; ao.a_out = A_all + (int64_t)t * B * Hd;
-  ao.x_next = (cfg.input_feed && has_next) ? x1 + (int64_t)B * K1 : nullptr; ao.ld_next = K1;
+  ao.alpha = ALPHA + (int64_t)t * RS * S; ao.q_out = Q + (int64_t)t * RS * Hd; ao.a_out = A_all + (int64_t)t * RS * Hd;
+  ao.x_next = (cfg.input_feed && has_next) ? x1 + RS * K1 : nullptr; ao.ld_next = K1;
   ao.pk_next = (cfg.input_feed && has_next) ? pack_out(X1p, r1, 0) : PackOut();
   ao.B = B; ao.S = S; ao.H = Hd; ao.ctx_rows = dual_rows_;
   if (rec_ && tail_) rec_->add3(P_ATTN_OUT_GEN, ao, tail_->gen, tail_->sel);

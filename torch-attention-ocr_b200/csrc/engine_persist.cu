@@ -52,9 +52,32 @@ void Engine::run_program(int kind, int nsteps, int variant) {
           dec_steps_ = save;
           break;
         }
-        case PK_DEC_DUAL: {     // b_ = 2B here: rows [0,B) greedy (argmax feedback), rows [B,2B) teacher forced
-          const int save = dec_steps_, Bh = dual_rows_;
+        case PK_DEC_DUAL_TAIL: {   // greedy rows only, steps [variant, nsteps), on the dual pass's layout (slot_rows_ = 2B)
+          const int save = dec_steps_;
+          const int64_t RS = slot_rows_;
           dec_steps_ = nsteps;
+          for (int t = variant; t < nsteps; t++) {
+            StepTail tl;
+            GenTc& gp = tl.gen;
+            gp.a = A_all + (int64_t)t * RS * Hd; gp.W = d_params + L.wo; gp.bias = d_params + L.bo;
+            gp.y = nullptr; gp.logp = logp[1] + (int64_t)t * b_ * V; gp.logp2 = nullptr;
+            gp.dz = nullptr; gp.rowloss = nullptr; gp.split = b_;          // every row is a greedy row
+            gp.R = b_; gp.H = Hd; gp.V = V; gp.inv_bn = 1.0f;
+            GreedyTc& gs = tl.sel;
+            gs.logp = gp.logp; gs.tok = tokseq + (int64_t)t * RS; gs.tok_out = tokseq + (int64_t)(t + 1) * RS;
+            gs.score = score; gs.labels = labels; gs.ldl = Tmax; gs.t = t; gs.B = b_; gs.V = V;
+            tail_ = &tl;
+            try { decoder_step_tc(t, tokseq + (int64_t)t * RS); } catch (...) { tail_ = nullptr; throw; }
+            tail_ = nullptr;
+          }
+          dec_steps_ = save;
+          break;
+        }
+        case PK_DEC_DUAL: {     // b_ = 2B here: rows [0,B) greedy (argmax feedback), rows [B,2B) teacher forced
+          // variant > 0: the recurrence goes on after this program (greedy-only tail) for `variant` steps in total, so the
+          // last step still writes the next step's inputs
+          const int save = dec_steps_, Bh = dual_rows_;
+          dec_steps_ = variant > 0 ? variant : nsteps;
           for (int t = 0; t < nsteps; t++) {
             StepTail tl;
             GenTc& gp = tl.gen;
