@@ -652,11 +652,19 @@ void Engine::decode_enqueue() {
       greedy_select(ctx_, lp, tok, score, labels, Ld, t, B, V);
     }
   }
-  // gold pass: teacher forced with the padded targets (model.lua:589-627)
+  // gold pass: teacher forced with the padded targets (model.lua:589-627); only the batch's own target length carries
+  // loss / score (see the dual branch above), so the pass stops there
   decoder_init();
-  if (persist_on_ && cfg.gemm_mode != 2) run_program(PK_DEC_FWD, Ld, 0);
-  else for (int t = 0; t < Ld; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
-  generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[2], nullptr, rowloss, (int64_t)Ld * B, Hd, V,
+  const int Tg = (short_gold_on_ && T + 4 <= Ld) ? T : Ld;
+  if (Tg < Ld) {
+    AOCR_CUDA(cudaMemsetAsync(rowloss + (int64_t)Tg * B, 0, (size_t)(Ld - Tg) * B * sizeof(float), ctx_.st));
+    AOCR_CUDA(cudaMemsetAsync(logp[2] + (int64_t)Tg * B * V, 0, (size_t)(Ld - Tg) * B * V * sizeof(float), ctx_.st));
+  }
+  dec_steps_ = Tg;
+  if (persist_on_ && cfg.gemm_mode != 2) run_program(PK_DEC_FWD, Tg, 0);
+  else for (int t = 0; t < Tg; t++) decoder_step(t, tgt_tb + (int64_t)t * B);
+  dec_steps_ = Ld;
+  generator_fwd(ctx_, A_all, d_params + L.wo, d_params + L.bo, tev_tb, logp[2], nullptr, rowloss, (int64_t)Tg * B, Hd, V,
                 1.0f);
   reduce_sum_double(ctx_, rowloss, (int64_t)Ld * B, d_loss);
   last_logp_rows_[1] = last_logp_rows_[2] = Ld * B;
