@@ -11,6 +11,13 @@ local A = require 'aocr_ffi'
 local ffi, lib = A.ffi, A.lib
 local model = torch.class('Model')
 
+-- src/train.lua:288 builds the dictionary with the global `loadDictionary` of src/utils/utils.lua (a nested tds.Hash);
+-- the library takes the same trie as a flat child table.  utils.lua is loaded here first (train.lua has put src/utils on
+-- package.path before it requires 'model'; the later `require 'utils'` of data_gen.lua is then a cache hit) and the
+-- global is replaced, so an unmodified train.lua hands model:step the flat table.
+require 'utils'
+loadDictionary = function(dictionary_path, allow_digit_prefix) return A.loadDictionary(dictionary_path, allow_digit_prefix) end
+
 local CONFIG_KEYS = {'dropout', 'encoder_num_hidden', 'encoder_num_layers', 'decoder_num_layers', 'target_vocab_size',
                      'target_embedding_size', 'max_encoder_l', 'max_decoder_l', 'input_feed', 'batch_size', 'prealloc'}
 local BN_CHANNELS = {256, 512, 512}
