@@ -20,6 +20,7 @@ CASES = [
     {"AOCR_SHORT_GOLD": "0"},                                       # gold rows for all max_decoder_l steps
     {"AOCR_GRAPHS": "0", "AOCR_LANES": "0", "AOCR_PDL": "0"},       # plain serial launches
     {"AOCR_CG2": "0"},                                              # single-CTA GEMM kernel instead of the cta_group::2 pairs
+    {"AOCR_PERSIST_GEMM": "0"},                                     # one tile per CTA pair, no tile loop / double-buffered accumulator
     {"AOCR_CG2_BN": "128", "AOCR_BOX_POW2": "1"},                   # 256 x 128 pair tiles, power-of-two pixel boxes
 ]
 

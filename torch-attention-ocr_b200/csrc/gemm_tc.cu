@@ -529,6 +529,282 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ persistent CTA-pair kernel
+// The pair kernel above with a tile loop: pair j of P resident pairs works through tiles j, j + P, j + 2P, ... of the
+// (M pair, N tile, split) list.  TMEM holds TWO accumulators (2 x BN columns): while the epilogue warps of both CTAs
+// drain accumulator a of tile i, the producer and the MMA warp are already on tile i + 1 in accumulator a ^ 1, so the
+// per-tile prologue (TMEM allocation, barrier set-up, cluster rendezvous), the TMA fill latency and the epilogue leave
+// the critical path.  Used when a launch has more tiles than the machine has pair slots (conv2 has 400 tiles of nine
+// k-blocks at batch 64; every convolution at batch 256).
+//   tmem_full[a]  : MMA -> epilogue (tcgen05.commit multicast into both CTAs)
+//   tmem_empty[a] : epilogue -> MMA, on the LEADER's barrier: 2 CTAs x 4 epilogue warps arrive (the peer's remotely)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                 const TcParams p, const int total_tiles, const int m_pairs, const int n_tiles) {
+  using C_ = Cfg2<BN>;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + C_::kStages * C_::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C_::kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * C_::kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * C_::kStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C_::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C_::kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+
+  // tile -> (split z, N tile, M pair); consecutive pairs take consecutive M pairs of one N tile (they share the B tile in L2)
+  auto decode = [&](int tile, int& z, int& n0, int& mt) {
+    const int per_z = m_pairs * n_tiles;
+    z = tile / per_z;
+    const int rem = tile - z * per_z;
+    const int nt = rem / m_pairs;
+    mt = 2 * (rem - nt * m_pairs) + (int)rank;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int planes = p.terms == 3 ? 2 : 1;
+      const uint32_t a_bytes = p.conv ? (uint32_t)p.a_rows * (BK * 2) : (uint32_t)A_PLANE_BYTES;
+      const uint32_t tx_pair = 2u * (uint32_t)planes * (a_bytes + C_::kBPlane);
+      uint32_t it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        int z, n0, mt;
+        decode(tile, z, n0, mt);
+        const int m0 = mt * BM, nb0 = n0 + (int)rank * C_::BNH;
+        int cn0 = 0, ch0 = 0, cw0 = 0;
+        if (p.conv) {
+          int id = mt;
+          const int wb = id % p.tiles_w; id /= p.tiles_w;
+          const int hb = id % p.tiles_h; id /= p.tiles_h;
+          cn0 = id * p.bn; ch0 = hb * p.bh; cw0 = wb * p.bw;
+        }
+        const int kb_begin = z * p.kb_per;
+        const int nkb = min(p.num_kb, kb_begin + p.kb_per) - kb_begin;
+        for (int i = 0; i < nkb; i++, it++) {
+          const int kb = kb_begin + i;
+          const int s = (int)(it % C_::kStages);
+          const uint32_t ph = (it / C_::kStages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = base + s * C_::kStageBytes;
+          const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+          const uint32_t fb = mapa_rank(full_bar(s), 0);
+          if (rank == 0) mbar_expect_tx(full_bar(s), tx_pair);
+          if (p.mn) {
+            int kc1 = kb * BK, kc2 = 0, kc3 = 0;
+            int bs1 = 0, bs2 = 0, bco = nb0;
+            if (p.mn == 2) {
+              int id = kb;
+              const int wb = id % p.tiles_w; id /= p.tiles_w;
+              const int hb = id % p.tiles_h; id /= p.tiles_h;
+              kc1 = wb * p.bw; kc2 = hb * p.bh; kc3 = id * p.bn;
+              const int tap = n0 / p.wg_cin;
+              bco = nb0 % p.wg_cin;
+              bs1 = tap % p.ksz - p.pad; bs2 = tap / p.ksz - p.pad;
+            }
+            for (int pl = 0; pl < planes; pl++) {
+              const CUtensorMap* ta = pl ? &tmAl : &tmAh;
+              const CUtensorMap* tb = pl ? &tmBl : &tmBh;
+#pragma unroll
+              for (int j = 0; j < BM / 64; j++) {
+                const uint32_t dst = sa + pl * A_PLANE_BYTES + j * 8192;
+                if (p.mn == 2) tma2_load_4d(dst, ta, fb, m0 + 64 * j, kc1, kc2, kc3);
+                else tma2_load_2d(dst, ta, fb, m0 + 64 * j, kc1);
+              }
+#pragma unroll
+              for (int j = 0; j < C_::BNH / 64; j++) {
+                const uint32_t dst = sb + pl * C_::kBPlane + j * 8192;
+                if (p.mn == 2) tma2_load_4d(dst, tb, fb, bco + 64 * j, kc1 + bs1, kc2 + bs2, kc3);
+                else tma2_load_2d(dst, tb, fb, nb0 + 64 * j, kc1);
+              }
+            }
+          } else {
+            if (p.conv) {
+              const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+              const int kh = tap / p.ksz, kw = tap % p.ksz;
+              tma2_load_4d(sa, &tmAh, fb, cb * BK, cw0 + kw - p.pad, ch0 + kh - p.pad, cn0);
+              if (planes == 2) tma2_load_4d(sa + A_PLANE_BYTES, &tmAl, fb, cb * BK, cw0 + kw - p.pad, ch0 + kh - p.pad, cn0);
+            } else {
+              tma2_load_2d(sa, &tmAh, fb, kb * BK, m0);
+              if (planes == 2) tma2_load_2d(sa + A_PLANE_BYTES, &tmAl, fb, kb * BK, m0);
+            }
+            tma2_load_2d(sb, &tmBh, fb, kb * BK, nb0);
+            if (planes == 2) tma2_load_2d(sb + C_::kBPlane, &tmBl, fb, kb * BK, nb0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the leader CTA only =====================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc2(BN, p.mn);
+      uint32_t it = 0, ti = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ti++) {
+        int z, n0, mt;
+        decode(tile, z, n0, mt);
+        const int kb_begin = z * p.kb_per;
+        const int nkb = min(p.num_kb, kb_begin + p.kb_per) - kb_begin;
+        const int acc = (int)(ti & 1u);
+        mbar_wait(tmem_empty_bar(acc), ((ti >> 1) & 1u) ^ 1u);      // both CTAs have drained this accumulator's previous tile
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        for (int i = 0; i < nkb; i++, it++) {
+          const int s = (int)(it % C_::kStages);
+          const uint32_t ph = (it / C_::kStages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + s * C_::kStageBytes;
+            const uint32_t sb = sa + 2 * A_PLANE_BYTES;
+            const uint64_t dah = p.mn ? make_desc_mnmajor_sw128(sa) : make_desc_kmajor_sw128(sa);
+            const uint64_t dal = p.mn ? make_desc_mnmajor_sw128(sa + A_PLANE_BYTES) : make_desc_kmajor_sw128(sa + A_PLANE_BYTES);
+            const uint64_t dbh = p.mn ? make_desc_mnmajor_sw128(sb) : make_desc_kmajor_sw128(sb);
+            const uint64_t dbl = p.mn ? make_desc_mnmajor_sw128(sb + C_::kBPlane) : make_desc_kmajor_sw128(sb + C_::kBPlane);
+            const uint64_t kstep = p.mn ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t adv = kstep * k;
+              tc2_mma(tacc, dah + adv, dbh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              if (p.terms == 3) {
+                tc2_mma(tacc, dah + adv, dbl + adv, idesc, 1u);
+                tc2_mma(tacc, dal + adv, dbh + adv, idesc, 1u);
+              }
+            }
+            tc2_commit(empty_bar(s));
+            if (i == nkb - 1) tc2_commit(tmem_full_bar(acc));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: this CTA's 128 rows of every tile of the pair =====================
+    const int q = warp & 3;
+    const uint32_t te_leader0 = mapa_rank(tmem_empty_bar(0), 0), te_leader1 = mapa_rank(tmem_empty_bar(1), 0);
+    uint32_t ti = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ti++) {
+      int z, n0, mt;
+      decode(tile, z, n0, mt);
+      const int m0 = mt * BM;
+      const int acc = (int)(ti & 1u);
+      mbar_wait(tmem_full_bar(acc), (ti >> 1) & 1u);
+      tc_fence_after();
+      const int ml = q * 32 + lane;
+      long long row = (long long)m0 + ml;
+      bool row_ok = row < p.M;
+      if (p.conv) {
+        int id = mt;
+        const int wb = id % p.tiles_w; id /= p.tiles_w;
+        const int hb = id % p.tiles_h; id /= p.tiles_h;
+        const int cn0 = id * p.bn, ch0 = hb * p.bh, cw0 = wb * p.bw;
+        const int wl = ml % p.bw, hl = (ml / p.bw) % p.bh, nl = ml / (p.bw * p.bh);
+        const int n = cn0 + nl, h = ch0 + hl, w = cw0 + wl;
+        row_ok = (nl < p.bn) && (n < p.Nimg) && (h < p.Ho) && (w < p.Wo);
+        row = ((long long)n * p.Ho + h) * p.Wo + w;
+      }
+      const float bm = (p.bias_m && row_ok) ? p.bias_m[row] : 0.f;
+      float* __restrict__ outp = p.splits > 1 ? p.ws + (long long)z * p.part_stride : p.C;
+      const bool plain = (p.splits > 1);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+        const int nb = n0 + c0;
+        if (nb >= p.N) continue;
+        float bias[16], old[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) { bias[j] = 0.f; old[j] = 0.f; }
+        if (!plain) {
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (nb + j < p.N)
+                old[j] = p.transpose_out ? p.C[(long long)(nb + j) * p.ldc + row] : p.C[row * p.ldc + nb + j];
+          }
+          if (p.bias_n) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+              if (nb + j < p.N) bias[j] = p.bias_n[nb + j];
+          }
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          v[j] = __uint_as_float(r[j]);
+          if (!plain) {
+            v[j] += bm + bias[j];
+            if (p.act == ACT_TANH) v[j] = tanhf(v[j]);
+            v[j] += old[j];
+          }
+        }
+        if (!p.transpose_out && nb + 16 <= p.N && (p.ldc & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(outp + row * p.ldc + nb) & 15) == 0) {
+          float4* dst = reinterpret_cast<float4*>(outp + row * p.ldc + nb);
+#pragma unroll
+          for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const int n = nb + j;
+            if (n < p.N) {
+              float* dst = p.transpose_out ? outp + (long long)n * p.ldc + row : outp + row * p.ldc + n;
+              *dst = v[j];
+            }
+          }
+        }
+      }
+      // this warp's quarter of the accumulator is drained: tell the leader's MMA warp (its own or the peer's barrier)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? te_leader1 : te_leader0);
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ fp32 -> (hi, lo) bf16 planes
 __device__ __forceinline__ void split2(float x, __nv_bfloat16& h, __nv_bfloat16& l) {
   h = __float2bfloat16_rn(x);
@@ -730,6 +1006,34 @@ void launch2(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUten
   ctx.launches++;
 }
 
+template <int BN>
+void launch2p(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+              const TcParams& p, dim3 grid, int npairs) {
+  {
+    static std::mutex mu;
+    static std::set<int> done;
+    int dev = 0;
+    AOCR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done.count(dev)) {
+      AOCR_CUDA(cudaFuncSetAttribute(tc_gemm2p_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::kSmemBytes));
+      done.insert(dev);
+    }
+  }
+  const int m_pairs = (int)grid.y / 2, n_tiles = (int)grid.x, total = m_pairs * n_tiles * (int)grid.z;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (unsigned)npairs, 1, 1);
+  cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = (size_t)Cfg2<BN>::kSmemBytes; cfg.stream = ctx.st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ctx.pdl ? 2 : 1;
+  AOCR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2p_kernel<BN>, ah, al, bh, bl, p, total, m_pairs, n_tiles));
+  ctx.launches++;
+}
+
 }  // namespace
 
 const CUtensorMap& tc_map_2d(const __nv_bfloat16* ptr, int64_t rows, int64_t kp, int box_rows) {
@@ -905,7 +1209,14 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     p.C = wsbase;        // splits == 1 writes the single partial straight into the workspace
   }
   grid.z = p.splits;
-  if (pair) {
+  // more tiles than resident pairs: the persistent variant (tile loop, double-buffered accumulator)
+  const int pair_slots = ctx.num_sms / 2;
+  const long long pair_tiles = pair ? (long long)(grid.y / 2) * grid.x * grid.z : 0;
+  const bool persistent = pair && pair_tiles > pair_slots && !(getenv("AOCR_PERSIST_GEMM") && atoi(getenv("AOCR_PERSIST_GEMM")) == 0);
+  if (persistent) {
+    if (BN == 256) launch2p<256>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
+    else launch2p<128>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
+  } else if (pair) {
     if (BN == 256) launch2<256>(ctx, *ah, *al, bh_, bl_, p, grid);
     else launch2<128>(ctx, *ah, *al, bh_, bl_, p, grid);
   } else
