@@ -1079,7 +1079,9 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   // CTA-pair kernel (256 x BN tiles, cta_group::2): whenever there are at least two M tiles and N fills a 128-wide tile
   const bool pair_on = !(getenv("AOCR_CG2") && atoi(getenv("AOCR_CG2")) == 0);      // read per call: an A/B switch
   const int pair_maxbn = getenv("AOCR_CG2_BN") ? atoi(getenv("AOCR_CG2_BN")) : 256;
-  bool pair = pair_on && BN == 128 && g.M > BM && !(g.dbg);
+  // (BN = 64 as well when the operands are K-major - conv2's data gradient has N = Cin = 64 and 400+ M tiles; the
+  // MN-major modes need whole 64-column boxes per CTA)
+  bool pair = pair_on && (BN == 128 || (BN == 64 && g.mn == 0 && g.N > 32 && g.M > 8 * BM)) && g.M > BM && !(g.dbg);
   if (pair && pair_maxbn >= 256 && g.N >= 256 && (g.mn != 2 || g.conv->C % 256 == 0)) BN = 256;
   const int BNB = pair ? BN / 2 : BN;               // B rows one CTA loads
   TcParams p{};
@@ -1215,10 +1217,12 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   const bool persistent = pair && pair_tiles > pair_slots && !(getenv("AOCR_PERSIST_GEMM") && atoi(getenv("AOCR_PERSIST_GEMM")) == 0);
   if (persistent) {
     if (BN == 256) launch2p<256>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
-    else launch2p<128>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
+    else if (BN == 128) launch2p<128>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
+    else launch2p<64>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
   } else if (pair) {
     if (BN == 256) launch2<256>(ctx, *ah, *al, bh_, bl_, p, grid);
-    else launch2<128>(ctx, *ah, *al, bh_, bl_, p, grid);
+    else if (BN == 128) launch2<128>(ctx, *ah, *al, bh_, bl_, p, grid);
+    else launch2<64>(ctx, *ah, *al, bh_, bl_, p, grid);
   } else
   switch (BN) {
     case 128: launch<128>(ctx, *ah, *al, bh_, bl_, p, grid); break;
