@@ -6,8 +6,8 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [(128, 128, 64), (256, 128, 128), (128, 64, 256), (200, 96, 200), (130, 17, 70), (512, 4, 2048),
           (1536, 2048, 512), (64, 300, 1152),
-          (9600, 512, 320), (5000, 700, 192),      # more tiles than CTA-pair slots: the persistent tile loop, ragged edges
-          (4096, 64, 1152), (20000, 48, 640)]      # N <= 64 on CTA pairs (32 B rows per CTA), persistent at the larger M
+          (40000, 512, 128), (38000, 200, 192),    # >= 4 tiles per CTA-pair slot: the persistent tile loop, ragged edges
+          (4096, 64, 1152), (80000, 48, 128)]      # N <= 64 on CTA pairs (32 B rows per CTA), persistent at the larger M
 
 
 def _check(M, N, K, ta, tb, mode, swap, tol):

@@ -69,7 +69,7 @@ print("executor: DRAM MB per train step", round(tot, 1), "-> per launch", round(
 lines = [l for l in open(f"gpurun_out/{tag}_gemm_metrics.csv") if l.startswith('"')]
 by = collections.OrderedDict()
 for r in csv.DictReader(lines):
-    km = re.search(r"(tc_gemm2?_kernel)<(?:\(int\))?(\d+)>", r["Kernel Name"])
+    km = re.search(r"(tc_gemm2?p?_kernel)<(?:\(int\))?(\d+)>", r["Kernel Name"])
     e = by.setdefault(r["ID"], {"kernel": f"{km.group(1)}<{km.group(2)}>" if km else r["Kernel Name"][:60], "grid": r.get("Grid Size")})
     e[r["Metric Name"]] = (r["Metric Value"], r["Metric Unit"])
 gl = []

@@ -1211,10 +1211,12 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
     p.C = wsbase;        // splits == 1 writes the single partial straight into the workspace
   }
   grid.z = p.splits;
-  // more tiles than resident pairs: the persistent variant (tile loop, double-buffered accumulator)
+  // many more tiles than resident pairs (>= 4 per pair): the persistent variant (tile loop, double-buffered accumulator).
+  // At batch 64 no launch of the step qualifies (conv2: 200 pair tiles on 74 slots gains 0.4 % of the step); at batch
+  // 256 the large convolutions do.
   const int pair_slots = ctx.num_sms / 2;
   const long long pair_tiles = pair ? (long long)(grid.y / 2) * grid.x * grid.z : 0;
-  const bool persistent = pair && pair_tiles > pair_slots && !(getenv("AOCR_PERSIST_GEMM") && atoi(getenv("AOCR_PERSIST_GEMM")) == 0);
+  const bool persistent = pair && pair_tiles >= 4 * pair_slots && !(getenv("AOCR_PERSIST_GEMM") && atoi(getenv("AOCR_PERSIST_GEMM")) == 0);
   if (persistent) {
     if (BN == 256) launch2p<256>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
     else if (BN == 128) launch2p<128>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
