@@ -534,8 +534,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 // (M pair, N tile, split) list.  TMEM holds TWO accumulators (2 x BN columns): while the epilogue warps of both CTAs
 // drain accumulator a of tile i, the producer and the MMA warp are already on tile i + 1 in accumulator a ^ 1, so the
 // per-tile prologue (TMEM allocation, barrier set-up, cluster rendezvous), the TMA fill latency and the epilogue leave
-// the critical path.  Used when a launch has more tiles than the machine has pair slots (conv2 has 400 tiles of nine
-// k-blocks at batch 64; every convolution at batch 256).
+// the critical path.  Used when a launch has at least four tiles per pair slot (the large convolutions at batch 256);
+// measured with the loop on every launch above 74 pair tiles: conv2 forward at batch 64 (200 pair tiles of nine k-blocks)
+// 54 -> 42 us, config 4 9.19 -> 8.85 ms per step.
 //   tmem_full[a]  : MMA -> epilogue (tcgen05.commit multicast into both CTAs)
 //   tmem_empty[a] : epilogue -> MMA, on the LEADER's barrier: 2 CTAs x 4 epilogue warps arrive (the peer's remotely)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
