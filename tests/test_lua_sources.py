@@ -63,3 +63,32 @@ def test_shim_calls_only_declared_entry_points():
             assert len(called) >= 10                      # the check sees the calls it is meant to check
         missing = called - declared
         assert not missing, f"{os.path.basename(path)} calls undeclared entry points {sorted(missing)}"
+
+
+def test_lua_checkpoint_layout_matches_python_layout():
+    """lua/aocr_ckpt.lua flattens named tensors in M.ORDER; aocr/layout.py param_specs is the order the library and the
+    Python checkpoint reader use: the two lists must be the same, group by group"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "torch-attention-ocr_b200"))
+    from aocr.layout import GROUPS, param_specs
+    src = open(os.path.join(LUA_DIR, "aocr_ckpt.lua")).read()
+    lint(src)
+    names = lambda body: re.findall(r"'([^']+)'", body)
+    enc = names(re.search(r"local ENC = \{([^}]*)\}", src).group(1))
+    order_body = src.split("M.ORDER = {", 1)[1]
+    lua = {"enc_fw": enc, "enc_bw": enc}
+    for g in ("cnn", "decoder", "proj"):
+        lua[g] = names(re.search(g + r" = \{([^}]*)\}", order_body).group(1))
+    assert re.search(r"enc_fw = ENC, enc_bw = ENC", order_body)
+    spec = param_specs({})
+    for g in GROUPS:
+        assert lua[g] == [n for n, _ in spec[g]], g
+    assert names(re.search(r"M.GROUPS = \{([^}]*)\}", src).group(1)) == list(GROUPS)
+
+
+def test_model_lua_loads_every_checkpoint_kind():
+    src = open(os.path.join(LUA_DIR, "model.lua")).read()
+    assert "K.normalise(torch.load(model_path))" in src
+    ck = open(os.path.join(LUA_DIR, "aocr_ckpt.lua")).read()
+    for kind in ("'reference'", "'named'", "'flat'"):
+        assert kind in ck

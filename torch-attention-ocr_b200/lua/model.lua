@@ -8,6 +8,7 @@
      Mirrors aocr/model.py line for line (that twin is the one exercised by the test-suite; LuaJIT/Torch7 are absent
      from the build image). ]]
 local A = require 'aocr_ffi'
+local K = require 'aocr_ckpt'
 local ffi, lib = A.ffi, A.lib
 local model = torch.class('Model')
 
@@ -77,9 +78,12 @@ function model:create(config)   -- model.lua:83-112
   A.check(self.h, lib.aocr_init_params(self.h, (config.seed or 910820)))
 end
 
--- Checkpoint = a Torch7-serialised table {params = {5 x FloatTensor}, bn = {3 x {mean, var}}, config, global_step,
--- optim_state}: written and read by torch.save / torch.load themselves (model.lua:45-80,720-725 keep whole nn modules;
--- the 5 flat vectors are what those modules' getParameters() return, model.lua:161-168).
+-- Checkpoints.  model:save writes a Torch7-serialised table {params = {5 x FloatTensor}, bn = {3 x {mean, var}}, config,
+-- global_step, optim_state}: the 5 flat vectors are what the reference's modules' getParameters() return
+-- (model.lua:161-168).  model:load reads that, the named-tensor table of aocr/checkpoint.py, AND the reference's own
+-- checkpoint {{cnn_model, encoder_fw, encoder_bw, decoder, output_projector}, config, global_step, optim_state}
+-- (model.lua:45-80,720-725) — `-load_model` keeps working on a model directory trained by the reference.  To hand
+-- weights back to the reference: lua/t7_convert.lua import.
 function model:save(model_path)   -- model.lua:720-725
   local ck = { params = {}, bn = {}, config = self.config, global_step = self.global_step, optim_state = self.optim_state }
   for i = 1, 5 do ck.params[i] = self.params[i]:float() end
@@ -94,7 +98,10 @@ end
 function model:load(model_path, config)   -- model.lua:45-80
   config = config or {}
   assert(paths.filep(model_path), string.format('Model %s does not exist!', model_path))
-  local ck = torch.load(model_path)
+  -- classes a reference checkpoint deserialises into (train.lua:4-7 has loaded nn / nngraph / cudnn; nn.LinearNoBias
+  -- lives in src/utils/model_utils.lua, CUDA tensors need cutorch)
+  for _, name in ipairs({'nn', 'nngraph', 'cutorch', 'cunn', 'cudnn', 'model_utils'}) do pcall(require, name) end
+  local ck = K.normalise(torch.load(model_path))
   for _, k in ipairs(CONFIG_KEYS) do self[k] = ck.config[k] end
   self.max_encoder_l = config.max_encoder_l or ck.config.max_encoder_l        -- model.lua:71-74
   self.max_decoder_l = config.max_decoder_l or ck.config.max_decoder_l
