@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from aocr.data import DataGen, scale_bilinear, rgb2y, str2numlist, numlist2str
+from aocr.data import DataGen, load_image, scale_bilinear, rgb2y, str2numlist, numlist2str
 
 
 def _write_images(tmp_path, specs):
@@ -35,6 +35,35 @@ def test_scale_bilinear_follows_torch_image_semantics():
     assert scale_bilinear(x, 4, 3) is not x and np.array_equal(scale_bilinear(x, 4, 3), x)
     y = rgb2y(np.stack([np.full((2, 2), 1.0), np.zeros((2, 2)), np.zeros((2, 2))]).astype(np.float32))
     assert y.shape == (1, 2, 2) and abs(y[0, 0, 0] - 0.299) < 1e-6
+
+
+def test_image_decoders_agree(tmp_path):
+    """the same picture as PNG (through PIL), .npy, binary and ASCII PGM / PPM decodes to the same (C,H,W) array in
+    [0,1] (image.load's contract, data_gen.lua:65); an undecodable file raises (the caller's pcall skips it)"""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    gray = rng.integers(0, 256, size=(7, 11), dtype=np.uint8)
+    rgb = rng.integers(0, 256, size=(7, 11, 3), dtype=np.uint8)
+    Image.fromarray(gray, mode="L").save(tmp_path / "g.png")
+    Image.fromarray(rgb, mode="RGB").save(tmp_path / "c.png")
+    np.save(tmp_path / "g.npy", gray)
+    np.save(tmp_path / "c.npy", rgb)
+    np.save(tmp_path / "c_chw.npy", (rgb.transpose(2, 0, 1) / 255.0).astype(np.float32))
+    (tmp_path / "g.pgm").write_bytes(b"P5\n# a comment\n11 7\n255\n" + gray.tobytes())
+    (tmp_path / "c.ppm").write_bytes(b"P6 11 7 255\n" + rgb.tobytes())
+    (tmp_path / "g_ascii.pgm").write_text("P2\n11 7\n255\n" + " ".join(str(v) for v in gray.ravel()) + "\n")
+    (tmp_path / "g16.pgm").write_bytes(b"P5 11 7 65535\n" + (gray.astype(">u2") * 257).tobytes())
+    g_ref, c_ref = load_image(str(tmp_path / "g.png")), load_image(str(tmp_path / "c.png"))
+    assert g_ref.shape == (1, 7, 11) and c_ref.shape == (3, 7, 11) and g_ref.dtype == np.float32
+    for name in ("g.npy", "g.pgm", "g_ascii.pgm", "g16.pgm"):
+        np.testing.assert_allclose(load_image(str(tmp_path / name)), g_ref, atol=1e-6, err_msg=name)
+    for name in ("c.npy", "c_chw.npy", "c.ppm"):
+        np.testing.assert_allclose(load_image(str(tmp_path / name)), c_ref, atol=1e-6, err_msg=name)
+    (tmp_path / "bad.pgm").write_bytes(b"P5 11 7 255\n" + gray.tobytes()[:10])
+    (tmp_path / "bad.png").write_bytes(b"not an image")
+    for name in ("bad.pgm", "bad.png", "absent.npy"):
+        with pytest.raises(Exception):
+            load_image(str(tmp_path / name))
 
 
 def test_datagen_batches_follow_the_reference_format(tmp_path):

@@ -142,9 +142,66 @@ def scale_bilinear(img, width, height):
     return np.ascontiguousarray(_scale_linear_1d(tmp.transpose(0, 2, 1), height).transpose(0, 2, 1))
 
 
+def _read_pnm(path):
+    """binary / ASCII PGM and PPM (P2, P3, P5, P6; 8 or 16 bit): (C,H,W) float in [0,1]"""
+    with open(path, "rb") as f:
+        data = f.read()
+    pos, fields = 0, []
+    while len(fields) < 4:                       # magic, width, height, maxval — whitespace separated, '#' comments
+        while pos < len(data) and data[pos:pos + 1].isspace():
+            pos += 1
+        if data[pos:pos + 1] == b"#":
+            while pos < len(data) and data[pos:pos + 1] != b"\n":
+                pos += 1
+            continue
+        start = pos
+        while pos < len(data) and not data[pos:pos + 1].isspace():
+            pos += 1
+        if start == pos:
+            raise ValueError("truncated PNM header: %s" % path)
+        fields.append(data[start:pos])
+    magic, w, h, maxval = fields[0], int(fields[1]), int(fields[2]), int(fields[3])
+    if magic not in (b"P2", b"P3", b"P5", b"P6") or not (0 < maxval < 65536):
+        raise ValueError("unsupported PNM file: %s" % path)
+    c = 3 if magic in (b"P3", b"P6") else 1
+    if magic in (b"P5", b"P6"):
+        pos += 1                                 # exactly one whitespace byte after maxval
+        dt = np.dtype(">u2") if maxval > 255 else np.dtype("u1")
+        a = np.frombuffer(data, dtype=dt, count=w * h * c, offset=pos)
+    else:
+        a = np.array(data[pos:].split()[:w * h * c], dtype=np.int64)
+    if a.size != w * h * c:
+        raise ValueError("truncated PNM file: %s" % path)
+    a = a.reshape(h, w, c).astype(np.float32) / np.float32(maxval)
+    return np.ascontiguousarray(a.transpose(2, 0, 1))
+
+
+def _from_array(a):
+    """a decoded array -> (C,H,W) float in [0,1]: (H,W), (H,W,3|4) or (1|3,H,W); integer types are scaled by their range"""
+    a = np.asarray(a)
+    scale = np.float32(1.0 / np.iinfo(a.dtype).max) if np.issubdtype(a.dtype, np.integer) else np.float32(1.0)
+    a = a.astype(np.float32) * scale
+    if a.ndim == 2:
+        return a[None]
+    if a.ndim == 3 and a.shape[0] in (1, 3) and a.shape[2] not in (1, 3, 4):
+        return np.ascontiguousarray(a)
+    if a.ndim == 3 and a.shape[2] in (1, 3, 4):
+        return np.ascontiguousarray(a[:, :, :3].transpose(2, 0, 1)) if a.shape[2] >= 3 else np.ascontiguousarray(a.transpose(2, 0, 1))
+    raise ValueError("cannot interpret an array of shape %s as an image" % (a.shape,))
+
+
 def load_image(path):
-    """image.load: (C,H,W) float in [0,1]; raises when the file cannot be decoded (data_gen.lua:65 uses pcall)"""
-    from PIL import Image
+    """image.load: (C,H,W) float in [0,1]; raises when the file cannot be decoded (data_gen.lua:65 uses pcall).
+    `.npy` arrays and PGM / PPM files are read here; every other format (JPEG, PNG, ...) goes through PIL."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npy":
+        return _from_array(np.load(path, allow_pickle=False))
+    if ext in (".pgm", ".ppm", ".pnm"):
+        return _read_pnm(path)
+    try:
+        from PIL import Image
+    except ImportError as e:
+        raise RuntimeError("decoding %s needs PIL (only .npy / .pgm / .ppm are read without it)" % path) from e
     with Image.open(path) as im:
         if im.mode not in ("L", "RGB"):
             im = im.convert("RGB")
