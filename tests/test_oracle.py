@@ -44,7 +44,7 @@ def autograd_reference(orc, batch):
         for v in orc.P[g].values():
             v.requires_grad_(False)
             v.grad = None
-    return float(loss) * B, grads
+    return float(loss.detach()) * B, grads
 
 
 @pytest.mark.parametrize("input_feed", [True, False])
