@@ -63,19 +63,20 @@ def read_results(path):
 
 
 def load_freq(path):
+    """word -> count.  A `.pkl` / `.pickle` file is unpickled (the reference's freq.pkl; only open files you trust —
+    unpickling runs code), anything else is read as `word count` lines."""
     if not path:
         return None
-    try:
+    if path.endswith((".pkl", ".pickle")):
         with open(path, "rb") as f:
             return dict(pickle.load(f, encoding="latin-1"))
-    except Exception:
-        freq = {}
-        with open(path) as f:
-            for line in f:
-                parts = line.split()
-                if len(parts) >= 2:
-                    freq[parts[0]] = int(parts[1])
-        return freq
+    freq = {}
+    with open(path) as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) >= 2:
+                freq[parts[0]] = int(parts[1])
+    return freq
 
 
 def image_file_name(rel_path):
