@@ -122,6 +122,15 @@ int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n);
 /* parity tap for intermediate tensors ("cnn_out" (S,b,512), "context" (b,S,1024), ...) */
 int aocr_debug_read(aocr_handle* h, const char* name, float* out, int64_t n);
 
+/* ---- page-locked host buffers for the batch tuple ---- */
+/* The data layer builds every batch into fresh host tensors (`torch.Tensor(batch_size, 1, imgH, imgW)`,
+ * src/data/data_gen.lua:97,105-109).  Allocated here instead, they are page-locked: the copies aocr_train_step /
+ * aocr_decode_* / aocr_stage_batch issue from them are asynchronous DMA transfers, so a prefetching data layer overlaps
+ * input transfer with the previous step.  Needs a CUDA device (AOCR_ERR_CUDA otherwise, message through
+ * aocr_last_global_error); any host pointer remains valid input to every entry point. */
+int aocr_host_alloc(void** ptr, int64_t bytes);
+void aocr_host_free(void* ptr);
+
 /* ---- device-resident entry points (bench `value`, data-parallel plumbing) ---- */
 /* stage a batch in HBM once; *_staged calls then run with no host<->device copies of inputs */
 int aocr_stage_batch(aocr_handle* h, const float* images, int b, int W,

@@ -56,6 +56,8 @@ _SYMBOLS = {
     "aocr_trie_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]),
     "aocr_trie_from_words": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]),
     "aocr_trie_free": (None, [C.POINTER(C.c_int32)]),
+    "aocr_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "aocr_host_free": (None, [C.c_void_p]),
     "aocr_get_logprobs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "aocr_debug_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "aocr_stage_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
@@ -140,6 +142,94 @@ class Lib:
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class _PinnedBlock:
+    """owner of one aocr_host_alloc block.  Arrays are made over `buf`; `buf` holds a reference to its owner, so the
+    block is returned (aocr_host_free) only when the last array over it is gone."""
+
+    def __init__(self, nbytes):
+        import weakref
+        self.lib = Lib.get()
+        p = C.c_void_p()
+        rc = self.lib.dll.aocr_host_alloc(C.byref(p), int(nbytes))
+        if rc != 0:
+            raise AocrError(rc, self.lib.dll.aocr_last_global_error().decode())
+        self.ptr, self.nbytes = p.value, int(nbytes)
+        self.buf = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+        self.buf._owner = self
+        _PINNED_OWNERS[self.ptr] = weakref.ref(self, lambda _r, k=self.ptr: _PINNED_OWNERS.pop(k, None))
+
+    def array(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64))
+        assert n * dtype.itemsize <= self.nbytes
+        return np.frombuffer(self.buf, dtype=dtype, count=n).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.dll.aocr_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+_PINNED_OWNERS = {}     # address of a live block -> weak reference to its owner (introspection: is_pinned)
+
+
+def _nbytes(shape, dtype):
+    return max(int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize, 1)
+
+
+def host_empty(shape, dtype=np.float32):
+    """np.empty in page-locked host memory (aocr_host_alloc): what the data layer allocates batch tensors from so that
+    the library's host-to-device copies are asynchronous.  Raises AocrError when no CUDA device is present."""
+    return _PinnedBlock(_nbytes(shape, dtype)).array(shape, dtype)
+
+
+def is_pinned(a):
+    """True when the array's memory lies inside a live aocr_host_alloc block"""
+    addr = a.ctypes.data
+    for ptr, ref in list(_PINNED_OWNERS.items()):
+        blk = ref()
+        if blk is not None and blk.ptr is not None and ptr <= addr < ptr + blk.nbytes:
+            return True
+    return False
+
+
+class PinnedRing:
+    """Allocator of batch tensors for the data layer (`DataGen(..., alloc=PinnedRing(depth))`): `depth` generations of
+    page-locked blocks, recycled round-robin — page-locking is expensive (and releasing it synchronises the device), so
+    blocks are reused instead of allocated per batch.  `next_batch()` opens the next generation; each call then hands
+    out that generation's next block (grown when a batch needs more).  A batch's arrays are overwritten `depth` batches
+    later: depth must exceed the number of batches alive at once (prefetch queue + the one being built + the one the
+    step reads: prefetch + 2)."""
+
+    def __init__(self, depth=6):
+        assert depth >= 2
+        self.depth = depth
+        self.generations = [[] for _ in range(depth)]
+        self.cur, self.k = -1, 0
+        self.allocations = 0          # page-locking calls made so far (tests: stays flat once warm)
+
+    def next_batch(self):
+        self.cur = (self.cur + 1) % self.depth
+        self.k = 0
+
+    def __call__(self, shape, dtype=np.float32):
+        if self.cur < 0:
+            self.next_batch()
+        gen, i = self.generations[self.cur], self.k
+        self.k += 1
+        need = _nbytes(shape, dtype)
+        if i >= len(gen):
+            gen.append(None)
+        if gen[i] is None or gen[i].nbytes < need:
+            grown = need if gen[i] is None else max(need, gen[i].nbytes * 3 // 2)
+            gen[i] = _PinnedBlock(grown)        # arrays still alive over the old block keep it until they die
+            self.allocations += 1
+        return gen[i].array(shape, dtype)
 
 
 class Trie:

@@ -215,10 +215,13 @@ class DataGen:
     `fixed_width`: the reference overrides every computed width with 100 (data_gen.lua:78), which
     makes its width bucketing dormant; fixed_width=100 reproduces that, fixed_width=None (default here) keeps the width
     ceil(aspect_ratio * 32) the line above computes, i.e. true bucketing.  `prefetch` > 0 decodes ahead on a worker
-    thread so the device step does not wait for image I/O."""
+    thread so the device step does not wait for image I/O; `alloc` (e.g. `capi.PinnedRing`) supplies the batch tensors,
+    page-locked so the library's input copies are asynchronous transfers."""
 
-    def __init__(self, data_base_dir, data_path, max_aspect_ratio, fixed_width=None, log=print, seed=None, prefetch=0):
+    def __init__(self, data_base_dir, data_path, max_aspect_ratio, fixed_width=None, log=print, seed=None, prefetch=0,
+                 alloc=None):
         self.imgH = 32
+        self.alloc = alloc           # (shape, dtype) -> ndarray for the batch tensors; capi.PinnedRing: page-locked memory
         self.data_base_dir, self.data_path = data_base_dir, data_path
         self.max_aspect_ratio, self.min_aspect_ratio = max_aspect_ratio, 0.5
         self.fixed_width = fixed_width
@@ -267,12 +270,17 @@ class DataGen:
 
     def _batch(self, items, imgW):                                                # data_gen.lua:97-120 / 132-153
         b = len(items)
-        images = np.empty((b, 1, self.imgH, imgW), np.float32)
+        alloc = self.alloc or np.empty
+        if hasattr(alloc, "next_batch"):
+            alloc.next_batch()
+        images = alloc((b, 1, self.imgH, imgW), np.float32)
         for i, it in enumerate(items):
             images[i] = it[0]
         T = max(len(it[1]) for it in items) - 1
-        targets = np.ones((b, T), np.int32)
-        targets_eval = np.ones((b, T), np.int32)
+        targets = alloc((b, T), np.int32)
+        targets_eval = alloc((b, T), np.int32)
+        targets[...] = 1
+        targets_eval[...] = 1
         nnz = 0
         for i, it in enumerate(items):
             l = it[1]

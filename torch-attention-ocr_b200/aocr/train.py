@@ -213,7 +213,10 @@ def main(argv=None):
     fixed = opt.fixed_width if opt.fixed_width > 0 else None
     logging.info("Data base dir %s" % opt.data_base_dir)
     logging.info("Load training data from %s" % opt.data_path)
-    train_data = DataGen(opt.data_base_dir, opt.data_path, 10.0, fixed_width=fixed, log=logging.info, seed=opt.seed, prefetch=2)
+    from .capi import PinnedRing
+    prefetch = 2
+    train_data = DataGen(opt.data_base_dir, opt.data_path, 10.0, fixed_width=fixed, log=logging.info, seed=opt.seed,
+                         prefetch=prefetch, alloc=PinnedRing(prefetch + 4))     # page-locked batches, built ahead
     logging.info("Training data loaded from %s" % opt.data_path)
     val_data = None
     if opt.phase == "train":

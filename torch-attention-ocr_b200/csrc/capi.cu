@@ -194,6 +194,21 @@ int aocr_set_allreduce(aocr_handle* h, aocr_allreduce_fn fn, void* user) {
   h->eng->ar_fn = fn; h->eng->ar_user = user;
   AOCR_API_END(h)
 }
+int aocr_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) { g_create_error = "aocr_host_alloc: null pointer or non-positive size"; return AOCR_ERR_INVALID; }
+  *ptr = nullptr;
+  cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *ptr = nullptr;
+    g_create_error = std::string("aocr_host_alloc: ") + cudaGetErrorString(e);
+    return AOCR_ERR_CUDA;
+  }
+  return AOCR_OK;
+}
+void aocr_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
 int aocr_dp_unique_id(void* out128) {
   try {
     if (!out128) return AOCR_ERR_INVALID;

@@ -38,6 +38,8 @@ int aocr_decode_beam(aocr_handle* h, const float* images, int b, int W, const in
 int aocr_trie_load(const char* path, int allow_digit_prefix, int32_t** table, int32_t* num_nodes);
 int aocr_trie_from_words(const char* words, int allow_digit_prefix, int32_t** table, int32_t* num_nodes);
 void aocr_trie_free(int32_t* table);
+int aocr_host_alloc(void** ptr, int64_t bytes);
+void aocr_host_free(void* ptr);
 int aocr_get_logprobs(aocr_handle* h, int which, float* out, int64_t n);
 int aocr_debug_read(aocr_handle* h, const char* name, float* out, int64_t n);
 /* device-resident entry points and the data-parallel plumbing (no reference counterpart: train.lua is single-device) */
