@@ -1217,7 +1217,10 @@ TcOut gemm_tc(Ctx& ctx, const TcGemm& g) {
   // 256 the large convolutions do.
   const int pair_slots = ctx.num_sms / 2;
   const long long pair_tiles = pair ? (long long)(grid.y / 2) * grid.x * grid.z : 0;
-  const bool persistent = pair && pair_tiles >= 4 * pair_slots && !(getenv("AOCR_PERSIST_GEMM") && atoi(getenv("AOCR_PERSIST_GEMM")) == 0);
+  // AOCR_PERSIST_GEMM = minimum number of tiles per pair slot (default 4; 0 = never; 2 = the setting the batch-64
+  // measurement above was taken with, also the stress setting: it puts conv2 of every batch-64 step on the tile loop)
+  const int per_slot = getenv("AOCR_PERSIST_GEMM") ? atoi(getenv("AOCR_PERSIST_GEMM")) : 4;
+  const bool persistent = pair && per_slot > 0 && pair_tiles >= (long long)(per_slot == 1 ? 4 : per_slot) * pair_slots;
   if (persistent) {
     if (BN == 256) launch2p<256>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
     else if (BN == 128) launch2p<128>(ctx, *ah, *al, bh_, bl_, p, grid, pair_slots);
