@@ -549,7 +549,10 @@ tc_gemm2p_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                  const TcParams p, const int total_tiles, const int m_pairs, const int n_tiles) {
   using C_ = Cfg2<BN>;
-  pdl_launch_dependents();
+  // No programmatic dependent launch around this kernel (neither the early trigger here nor the launch attribute in
+  // launch2p): it holds every SM for its whole duration, and with PDL a soak of the step hung at about one in 2-3
+  // thousand launches (with AOCR_PDL=0 the same soak ran clean).  The kernel after it starts when this
+  // one has completed; the overlap given up is one prologue per launch.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1030,7 +1033,7 @@ void launch2p(Ctx& ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUte
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = ctx.pdl ? 2 : 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;          // cluster dimension only: no PDL for the persistent kernel (see the kernel)
   AOCR_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2p_kernel<BN>, ah, al, bh, bl, p, total, m_pairs, n_tiles));
   ctx.launches++;
 }
